@@ -1,0 +1,269 @@
+/*
+ * srfdet_b200.h -- C ABI of libsrfdet_b200.so: the sm_100a kernels behind the
+ * mmdet3d_plugin drop-in modules (srfdet_b200/plugin/*.py).
+ *
+ * The reference (gopi-erabati/SRFDet3D) has no FFI of its own: its boundary to native
+ * code is the set of third-party Python ops it calls.  Each entry point below names the
+ * reference call site (file:line under /root/reference) and the third-party op it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; buffers are
+ *    caller-allocated (torch tensors); the library never allocates device memory.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host
+ *    synchronisation happens inside any call.
+ *  - counts produced on the device stay on the device (int32_t* d_...); kernels that
+ *    consume them are launched over a host-known capacity and read the count themselves,
+ *    so a whole frame can be enqueued (or graph-captured) without a host round trip.
+ *  - return 0 on success; otherwise a negative code and srf_last_error() (thread-local
+ *    string).  No exceptions cross the boundary.
+ *  - coordinates are int32 (b, z, y, x) as in mmcv / spconv.
+ */
+#ifndef SRFDET_B200_H_
+#define SRFDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRF_OK 0
+#define SRF_ERR_ARG (-1)
+#define SRF_ERR_CUDA (-2)
+#define SRF_ERR_UNSUPPORTED (-3)
+
+#define SRF_F32 0
+#define SRF_BF16 1
+
+int srf_version(void);
+const char* srf_last_error(void);
+/* number of SMs of the current device (grid sizing of the persistent kernels) */
+int srf_sm_count(void);
+/* kernels launched by this library since load (host counter; bench.py's gpu_launches) */
+unsigned long long srf_launch_count(void);
+
+/* ---------------------------------------------------------------------------------- *
+ * Voxel geometry.  Replaces mmcv/ops/voxelize.py grid computation
+ * (call site: mmdet3d_plugin/models/detectors/srfdet.py:58).
+ * ---------------------------------------------------------------------------------- */
+typedef struct srf_geom {
+  float vs[3];     /* voxel size x,y,z */
+  float lo[3];     /* range min x,y,z */
+  float hi[3];     /* range max x,y,z */
+  int32_t grid[3]; /* cells x,y,z = round((hi-lo)/vs) in fp32 */
+} srf_geom;
+int srf_geom_init(srf_geom* g_host, const float voxel_size_host[3], const float pc_range_host[6]);
+
+/* Dynamic voxelization: replaces mmcv dynamic_voxelize_forward
+ * (srfdet.py:238; batch-index padding of srfdet.py:242-246 fused when batch_idx >= 0).
+ * coors: (n,3) (z,y,x) when batch_idx < 0, else (n,4) (b,z,y,x); invalid points -> -1s. */
+int srf_dynamic_voxelize(const float* points, int32_t n, int32_t c, const srf_geom* g_host,
+                         int32_t batch_idx, int32_t* coors, void* stream);
+
+/* Hard voxelization: replaces mmcv hard_voxelize_forward (deterministic) (srfdet.py:221)
+ * and, when `mean` is given, HardSimpleVFE (cfg configs/nus/srfdet_voxel_nusc_L.py:40).
+ *  voxels      (max_voxels, max_points, c) f32, zero padded   [nullable]
+ *  coors       (max_voxels, 3) zyx, or (max_voxels, 4) bzyx when batch_idx >= 0
+ *  num_points  (max_voxels)
+ *  mean        (max_voxels, c) f32 = sum of kept points / num_points       [nullable]
+ *  point2voxel (n) voxel id that stored the point, -1 if dropped          [nullable]
+ *  d_voxel_num device scalar: number of voxels produced (<= max_voxels)
+ * Rows >= *d_voxel_num of the outputs are left untouched. */
+size_t srf_hard_voxelize_ws_bytes(int32_t n, int32_t max_points, int32_t max_voxels);
+int srf_hard_voxelize(const float* points, int32_t n, int32_t c, const srf_geom* g_host,
+                      int32_t max_points, int32_t max_voxels, int32_t batch_idx, float* voxels,
+                      int32_t* coors, int32_t* num_points, float* mean, int32_t* point2voxel,
+                      int32_t* d_voxel_num, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------- *
+ * Cell index: occupancy bitmap + per-word rank over a dense (B,Z,Y,X) grid.  rank(cell)
+ * enumerates occupied cells in ascending linear order, i.e. lexicographic (b,z,y,x):
+ * exactly the order of at::unique_dim in mmcv DynamicScatter and the canonical rulebook
+ * order.  It replaces: the sort in DynamicPointToVoxelForward, the dense
+ * canvas of map_voxel_center_to_point (voxel_encoder.py:118-158) and spconv's hash table.
+ * ---------------------------------------------------------------------------------- */
+size_t srf_index_bytes(int64_t ncells);
+int srf_index_clear(void* index, int64_t ncells, void* stream);
+/* set the bit of every row of coors (n,4); rows with a negative entry are skipped.
+ * d_n (nullable) overrides n with a device-side count (n is then the capacity). */
+int srf_index_mark(void* index, const int32_t dims_host[4], const int32_t* coors, int32_t n,
+                   const int32_t* d_n, void* stream);
+/* mark the outputs of a strided sparse conv: o = (p + pad - k)/stride where divisible
+ * (spconv pair rule; sparse_encoder_custom.py:99-107,172-194).  dims are the OUTPUT dims. */
+int srf_index_mark_strided(void* out_index, const int32_t out_dims_host[4], const int32_t* in_coors,
+                           int32_t cap_in, const int32_t* d_n_in, const int32_t ksize_host[3],
+                           const int32_t stride_host[3], const int32_t pad_host[3], void* stream);
+/* popcount scan -> ranks; *d_num = number of occupied cells */
+int srf_index_finalize(void* index, int64_t ncells, int32_t* d_num, void* stream);
+/* coors_out (cap,4): coordinates of the occupied cells in rank order */
+int srf_index_emit_coors(const void* index, const int32_t dims_host[4], int32_t* coors_out,
+                         int32_t cap, void* stream);
+/* rows[i] = rank of coors[i] or -1 (absent / negative coordinate) */
+int srf_index_lookup(const void* index, const int32_t dims_host[4], const int32_t* coors, int32_t n,
+                     const int32_t* d_n, int32_t* rows, void* stream);
+/* perm[rank(coors[i])] = i  (rank -> caller's row order) */
+int srf_index_perm(const void* index, const int32_t dims_host[4], const int32_t* coors, int32_t n,
+                   const int32_t* d_n, int32_t* perm, void* stream);
+
+/* out[r,:] = in[perm[r],:] for r < *d_n (cap rows when d_n is null); rows of c floats.
+ * Brings caller-ordered voxel features (SparseEncoderCustom.forward input,
+ * sparse_encoder_custom.py:110-124) into the index's sorted row order. */
+int srf_gather_rows(const float* in, const int32_t* perm, const int32_t* d_n, int32_t cap, int32_t c,
+                    float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------- *
+ * DynamicScatter: replaces mmcv dynamic_point_to_voxel_forward
+ * (voxel_encoder.py:82,99-102,189,232).  mode 0 = max, 1 = mean.  coor_dim 3 or 4.
+ * dims_host = (B,Z,Y,X) of the voxel grid (B = 1 for coor_dim 3).
+ * Outputs have capacity n rows; *d_num_voxels rows are valid, sorted like unique_dim.
+ * point2voxel (n) [nullable].  ws: srf_scatter_ws_bytes.
+ * ---------------------------------------------------------------------------------- */
+size_t srf_scatter_ws_bytes(int64_t ncells, int32_t n, int32_t c);
+int srf_dynamic_scatter(const float* feats, const int32_t* coors, int32_t n, int32_t c,
+                        int32_t coor_dim, const int32_t dims_host[4], int32_t mode,
+                        float* out_feats, int32_t* out_coors, int32_t* d_num_voxels,
+                        int32_t* point2voxel, void* ws, size_t ws_bytes, void* stream);
+
+/* DynamicVFECustom.forward, eval mode, fused (voxel_encoder.py:162-240 with
+ * map_voxel_center_to_point :118-158, DynamicVFELayer utils.py:8-45 and the eval path of
+ * NaiveSyncBatchNorm1dCustom ops/norm.py:57-58 folded into the weights).
+ *  points (n,cin), coors (n,4)    pos_w0 (32,3) pos_b0 (32) pos_w1 (32,32) pos_b1 (32)
+ *  vfe_w0 (c0, cin+35) vfe_b0 (c0); vfe_w1 (c1, 2*c0) vfe_b1 (c1) [nullable: one layer]
+ *  out_feats (n, c_last), out_coors (n,4): *d_num_voxels valid rows. */
+typedef struct srf_vfe_params {
+  const float *pos_w0, *pos_b0, *pos_w1, *pos_b1;
+  const float *vfe_w0, *vfe_b0, *vfe_w1, *vfe_b1;
+  int32_t cin, c0, c1; /* c1 = 0 when there is a single VFE layer */
+  float vx, vy, vz, x_off, y_off, z_off;
+} srf_vfe_params;
+size_t srf_dynamic_vfe_ws_bytes(int64_t ncells, int32_t n);
+int srf_dynamic_vfe(const float* points, const int32_t* coors, int32_t n, const int32_t dims_host[4],
+                    const srf_vfe_params* p_host, float* out_feats, int32_t* out_coors,
+                    int32_t* d_num_voxels, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------- *
+ * Rulebook: replaces spconv get_indice_pairs for SubMConv3d / SparseConv3d
+ * (sparse_encoder_custom.py:84-107,165-215).  Output-stationary form:
+ *   nbr[k * cap_out + o] = input row feeding output row o through kernel offset k
+ *   (k = (kz*KH + ky)*KW + kx, input cell = o*stride - pad + k), or -1.
+ *   tile_mask[o / 128] bit k set iff some row of that 128-row tile has a neighbour at k.
+ * in_perm (nullable) maps input rank -> caller row (first layer, unsorted input rows).
+ * ---------------------------------------------------------------------------------- */
+int srf_rulebook_build(const void* in_index, const int32_t in_dims_host[4], const int32_t* in_perm,
+                       const int32_t* out_coors, int32_t cap_out, const int32_t* d_n_out,
+                       const int32_t ksize_host[3], const int32_t stride_host[3],
+                       const int32_t pad_host[3], int32_t* nbr, uint32_t* tile_mask, void* stream);
+
+/* ---------------------------------------------------------------------------------- *
+ * Sparse convolution + folded BatchNorm1d + residual + ReLU (+ dense scatter).
+ * Replaces spconv SubMConv3d/SparseConv3d forward, BN1d, ReLU, SparseBasicBlock residual
+ * and SparseConvTensor.dense() (sparse_encoder_custom.py:125-138).
+ *   out[o] = act( sum_k W_k^T in[nbr[k][o]] + bias (+ residual[o]) )
+ * f32 path : SIMT FFMA, exact fp32 ("FP32 mode", tol 1e-4).  w (kvol, cin, cout) f32.
+ * bf16 path: tcgen05/TMEM implicit GEMM, bf16 operands, fp32 accumulate ("BF16 mode").
+ *            w packed by srf_pack_weight_bf16.  cin, cout in {16,32,64,128}.
+ * dense (nullable): write the result into a zeroed (B, cout*D, H, W) f32 map instead of
+ * `out` (needs out_coors + out_dims_host).
+ * ---------------------------------------------------------------------------------- */
+typedef struct srf_conv_args {
+  const void* in;          /* (n_in, cin) f32 | bf16 */
+  int32_t in_dtype;        /* SRF_F32 | SRF_BF16 */
+  int32_t cin, cout, kvol;
+  const int32_t* nbr;      /* (kvol, cap_out) */
+  const uint32_t* tile_mask;
+  int32_t cap_out;
+  const int32_t* d_n_out;
+  const void* w;           /* f32 (kvol,cin,cout) | packed bf16 */
+  const float* bias;       /* (cout) folded BN */
+  const void* residual;    /* (cap_out, cout) same dtype as out, nullable */
+  int32_t relu;
+  void* out;               /* (cap_out, cout) */
+  int32_t out_dtype;
+  float* dense;            /* nullable */
+  const int32_t* out_coors;
+  int32_t out_dims[4];
+} srf_conv_args;
+int srf_spconv_f32(const srf_conv_args* a_host, void* stream);
+int srf_spconv_bf16(const srf_conv_args* a_host, void* stream);
+/* w_f32 (kvol, cin, cout) device -> packed bf16 (kvol*cin*cout elements) device */
+int srf_pack_weight_bf16(const float* w_f32, int32_t kvol, int32_t cin, int32_t cout, void* w_packed,
+                         void* stream);
+/* f32 <-> bf16 row conversion with optional channel zero-padding (cout_pad >= c) */
+int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------- *
+ * Dense linear on tcgen05: out = epi(A (m,k) . W(n,k)^T + bias).  Replaces the cuBLAS
+ * GEMMs of DynamicConv (srfdet_head.py:2668,2689) and the fusion projection (:2257-2262).
+ * A bf16 row-major, W packed by srf_pack_linear_bf16 from nn.Linear's (n,k) f32 weight.
+ * epi: bit0 relu, bit1 layernorm over n (requires n == tile n <= 128) with ln_w/ln_b.
+ * k multiple of 16 (and of 128 when k > 128); n multiple of 16 (of 128 when n > 128).
+ * ---------------------------------------------------------------------------------- */
+int srf_linear_tile_k(int32_t k); /* host: K-slice width used by the packer (min(k,128)) */
+int srf_linear_tile_n(int32_t n); /* host: N tile width (min(n,128)) */
+int srf_pack_linear_bf16(const float* w_f32, int32_t n, int32_t k, void* w_packed, void* stream);
+int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n,
+                    const float* bias, int32_t epi, const float* ln_w, const float* ln_b,
+                    void* out, int32_t out_dtype, void* stream);
+
+/* FP32-mode linear (SIMT FFMA): out = relu?(A (m,k) . W(n,k)^T + bias), any n, k. */
+int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t n, const float* bias,
+                   int32_t relu, float* out, void* stream);
+/* Row-wise LayerNorm (+ReLU) over (rows, n); dtype SRF_F32 | SRF_BF16 (in and out).
+ * Used where the norm cannot be fused into a GEMM epilogue (n > 128, FP32 mode). */
+int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, const float* gamma,
+                  const float* beta, float eps, int32_t relu, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------- *
+ * Region features.
+ * srf_boxes_to_corners: boxes3d_to_corners3d(bottom_center=False, ry=False)
+ *   (core/bbox/util.py:84-176).  boxes (nb, box_dim>=8) -> corners (nb, 8, 3).
+ * ---------------------------------------------------------------------------------- */
+int srf_boxes_to_corners(const float* boxes, int32_t nb, int32_t box_dim, float* corners, void* stream);
+
+typedef struct srf_pyramid {
+  const float* feat[4]; /* level l: (n_img, C, H_l, W_l) f32 NCHW */
+  int32_t h[4], w[4];
+  float stride[4];      /* featmap_strides */
+  int32_t n_levels;     /* pooler.num_inputs */
+  int32_t channels;
+} srf_pyramid;
+
+/* Generic SingleRoIExtractor + RoIAlign(7x7, sampling_ratio 2, avg, aligned): replaces
+ * mmdet SingleRoIExtractor.forward / mmcv roi_align_forward
+ * (srfdet_head.py:1685,2082,2548,2626).  rois (k,5) = (img_idx, x1,y1,x2,y2).
+ * out (k, C, 7, 7) when channel_last == 0, else (k, 49, C). */
+int srf_roi_extract(const srf_pyramid* p_host, const float* rois, int32_t k, float* out,
+                    int32_t channel_last, void* stream);
+
+/* Fused points_feats_sampling_bboxes_roi (srfdet_head.py:2568-2629 / 1627-1688):
+ * centre de-normalisation IN PLACE on `boxes` (:2587) when mutate != 0, corners, BEV
+ * rectangle, level map, RoIAlign.  boxes (B, P, box_dim).  Maps are (B, C, H_l, W_l).
+ * out as in srf_roi_extract (k = B*P).  rois_out (B*P,5) nullable (for parity checks). */
+int srf_bev_roi_features(const srf_pyramid* p_host, float* boxes, int32_t batch, int32_t n_prop,
+                         int32_t box_dim, const float pc_range_host[6], const float voxel_size_host[3],
+                         int32_t mutate, float* out, int32_t channel_last, float* rois_out,
+                         void* stream);
+
+/* Fused img_feats_sampling_bboxes_roi (srfdet_head.py:2424-2565 / 1963-2099), B = 1
+ * semantics: projection by lidar2img (n_cam,4,4), per-camera rectangle,
+ * level map, RoIAlign, sum over cameras in registers.  Maps are (n_cam, C, H_l, W_l).
+ * boxes (P, box_dim) normalised centres, NOT mutated.  rois_out (n_cam*P,5) nullable. */
+int srf_img_roi_features(const srf_pyramid* p_host, const float* boxes, int32_t n_prop, int32_t box_dim,
+                         const float* lidar2img, int32_t n_cam, const float pc_range_host[6],
+                         float* out, int32_t channel_last, float* rois_out, void* stream);
+
+/* DynamicConv interaction core (srfdet_head.py:2679-2686): per proposal
+ *   f = relu(LN_d(feats(49,C) . P1(C,d))) ; g = relu(LN_C(f . P2(d,C)))
+ * roi (K,49,C) f32|bf16, params (K, 2*C*d) f32|bf16 (P1 then P2, row-major),
+ * out (K, 49*C) f32|bf16 (dtype flags).  C <= 256, d <= 64. */
+int srf_dynconv_interact(const void* roi, int32_t roi_dtype, const void* params, int32_t param_dtype,
+                         int32_t k, int32_t c, int32_t d, const float* ln1_w, const float* ln1_b,
+                         const float* ln2_w, const float* ln2_b, void* out, int32_t out_dtype,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRFDET_B200_H_ */

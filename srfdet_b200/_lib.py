@@ -1,0 +1,159 @@
+"""ctypes binding of libsrfdet_b200.so (include/srfdet_b200.h).
+
+There is NO CPU fallback: if the shared object is missing or a call fails, the op raises.
+torch is used only to own device memory and streams; every kernel argument crosses the
+boundary as a raw pointer / integer.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, 'csrc', 'libsrfdet_b200.so')
+
+F32, BF16 = 0, 1
+
+
+class SrfError(RuntimeError):
+    pass
+
+
+class Geom(Structure):
+    _fields_ = [('vs', c_float * 3), ('lo', c_float * 3), ('hi', c_float * 3), ('grid', c_int32 * 3)]
+
+
+class VfeParams(Structure):
+    _fields_ = [('pos_w0', c_void_p), ('pos_b0', c_void_p), ('pos_w1', c_void_p), ('pos_b1', c_void_p),
+                ('vfe_w0', c_void_p), ('vfe_b0', c_void_p), ('vfe_w1', c_void_p), ('vfe_b1', c_void_p),
+                ('cin', c_int32), ('c0', c_int32), ('c1', c_int32),
+                ('vx', c_float), ('vy', c_float), ('vz', c_float),
+                ('x_off', c_float), ('y_off', c_float), ('z_off', c_float)]
+
+
+class ConvArgs(Structure):
+    _fields_ = [('in_', c_void_p), ('in_dtype', c_int32), ('cin', c_int32), ('cout', c_int32), ('kvol', c_int32),
+                ('nbr', c_void_p), ('tile_mask', c_void_p), ('cap_out', c_int32), ('d_n_out', c_void_p),
+                ('w', c_void_p), ('bias', c_void_p), ('residual', c_void_p), ('relu', c_int32),
+                ('out', c_void_p), ('out_dtype', c_int32), ('dense', c_void_p), ('out_coors', c_void_p),
+                ('out_dims', c_int32 * 4)]
+
+
+class Pyramid(Structure):
+    _fields_ = [('feat', c_void_p * 4), ('h', c_int32 * 4), ('w', c_int32 * 4), ('stride', c_float * 4),
+                ('n_levels', c_int32), ('channels', c_int32)]
+
+
+_I4 = c_int32 * 4
+_I3 = c_int32 * 3
+_F3 = c_float * 3
+_F6 = c_float * 6
+
+# name -> (restype, argtypes).  Every symbol of include/srfdet_b200.h is listed here; the
+# CPU test-suite checks the two stay in sync and that the library exports all of them.
+PROTOTYPES = {
+    'srf_version': (c_int32, []),
+    'srf_last_error': (c_char_p, []),
+    'srf_sm_count': (c_int32, []),
+    'srf_launch_count': (ctypes.c_uint64, []),
+    'srf_geom_init': (c_int32, [POINTER(Geom), POINTER(c_float), POINTER(c_float)]),
+    'srf_dynamic_voxelize': (c_int32, [c_void_p, c_int32, c_int32, POINTER(Geom), c_int32, c_void_p, c_void_p]),
+    'srf_hard_voxelize_ws_bytes': (c_size_t, [c_int32, c_int32, c_int32]),
+    'srf_hard_voxelize': (c_int32, [c_void_p, c_int32, c_int32, POINTER(Geom), c_int32, c_int32, c_int32, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'srf_index_bytes': (c_size_t, [c_int64]),
+    'srf_index_clear': (c_int32, [c_void_p, c_int64, c_void_p]),
+    'srf_index_mark': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_int32, c_void_p, c_void_p]),
+    'srf_index_mark_strided': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_int32, c_void_p, POINTER(c_int32),
+                                         POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    'srf_index_finalize': (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
+    'srf_index_emit_coors': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_int32, c_void_p]),
+    'srf_index_lookup': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    'srf_index_perm': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    'srf_gather_rows': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_scatter_ws_bytes': (c_size_t, [c_int64, c_int32, c_int32]),
+    'srf_dynamic_scatter': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32), c_int32,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'srf_dynamic_vfe_ws_bytes': (c_size_t, [c_int64, c_int32]),
+    'srf_dynamic_vfe': (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_int32), POINTER(VfeParams), c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'srf_rulebook_build': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_void_p, c_int32, c_void_p,
+                                     POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]),
+    'srf_spconv_f32': (c_int32, [POINTER(ConvArgs), c_void_p]),
+    'srf_spconv_bf16': (c_int32, [POINTER(ConvArgs), c_void_p]),
+    'srf_pack_weight_bf16': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_f32_to_bf16': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_linear_tile_k': (c_int32, [c_int32]),
+    'srf_linear_tile_n': (c_int32, [c_int32]),
+    'srf_pack_linear_bf16': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_linear_bf16': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                  c_void_p, c_void_p, c_int32, c_void_p]),
+    'srf_linear_f32': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    'srf_layernorm': (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p]),
+    'srf_boxes_to_corners': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_roi_extract': (c_int32, [POINTER(Pyramid), c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
+    'srf_bev_roi_features': (c_int32, [POINTER(Pyramid), c_void_p, c_int32, c_int32, c_int32, POINTER(c_float),
+                                       POINTER(c_float), c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    'srf_img_roi_features': (c_int32, [POINTER(Pyramid), c_void_p, c_int32, c_int32, c_void_p, c_int32,
+                                       POINTER(c_float), c_void_p, c_int32, c_void_p, c_void_p]),
+    'srf_dynconv_interact': (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared object (raises SrfError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise SrfError(f'{SO_PATH} not found: build it with `python -m srfdet_b200.build` '
+                           '(there is no CPU fallback)')
+        lib = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = load().srf_last_error()
+        raise SrfError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'kernel arguments must be contiguous CUDA tensors'
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def i4(v):
+    return _I4(*[int(x) for x in v])
+
+
+def i3(v):
+    return _I3(*[int(x) for x in v])
+
+
+def f3(v):
+    return _F3(*[float(x) for x in v])
+
+
+def f6(v):
+    return _F6(*[float(x) for x in v])
+
+
+def make_geom(voxel_size, pc_range):
+    g = Geom()
+    check(load().srf_geom_init(ctypes.byref(g), f3(voxel_size), f6(pc_range)), 'srf_geom_init')
+    return g

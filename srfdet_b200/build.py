@@ -1,0 +1,59 @@
+"""Build libsrfdet_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m srfdet_b200.build [--force]
+
+The shared object is plain C ABI (include/srfdet_b200.h); it links only cudart.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+SO = os.path.join(CSRC, 'libsrfdet_b200.so')
+SOURCES = ['index.cu', 'voxelize.cu', 'scatter.cu', 'spconv_simt.cu', 'igemm_umma.cu', 'roi.cu', 'dynconv.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return 'nvcc'
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, 'common.cuh'),
+                                                        os.path.join(HERE, '..', 'include', 'srfdet_b200.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    objs = []
+    procs = []
+    for s in SOURCES:
+        obj = os.path.join(CSRC, s.replace('.cu', '.o'))
+        cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, s), '-o', obj]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(f'--- {s}\n{out}\n')
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError('nvcc failed')
+    link = [_nvcc(), '-shared', '-o', SO] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    subprocess.check_call(link)
+    return SO
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,90 @@
+// Shared helpers for the sm_100a kernels of libsrfdet_b200.so.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/srfdet_b200.h"
+
+namespace srf {
+
+void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;  // kernels launched by this library (bench evidence)
+#define SRF_COUNT(n) (srf::g_launches += (n))
+int sm_count();
+
+#define SRF_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      srf::set_error(__VA_ARGS__);        \
+      return SRF_ERR_ARG;                 \
+    }                                     \
+  } while (0)
+
+#define SRF_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      srf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                     __LINE__);                                                         \
+      return SRF_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define SRF_LAUNCH_CHECK() SRF_CUDA(cudaGetLastError())
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------
+// Cell index (occupancy bitmap + per-word exclusive rank).  Layout inside the caller's
+// buffer:  [bits: nwords u32][rank: nwords u32][blocksum: SCAN_BLOCKS u32]
+// ------------------------------------------------------------------------------------
+constexpr int SCAN_BLOCKS = 1024;
+constexpr int SCAN_THREADS = 256;
+
+struct IndexView {
+  uint32_t* bits;
+  uint32_t* rank;
+  uint32_t* blocksum;
+  int64_t nwords;
+};
+
+static inline int64_t index_nwords(int64_t ncells) { return (ncells + 31) / 32; }
+
+static inline IndexView index_view(const void* p, int64_t ncells) {
+  IndexView v;
+  v.nwords = index_nwords(ncells);
+  int64_t nw_al = (v.nwords + 3) / 4 * 4;
+  v.bits = (uint32_t*)p;
+  v.rank = v.bits + nw_al;
+  v.blocksum = v.rank + nw_al;
+  return v;
+}
+
+struct Dims4 {
+  int32_t b, z, y, x;
+};
+
+__device__ __forceinline__ int64_t cell_of(const Dims4& d, int b, int z, int y, int x) {
+  return (((int64_t)b * d.z + z) * d.y + y) * d.x + x;
+}
+
+// rank of an occupied cell, or -1
+__device__ __forceinline__ int index_rank(const uint32_t* __restrict__ bits,
+                                          const uint32_t* __restrict__ rank, int64_t cell) {
+  int64_t w = cell >> 5;
+  uint32_t bit = 1u << (cell & 31);
+  uint32_t word = __ldg(bits + w);
+  if (!(word & bit)) return -1;
+  return (int)(__ldg(rank + w) + __popc(word & (bit - 1)));
+}
+
+// device-wide exclusive scan of uint32 values produced by a functor; 3 launches.
+// (implemented in index.cu; used by voxelize.cu as well)
+int scan_flags_launch(const uint32_t* in, uint32_t* out_excl, uint32_t* blocksum, int64_t n,
+                      int32_t* d_total, int popcount_mode, cudaStream_t st);
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __uint_as_float(hi16 << 16); }
+
+}  // namespace srf

@@ -1,0 +1,338 @@
+// FP32 ("exact") sparse convolution and linear kernels on the SIMT pipes, plus the
+// weight-packing / conversion helpers used by the tcgen05 path.
+//
+// The FP32 kernels are the parity mode (tolerance 1e-4 vs the fp32 reference): same
+// output-stationary rulebook as the tensor-core kernel, FFMA accumulation in fp32.
+#include "common.cuh"
+
+namespace srf {
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+struct ConvDev {
+  const void* in;
+  const int32_t* nbr;
+  const uint32_t* tile_mask;
+  const int32_t* d_n_out;
+  const float* w;
+  const float* bias;
+  const void* residual;
+  void* out;
+  float* dense;
+  const int4* out_coors;
+  int cin, kvol, cap_out, relu, out_bf16;
+  int D, H, W;
+};
+
+constexpr int SIMT_TILE = 32;
+constexpr int SIMT_MAXCIN = 128;
+
+// block = 128 threads, tile = 32 output rows.  thread -> one output channel `co` and
+// RPT = COUT/4 rows; A tile (32 x cin) staged in shared memory, weights read through L1.
+template <int COUT, typename TIN>
+__global__ void __launch_bounds__(128) spconv_f32_kernel(ConvDev a) {
+  constexpr int NGROUPS = 128 / COUT;
+  constexpr int RPT = SIMT_TILE / NGROUPS;
+  __shared__ float sA[SIMT_TILE][SIMT_MAXCIN + 1];
+  __shared__ int sN[SIMT_TILE];
+  const int n_out = a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out;
+  const int ntiles = (n_out + SIMT_TILE - 1) / SIMT_TILE;
+  const int co = threadIdx.x % COUT;
+  const int rg = threadIdx.x / COUT;
+  const TIN* in = (const TIN*)a.in;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * SIMT_TILE;
+    float acc[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r] = 0.f;
+    const uint32_t mask = a.tile_mask ? a.tile_mask[row0 >> 7] : 0xffffffffu;
+    for (int k = 0; k < a.kvol; ++k) {
+      if (!((mask >> k) & 1u)) continue;
+      int nb = -1;
+      if (threadIdx.x < SIMT_TILE) {
+        int row = row0 + threadIdx.x;
+        nb = row < n_out ? __ldg(a.nbr + (size_t)k * a.cap_out + row) : -1;
+        sN[threadIdx.x] = nb;
+      }
+      if (!__syncthreads_or(nb >= 0)) continue;
+      for (int e = threadIdx.x; e < SIMT_TILE * a.cin; e += 128) {
+        int r = e / a.cin, ci = e - r * a.cin;
+        int src = sN[r];
+        sA[r][ci] = src >= 0 ? ld_as_float<TIN>(in + (size_t)src * a.cin + ci) : 0.f;
+      }
+      __syncthreads();
+      const float* wk = a.w + (size_t)k * a.cin * COUT + co;
+      for (int ci = 0; ci < a.cin; ++ci) {
+        float w = __ldg(wk + (size_t)ci * COUT);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) acc[r] = fmaf(sA[rg * RPT + r][ci], w, acc[r]);
+      }
+      __syncthreads();
+    }
+    const float b = a.bias ? __ldg(a.bias + co) : 0.f;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      int row = row0 + rg * RPT + r;
+      if (row >= n_out) continue;
+      float v = acc[r] + b;
+      if (a.residual) {
+        v += a.out_bf16 ? __bfloat162float(((const __nv_bfloat16*)a.residual)[(size_t)row * COUT + co])
+                        : ((const float*)a.residual)[(size_t)row * COUT + co];
+      }
+      if (a.relu) v = fmaxf(v, 0.f);
+      if (a.dense) {
+        int4 q = __ldg(a.out_coors + row);
+        size_t hw = (size_t)a.H * a.W;
+        a.dense[((size_t)q.x * COUT * a.D + (size_t)co * a.D + q.y) * hw + (size_t)q.z * a.W + q.w] = v;
+      } else if (a.out_bf16) {
+        ((__nv_bfloat16*)a.out)[(size_t)row * COUT + co] = __float2bfloat16(v);
+      } else {
+        ((float*)a.out)[(size_t)row * COUT + co] = v;
+      }
+    }
+  }
+}
+
+// (kvol, cin, cout) f32 -> bf16 in UMMA "core matrix" order:
+//   [k][ci/8][co][ci%8]   (one 16-byte K-chunk per output channel row)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int kvol, int cin, int cout,
+                                   __nv_bfloat16* __restrict__ out) {
+  int64_t total = (int64_t)kvol * cin * cout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(e % cout);
+    int64_t t = e / cout;
+    int ci = (int)(t % cin);
+    int k = (int)(t / cin);
+    int64_t dst = (((int64_t)k * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8);
+    out[dst] = __float2bfloat16(w[e]);
+  }
+}
+
+// nn.Linear weight (n, k) f32 -> bf16 tiles [n/tn][k/tk][tk/8][tn][8]
+__global__ void pack_linear_kernel(const float* __restrict__ w, int n, int k, int tn, int tk,
+                                   __nv_bfloat16* __restrict__ out) {
+  int64_t total = (int64_t)n * k;
+  int nkc = k / tk;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int kk = (int)(e % k);
+    int nn = (int)(e / k);
+    int nt = nn / tn, nl = nn % tn, kc = kk / tk, ci = kk % tk;
+    int64_t dst = ((((int64_t)nt * nkc + kc) * (tk / 8) + ci / 8) * tn + nl) * 8 + (ci % 8);
+    out[dst] = __float2bfloat16(w[e]);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, int64_t rows, int c, int c_pad,
+                                   __nv_bfloat16* __restrict__ out) {
+  int64_t total = rows * c_pad;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(e % c_pad);
+    int64_t r = e / c_pad;
+    out[e] = __float2bfloat16(j < c ? in[r * c + j] : 0.f);
+  }
+}
+
+// out[r] = in[perm[r]] for r < *d_n (rows of c floats): puts caller-ordered voxel features
+// into the index's sorted row order (perm from srf_index_perm).
+__global__ void gather_rows_kernel(const float* __restrict__ in, const int32_t* __restrict__ perm,
+                                   const int32_t* __restrict__ d_n, int cap, int c, float* __restrict__ out) {
+  int n = d_n ? min(*d_n, cap) : cap;
+  int64_t total = (int64_t)n * c;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(e % c);
+    int64_t r = e / c;
+    out[e] = __ldg(in + (size_t)__ldg(perm + r) * c + j);
+  }
+}
+
+// ---- generic fp32 linear: out = epi(A (m,k) . W(n,k)^T + bias) ----------------------------
+// block = 256 threads = 256 output columns (grid.y tiles n), LIN_ROWS rows (grid.x tiles m);
+// A is staged through shared memory in K-chunks, each thread keeps LIN_ROWS accumulators.
+constexpr int LIN_ROWS = 16;
+constexpr int LIN_KC = 256;
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ A, int m, int k,
+                                                        const float* __restrict__ W, int n,
+                                                        const float* __restrict__ bias, int relu,
+                                                        float* __restrict__ out) {
+  __shared__ float sa[LIN_ROWS][LIN_KC + 1];
+  const int row0 = blockIdx.x * LIN_ROWS;
+  const int col = blockIdx.y * 256 + threadIdx.x;
+  float acc[LIN_ROWS];
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS; ++r) acc[r] = 0.f;
+  const float* wr = W + (size_t)(col < n ? col : 0) * k;
+  for (int k0 = 0; k0 < k; k0 += LIN_KC) {
+    const int kc = min(LIN_KC, k - k0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < LIN_ROWS * LIN_KC; e += 256) {
+      int r = e / LIN_KC, j = e - r * LIN_KC;
+      sa[r][j] = (row0 + r < m && j < kc) ? A[(size_t)(row0 + r) * k + k0 + j] : 0.f;
+    }
+    __syncthreads();
+    if (col < n) {
+      for (int j = 0; j < kc; ++j) {
+        float w = __ldg(wr + k0 + j);
+#pragma unroll
+        for (int r = 0; r < LIN_ROWS; ++r) acc[r] = fmaf(sa[r][j], w, acc[r]);
+      }
+    }
+  }
+  if (col >= n) return;
+  const float b = bias ? bias[col] : 0.f;
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS; ++r) {
+    if (row0 + r >= m) continue;
+    float v = acc[r] + b;
+    if (relu) v = fmaxf(v, 0.f);
+    out[(size_t)(row0 + r) * n + col] = v;
+  }
+}
+
+// row-wise LayerNorm (+ReLU), one warp per row; in/out f32 or bf16
+template <typename T>
+__global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, int n, const float* __restrict__ g,
+                                      const float* __restrict__ b, float eps, int relu, T* __restrict__ out) {
+  int lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* x = in + row * n;
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s += (float)x[j];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / n;
+  float v = 0.f;
+  for (int j = lane; j < n; j += 32) { float d = (float)x[j] - mean; v += d * d; }
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  float rstd = rsqrtf(v / n + eps);
+  for (int j = lane; j < n; j += 32) {
+    float y = ((float)x[j] - mean) * rstd * g[j] + b[j];
+    if (relu) y = fmaxf(y, 0.f);
+    out[row * n + j] = (T)y;
+  }
+}
+
+static int lgrid2(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+template <typename TIN>
+static int launch_conv_f32(const ConvDev& d, int cout, int grid, cudaStream_t st) {
+  switch (cout) {
+    case 16: spconv_f32_kernel<16, TIN><<<grid, 128, 0, st>>>(d); break;
+    case 32: spconv_f32_kernel<32, TIN><<<grid, 128, 0, st>>>(d); break;
+    case 64: spconv_f32_kernel<64, TIN><<<grid, 128, 0, st>>>(d); break;
+    case 128: spconv_f32_kernel<128, TIN><<<grid, 128, 0, st>>>(d); break;
+    default: set_error("srf_spconv_f32: cout must be 16/32/64/128 (got %d)", cout); return SRF_ERR_UNSUPPORTED;
+  }
+  return SRF_OK;
+}
+
+}  // namespace srf
+
+using namespace srf;
+
+extern "C" {
+
+int srf_spconv_f32(const srf_conv_args* a, void* stream) {
+  SRF_CHECK_ARG(a && a->in && a->nbr && a->w && (a->out || a->dense), "srf_spconv_f32: null arg");
+  SRF_CHECK_ARG(a->cin >= 1 && a->cin <= SIMT_MAXCIN, "srf_spconv_f32: cin must be in [1,%d]", SIMT_MAXCIN);
+  SRF_CHECK_ARG(a->kvol >= 1 && a->kvol <= 27, "srf_spconv_f32: kvol must be in [1,27]");
+  SRF_CHECK_ARG(a->cap_out > 0 && a->cap_out % 128 == 0, "srf_spconv_f32: cap_out must be a multiple of 128");
+  SRF_CHECK_ARG(!a->dense || a->out_coors, "srf_spconv_f32: dense output needs out_coors");
+  ConvDev d;
+  d.in = a->in; d.nbr = a->nbr; d.tile_mask = a->tile_mask; d.d_n_out = a->d_n_out;
+  d.w = (const float*)a->w; d.bias = a->bias; d.residual = a->residual; d.out = a->out; d.dense = a->dense;
+  d.out_coors = (const int4*)a->out_coors; d.cin = a->cin; d.kvol = a->kvol; d.cap_out = a->cap_out;
+  d.relu = a->relu; d.out_bf16 = a->out_dtype == SRF_BF16;
+  d.D = a->out_dims[1]; d.H = a->out_dims[2]; d.W = a->out_dims[3];
+  int ntiles = a->cap_out / SIMT_TILE;
+  int grid = sm_count() * 8;
+  if (grid > ntiles) grid = ntiles;
+  cudaStream_t st = (cudaStream_t)stream;
+  SRF_COUNT(1);
+  int rc = a->in_dtype == SRF_BF16 ? launch_conv_f32<__nv_bfloat16>(d, a->cout, grid, st)
+                                   : launch_conv_f32<float>(d, a->cout, grid, st);
+  if (rc) return rc;
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+int srf_pack_weight_bf16(const float* w, int32_t kvol, int32_t cin, int32_t cout, void* packed, void* stream) {
+  SRF_CHECK_ARG(w && packed && kvol > 0 && cin % 8 == 0 && cout % 8 == 0, "srf_pack_weight_bf16: bad args");
+  int64_t total = (int64_t)kvol * cin * cout;
+  SRF_COUNT(1);
+  pack_weight_kernel<<<lgrid2(total, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cout, (__nv_bfloat16*)packed);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+int srf_linear_tile_k(int32_t k) { return k > 128 ? 128 : k; }
+int srf_linear_tile_n(int32_t n) { return n > 128 ? 128 : n; }
+
+int srf_pack_linear_bf16(const float* w, int32_t n, int32_t k, void* packed, void* stream) {
+  SRF_CHECK_ARG(w && packed, "srf_pack_linear_bf16: null arg");
+  int tk = srf_linear_tile_k(k), tn = srf_linear_tile_n(n);
+  SRF_CHECK_ARG(k % tk == 0 && n % tn == 0 && tk % 16 == 0 && tn % 16 == 0,
+                "srf_pack_linear_bf16: n=%d k=%d not tileable (multiples of 16; of 128 above 128)", n, k);
+  SRF_COUNT(1);
+  pack_linear_kernel<<<lgrid2((int64_t)n * k, 256), 256, 0, (cudaStream_t)stream>>>(w, n, k, tn, tk, (__nv_bfloat16*)packed);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, void* out, void* stream) {
+  SRF_CHECK_ARG(in && out && rows >= 0 && c > 0 && c_pad >= c, "srf_f32_to_bf16: bad args");
+  if (rows == 0) return SRF_OK;
+  SRF_COUNT(1);
+  f32_to_bf16_kernel<<<lgrid2(rows * c_pad, 256), 256, 0, (cudaStream_t)stream>>>(in, rows, c, c_pad, (__nv_bfloat16*)out);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+int srf_gather_rows(const float* in, const int32_t* perm, const int32_t* d_n, int32_t cap, int32_t c, float* out,
+                    void* stream) {
+  SRF_CHECK_ARG(in && perm && out && cap >= 0 && c > 0, "srf_gather_rows: bad args");
+  if (cap == 0) return SRF_OK;
+  SRF_COUNT(1);
+  gather_rows_kernel<<<lgrid2((int64_t)cap * c, 256), 256, 0, (cudaStream_t)stream>>>(in, perm, d_n, cap, c, out);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t n, const float* bias,
+                   int32_t relu, float* out, void* stream) {
+  SRF_CHECK_ARG(a && w && out && m >= 0 && k > 0 && n > 0, "srf_linear_f32: bad args");
+  if (m == 0) return SRF_OK;
+  dim3 grid(cdiv(m, LIN_ROWS), cdiv(n, 256));
+  SRF_COUNT(1);
+  linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, m, k, w, n, bias, relu, out);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, const float* gamma, const float* beta,
+                  float eps, int32_t relu, void* out, void* stream) {
+  SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
+  if (rows == 0) return SRF_OK;
+  SRF_COUNT(1);
+  int wpb = 8;
+  int grid = (int)((rows + wpb - 1) / wpb);
+  if (dtype == SRF_BF16)
+    layernorm_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, gamma, beta, eps, relu, (__nv_bfloat16*)out);
+  else
+    layernorm_rows_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, gamma, beta, eps, relu, (float*)out);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+"""Frame pipeline of the measured hot path (BASELINE.json metric: frames/s of
+voxelize + SparseEncoder + region fusion), assembled from the drop-in modules.
+
+One frame =
+  points (N,C) --Voxelization(+HardSimpleVFE | DynamicVFECustom)--> voxel features
+         --SparseEncoderCustom--> dense BEV map (1, 256, H, W)
+  for each of the 5 cascade stages (srfdet_head.py:428-458):
+         proposals --BEV RoIAlign [+ multi-view image RoIAlign + fusion Linear]--> (P,49,C)
+         --DynamicConv--> (P, C) region features
+
+What is NOT in the frame (outside the hot path): the dense BEV backbone/FPN
+between the encoder and the RoI stage, the image backbone, and the attention / FFN /
+box-regression rows of a stage.  The RoI stage therefore samples *synthetic* FPN pyramids
+(N(0,1) maps of the configs' shapes) with seeded per-stage proposal boxes; the proposal
+features chain from stage to stage through DynamicConv.
+"""
+import numpy as np
+import torch
+
+from . import synth
+from .plugin import (DynamicConv, SingleRoIExtractor, SRFDetPointPath, img_feats_sampling_bboxes_roi,
+                     points_feats_sampling_bboxes_roi)
+from .plugin import head as _head
+from .plugin import registry
+
+MODEL_CFG = {
+    # configs/nus/srfdet_voxel_nusc_L.py:34-50 (+ LC variant :40-84 for the image branch)
+    'nusc': dict(
+        pts_voxel_layer=dict(max_num_points=10, voxel_size=[0.075, 0.075, 0.2], max_voxels=(120000, 160000),
+                             point_cloud_range=[-55.2, -55.2, -5.0, 55.2, 55.2, 3.0]),
+        pts_voxel_encoder=dict(type='HardSimpleVFE', num_features=5),
+        pts_middle_encoder=dict(type='SparseEncoderCustom', in_channels=5, sparse_shape=[41, 1472, 1472], output_channels=128,
+                                order=('conv', 'norm', 'act'),
+                                encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+                                encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')),
+    # configs/waymo/srfdet_dvoxel_waymo_L.py:26-59
+    'waymo': dict(
+        pts_voxel_layer=dict(voxel_size=[0.1, 0.1, 0.15], max_num_points=-1, point_cloud_range=[-76.8, -76.8, -2, 76.8, 76.8, 4],
+                             max_voxels=(-1, -1)),
+        pts_voxel_encoder=dict(type='DynamicVFECustom', in_channels=5, feat_channels=[5, 5], with_distance=False,
+                               voxel_size=[0.1, 0.1, 0.15], with_cluster_center=True, with_voxel_center=True,
+                               point_cloud_range=[-76.8, -76.8, -2, 76.8, 76.8, 4],
+                               norm_cfg=dict(type='naiveSyncBN1dCustom', eps=1e-3, momentum=0.01)),
+        pts_middle_encoder=dict(type='SparseEncoderCustom', in_channels=5, sparse_shape=[41, 1536, 1536], output_channels=128,
+                                order=('conv', 'norm', 'act'),
+                                encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+                                encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')),
+    # configs/kitti/srfdet_voxel_kitti_L.py:30-56
+    'kitti': dict(
+        pts_voxel_layer=dict(voxel_size=[0.05, 0.05, 0.1], max_num_points=-1, point_cloud_range=[0, -40, -3, 70.4, 40, 1],
+                             max_voxels=(-1, -1)),
+        pts_voxel_encoder=dict(type='DynamicVFECustom', in_channels=4, feat_channels=[4], with_distance=False,
+                               voxel_size=[0.05, 0.05, 0.1], with_cluster_center=True, with_voxel_center=True,
+                               point_cloud_range=[0, -40, -3, 70.4, 40, 1],
+                               norm_cfg=dict(type='naiveSyncBN1dCustom', eps=1e-3, momentum=0.01)),
+        pts_middle_encoder=dict(type='SparseEncoderCustom', in_channels=4, sparse_shape=[41, 1600, 1408], order=('conv', 'norm', 'act'))),
+}
+
+HEAD_CFG = {  # feat channels C, dynamic dim d, BEV base size, box dims (Appendix A of SURVEY.md)
+    'nusc': dict(C=128, d=32, bev_hw=(184, 184), box_dim=10),
+    'waymo': dict(C=128, d=32, bev_hw=(192, 192), box_dim=8),
+    'kitti': dict(C=256, d=64, bev_hw=(200, 176), box_dim=8),
+}
+N_STAGES = 5
+N_PROP = 900
+
+
+def _randomize_bn(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+
+
+class RegionFeaturePipeline:
+    """kind in {'nusc','waymo','kitti'}; fusion=True adds the 6-camera image branch + fusion
+    projection of srfdet_voxel_nusc_LC.  Weights: torch.manual_seed(0) random init with
+    non-trivial BatchNorm statistics (no checkpoints offline)."""
+
+    def __init__(self, kind='nusc', fusion=False, device='cuda', precision=None, seed=0):
+        self.kind, self.fusion, self.device = kind, fusion, torch.device(device)
+        self.precision = precision or registry.get_precision()
+        h = HEAD_CFG[kind]
+        self.C, self.d, self.box_dim = h['C'], h['d'], h['box_dim']
+        self.pc_range = MODEL_CFG[kind]['pts_voxel_layer']['point_cloud_range']
+        self.voxel_size = MODEL_CFG[kind]['pts_voxel_layer']['voxel_size']
+        torch.manual_seed(seed)
+        self.detector = SRFDetPointPath(**MODEL_CFG[kind])
+        _randomize_bn(self.detector, seed + 1)
+        self.detector = self.detector.to(self.device).eval()
+        self.pooler = SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=2), self.C, [8, 16, 32, 64])
+        self.pooler_img = SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=2), self.C, [4, 8, 16, 32])
+        self.dynconvs = [DynamicConv(self.C, self.d).to(self.device).eval() for _ in range(N_STAGES)]
+        self.fuse = [torch.nn.Linear(2 * self.C, self.C).to(self.device).eval() for _ in range(N_STAGES)] if fusion else None
+        self._fuse_cache = [dict() for _ in range(N_STAGES)]
+        # synthetic FPN pyramids (stand-ins for the dense backbones)
+        self.bev_feats = [torch.as_tensor(f).to(self.device) for f in synth.feature_pyramid(seed + 10, self.C, h['bev_hw'], 4)]
+        self.img_feats = self.lidar2img = None
+        if fusion:
+            self.img_feats = [torch.as_tensor(f).to(self.device)
+                              for f in synth.feature_pyramid(seed + 11, self.C, (232, 400), 4, lead=(1, 6))]
+            self.lidar2img = torch.as_tensor(synth.lidar2img(6, 1)[0]).to(self.device)
+        self.stage_boxes = [torch.as_tensor(synth.proposals(seed + 20 + s, N_PROP, self.box_dim, 1)).to(self.device)
+                            for s in range(N_STAGES)]
+        self.prop0 = (torch.randn(N_PROP, self.C, generator=torch.Generator().manual_seed(seed + 30))).to(self.device)
+
+    def state(self):
+        """Weights / synthetic inputs as numpy, for the CPU oracle."""
+        sd = lambda m: {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+        return dict(encoder=sd(self.detector.pts_middle_encoder),
+                    vfe=sd(self.detector.pts_voxel_encoder),
+                    dynconv=[sd(m) for m in self.dynconvs],
+                    fuse=[sd(m) for m in self.fuse] if self.fusion else None,
+                    bev_feats=[f.cpu().numpy() for f in self.bev_feats],
+                    img_feats=[f.cpu().numpy() for f in self.img_feats] if self.fusion else None,
+                    lidar2img=self.lidar2img.cpu().numpy() if self.fusion else None,
+                    stage_boxes=[b.cpu().numpy() for b in self.stage_boxes], prop0=self.prop0.cpu().numpy())
+
+    @torch.no_grad()
+    def encode(self, points):
+        return self.detector.extract_point_features([points], precision=self.precision)
+
+    @torch.no_grad()
+    def region_stages(self):
+        prop = self.prop0
+        for s in range(N_STAGES):
+            boxes = self.stage_boxes[s].clone()          # the sampler de-normalises centres in place
+            if self.fusion:
+                img_roi = img_feats_sampling_bboxes_roi(self.img_feats, boxes, self.pooler_img, self.lidar2img, self.pc_range,
+                                                        channel_last=True)
+                pts_roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
+                                                           channel_last=True)
+                cat = torch.cat((img_roi, pts_roi), dim=2).view(N_PROP * 49, 2 * self.C)
+                roi = _head._linear(cat, self.fuse[s], self.precision, self._fuse_cache[s], 'fuse').view(N_PROP, 49, self.C)
+            else:
+                roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
+                                                       channel_last=True)
+            prop = self.dynconvs[s].forward_kc(prop, roi, precision=self.precision)
+        return prop
+
+    @torch.no_grad()
+    def run_frame(self, points):
+        """points (N,C) fp32 CUDA tensor -> (dense BEV map, region features (P,C))."""
+        bev = self.encode(points)
+        return bev, self.region_stages()
+
+    @torch.no_grad()
+    def run_frame_host(self, points_pinned):
+        """Public end-to-end call: HOST (pinned) points in, HOST region features out."""
+        pts = points_pinned.to(self.device, non_blocking=True)
+        bev, obj = self.run_frame(pts)
+        out = torch.empty(obj.shape, dtype=obj.dtype, pin_memory=True)
+        out.copy_(obj, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return bev, out

@@ -1,0 +1,297 @@
+"""SparseEncoderCustom (mmdet3d_plugin/models/middle_encoders/sparse_encoder_custom.py)
+re-built on the bitmap-rank rulebook and the output-stationary sparse convolution kernels.
+
+Same constructor signature, registry name and state-dict keys as the reference
+(`conv_input.0.weight`, `conv_input.1.*`, `encoder_layers.encoder_layer{i}.{j}.{0|conv1}...`,
+`conv_out.{0,1}.*`; conv weights in spconv-2 layout (Cout,kD,kH,kW,Cin)).
+
+Differences in HOW (not WHAT):
+  * one rulebook per resolution (the reference rebuilds 17 SubM rulebooks because the
+    convs inside SparseBasicBlock carry no indice_key, sparse_encoder_custom.py:197-201);
+  * rows are kept in ascending (b,z,y,x) order from the first layer on (gather locality);
+  * BatchNorm1d(eval) is folded into the conv weights, bias / residual / ReLU run in the
+    conv epilogue, and conv_out writes straight into the dense (B, C*D, H, W) map
+    (SparseConvTensor.dense() + view, :135-138);
+  * no host synchronisation: voxel counts stay on the device, buffers are sized by
+    worst-case capacities (<= 8x growth per stride-2 stage, bounded by the grid).
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from . import registry
+from .registry import MIDDLE_ENCODERS, build_norm_layer
+from .voxel_encoder import fold_bn
+
+
+def _t3(v):
+    return tuple(int(x) for x in v) if isinstance(v, (tuple, list)) else (int(v),) * 3
+
+
+class SparseConv3dParams(nn.Module):
+    """Parameter holder for SubMConv3d / SparseConv3d (bias=False), spconv-2 weight layout."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, subm=False, indice_key=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = _t3(kernel_size), _t3(stride), _t3(padding)
+        self.subm = subm
+        self.indice_key = indice_key
+        if subm:
+            self.stride = (1, 1, 1)
+            self.padding = tuple(k // 2 for k in self.kernel_size)
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        fan_in = in_channels * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        nn.init.uniform_(self.weight, -(3.0 / fan_in) ** 0.5 * 1.7, (3.0 / fan_in) ** 0.5 * 1.7)
+
+    def kio(self):
+        """(kvol, cin, cout) view of the weight (accepts the spconv-1/mmcv layout
+        (kD,kH,kW,Cin,Cout) when a checkpoint in that layout was loaded)."""
+        w = self.weight.detach().float()
+        k = self.kernel_size
+        if tuple(w.shape) == (self.out_channels, *k, self.in_channels):
+            return w.permute(1, 2, 3, 4, 0).reshape(k[0] * k[1] * k[2], self.in_channels, self.out_channels)
+        if tuple(w.shape) == (*k, self.in_channels, self.out_channels):
+            return w.reshape(k[0] * k[1] * k[2], self.in_channels, self.out_channels)
+        raise ValueError(f'unexpected sparse conv weight shape {tuple(w.shape)}')
+
+
+def make_sparse_convmodule(in_channels, out_channels, kernel_size, indice_key, stride=1, padding=0,
+                           conv_type='SubMConv3d', norm_cfg=None, order=('conv', 'norm', 'act')):
+    """[3P] mmdet3d.ops.make_sparse_convmodule: Sequential(conv(bias=False), BN1d, ReLU)."""
+    assert conv_type in ('SubMConv3d', 'SparseConv3d')
+    assert tuple(order) == ('conv', 'norm', 'act'), 'only post-activation order is built'
+    return nn.Sequential(
+        SparseConv3dParams(in_channels, out_channels, kernel_size, stride, padding, conv_type == 'SubMConv3d', indice_key),
+        build_norm_layer(norm_cfg, out_channels)[1], nn.ReLU(inplace=True))
+
+
+class SparseBasicBlock(nn.Module):
+    """[3P] mmdet3d.ops.SparseBasicBlock: conv1-bn1-relu-conv2-bn2-(+identity)-relu."""
+
+    def __init__(self, inplanes, planes, norm_cfg=None, conv_cfg=None):
+        super().__init__()
+        self.conv1 = SparseConv3dParams(inplanes, planes, 3, subm=True)
+        self.bn1 = build_norm_layer(norm_cfg, planes)[1]
+        self.conv2 = SparseConv3dParams(planes, planes, 3, subm=True)
+        self.bn2 = build_norm_layer(norm_cfg, planes)[1]
+        self.relu = nn.ReLU(inplace=True)
+
+
+class _Level:
+    __slots__ = ('dims', 'ncells', 'cap', 'index', 'coors', 'count', 'nbr', 'mask')
+
+
+@MIDDLE_ENCODERS.register_module()
+class SparseEncoderCustom(nn.Module):
+    def __init__(self, in_channels, sparse_shape, order=('conv', 'norm', 'act'),
+                 norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), base_channels=16, output_channels=128,
+                 encoder_channels=((16,), (32, 32, 32), (64, 64, 64), (64, 64, 64)),
+                 encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1)), block_type='conv_module',
+                 init_cfg=None):
+        super().__init__()
+        assert block_type in ['conv_module', 'basicblock']
+        assert isinstance(order, tuple) and set(order) == {'conv', 'norm', 'act'}
+        self.sparse_shape = [int(s) for s in sparse_shape]
+        self.in_channels = in_channels
+        self.order = order
+        self.base_channels = base_channels
+        self.output_channels = output_channels
+        self.encoder_channels = encoder_channels
+        self.encoder_paddings = encoder_paddings
+        self.stage_num = len(encoder_channels)
+        self.init_cfg = init_cfg
+        self.conv_input = make_sparse_convmodule(in_channels, base_channels, 3, norm_cfg=norm_cfg, padding=1,
+                                                 indice_key='subm1', conv_type='SubMConv3d')
+        enc_out = self.make_encoder_layers(make_sparse_convmodule, norm_cfg, base_channels, block_type=block_type)
+        self.conv_out = make_sparse_convmodule(enc_out, output_channels, kernel_size=(3, 1, 1), stride=(2, 1, 1),
+                                               norm_cfg=norm_cfg, padding=0, indice_key='spconv_down2',
+                                               conv_type='SparseConv3d')
+        self._packed = {}
+        self.last_counts = None
+
+    def make_encoder_layers(self, make_block, norm_cfg, in_channels, block_type='conv_module',
+                            conv_cfg=dict(type='SubMConv3d')):
+        self.encoder_layers = nn.Sequential()
+        for i, blocks in enumerate(self.encoder_channels):
+            blocks_list = []
+            for j, out_channels in enumerate(tuple(blocks)):
+                padding = tuple(self.encoder_paddings[i])[j]
+                if i != 0 and j == 0 and block_type == 'conv_module':
+                    blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg, stride=2,
+                                                  padding=padding, indice_key=f'spconv{i + 1}', conv_type='SparseConv3d'))
+                elif block_type == 'basicblock':
+                    if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
+                        blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg, stride=2,
+                                                      padding=padding, indice_key=f'spconv{i + 1}', conv_type='SparseConv3d'))
+                    else:
+                        blocks_list.append(SparseBasicBlock(out_channels, out_channels, norm_cfg=norm_cfg, conv_cfg=conv_cfg))
+                else:
+                    blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg, padding=padding,
+                                                  indice_key=f'subm{i + 1}', conv_type='SubMConv3d'))
+                in_channels = out_channels
+            self.encoder_layers.add_module(f'encoder_layer{i + 1}', nn.Sequential(*blocks_list))
+        return out_channels
+
+    # ------------------------------------------------------------------ execution plan
+    def layer_plan(self):
+        """Flat list of (conv, bn, save_identity, add_identity) in execution order."""
+        plan = [(self.conv_input[0], self.conv_input[1], False, False)]
+        for stage in self.encoder_layers:
+            for blk in stage:
+                if isinstance(blk, SparseBasicBlock):
+                    plan.append((blk.conv1, blk.bn1, True, False))
+                    plan.append((blk.conv2, blk.bn2, False, True))
+                else:
+                    plan.append((blk[0], blk[1], False, False))
+        plan.append((self.conv_out[0], self.conv_out[1], False, False))
+        return plan
+
+    def load_state_dict(self, *a, **k):
+        self._packed = {}
+        return super().load_state_dict(*a, **k)
+
+    def _pack(self, device, precision):
+        key = (str(device), precision)
+        if key in self._packed:
+            return self._packed[key]
+        lib = L.load()
+        packed = []
+        for li, (conv, bn, _, _) in enumerate(self.layer_plan()):
+            w = conv.kio().to(device)
+            s = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).to(device)
+            bias = (bn.bias.detach().float().to(device) - bn.running_mean.detach().float().to(device) * s).contiguous()
+            w = (w * s.view(1, 1, -1)).contiguous()
+            # layer 0 reads the raw fp32 voxel features (few channels): SIMT path, bf16 output
+            use_umma = precision == 'bf16' and li > 0 and conv.in_channels in (16, 32, 64, 128) \
+                and conv.out_channels in (16, 32, 64, 128)
+            if use_umma:
+                wp = torch.empty(w.numel(), dtype=torch.bfloat16, device=device)
+                L.check(lib.srf_pack_weight_bf16(L.ptr(w), w.shape[0], w.shape[1], w.shape[2], L.ptr(wp),
+                                                 L.stream_ptr()), 'srf_pack_weight_bf16')
+                w = wp
+            packed.append(dict(w=w, bias=bias, umma=use_umma))
+        self._packed[key] = packed
+        return packed
+
+    @staticmethod
+    def _out_dims(dims, k, s, p):
+        return [dims[0]] + [(dims[1 + j] + 2 * p[j] - k[j]) // s[j] + 1 for j in range(3)]
+
+    def _new_level(self, dims, cap, device):
+        lv = _Level()
+        lv.dims = [int(d) for d in dims]
+        lv.ncells = lv.dims[0] * lv.dims[1] * lv.dims[2] * lv.dims[3]
+        lv.cap = max(128, (int(min(cap, lv.ncells)) + 127) // 128 * 128)
+        lv.index = torch.empty(L.load().srf_index_bytes(lv.ncells), dtype=torch.uint8, device=device)
+        lv.coors = torch.empty((lv.cap, 4), dtype=torch.int32, device=device)
+        lv.count = torch.zeros((1,), dtype=torch.int32, device=device)
+        lv.nbr = None
+        lv.mask = None
+        return lv
+
+    def _rulebook(self, lv_in, lv_out, k, s, p, device):
+        kvol = k[0] * k[1] * k[2]
+        nbr = torch.empty((kvol, lv_out.cap), dtype=torch.int32, device=device)
+        mask = torch.empty((lv_out.cap // 128,), dtype=torch.int32, device=device)
+        L.check(L.load().srf_rulebook_build(L.ptr(lv_in.index), L.i4(lv_in.dims), None, L.ptr(lv_out.coors), lv_out.cap,
+                                            L.ptr(lv_out.count), L.i3(k), L.i3(s), L.i3(p), L.ptr(nbr), L.ptr(mask),
+                                            L.stream_ptr()), 'srf_rulebook_build')
+        return nbr, mask
+
+    def forward(self, voxel_features, coors, batch_size, num_voxels=None, precision=None, return_levels=False):
+        """voxel_features (N,C) f32, coors (N,4) int32 (b,z,y,x), batch_size -> (B, C*D, H, W).
+
+        num_voxels: optional (1,) int32 CUDA tensor with the number of valid rows (rows past
+        it are ignored) -- lets padded voxelizer outputs flow in without a host sync."""
+        if self.training:
+            raise NotImplementedError('srfdet_b200 implements the inference path only')
+        precision = precision or registry.get_precision()
+        lib = L.load()
+        dev = voxel_features.device
+        st = L.stream_ptr()
+        feats_in = voxel_features.contiguous().float()
+        coors = coors.contiguous().int()
+        n = feats_in.shape[0]
+        batch_size = int(batch_size)
+        packed = self._pack(dev, precision)
+        plan = self.layer_plan()
+        d_n_in = L.ptr(num_voxels) if num_voxels is not None else None
+
+        # level 0: index of the input coordinates, sorted coordinate list, rank->row perm
+        lv = self._new_level([batch_size] + self.sparse_shape, n, dev)
+        L.check(lib.srf_index_clear(L.ptr(lv.index), lv.ncells, st), 'srf_index_clear')
+        L.check(lib.srf_index_mark(L.ptr(lv.index), L.i4(lv.dims), L.ptr(coors), n, d_n_in, st), 'srf_index_mark')
+        L.check(lib.srf_index_finalize(L.ptr(lv.index), lv.ncells, L.ptr(lv.count), st), 'srf_index_finalize')
+        L.check(lib.srf_index_emit_coors(L.ptr(lv.index), L.i4(lv.dims), L.ptr(lv.coors), lv.cap, st), 'srf_index_emit_coors')
+        perm = torch.empty((lv.cap,), dtype=torch.int32, device=dev)
+        L.check(lib.srf_index_perm(L.ptr(lv.index), L.i4(lv.dims), L.ptr(coors), n, d_n_in, L.ptr(perm), st), 'srf_index_perm')
+        x = torch.empty((lv.cap, self.in_channels), dtype=torch.float32, device=dev)
+        L.check(lib.srf_gather_rows(L.ptr(feats_in), L.ptr(perm), L.ptr(lv.count), lv.cap, self.in_channels, L.ptr(x), st),
+                'srf_gather_rows')
+        x_dtype = L.F32
+        act_dtype = L.BF16 if precision == 'bf16' else L.F32
+        act_torch = torch.bfloat16 if precision == 'bf16' else torch.float32
+        levels = [lv]
+        identity = None
+        dense = None
+        for li, (conv, bn, save_id, add_id) in enumerate(plan):
+            pk = packed[li]
+            k, s, p = conv.kernel_size, conv.stride, conv.padding
+            last = li == len(plan) - 1
+            if conv.subm:
+                lv_out = lv
+                if lv.nbr is None:
+                    lv.nbr, lv.mask = self._rulebook(lv, lv, k, s, p, dev)
+                nbr, mask = lv.nbr, lv.mask
+            else:
+                od = self._out_dims(lv.dims, k, s, p)
+                growth = 1
+                for j in range(3):
+                    growth *= min(k[j], (k[j] + s[j] - 1) // s[j])
+                lv_out = self._new_level(od, lv.cap * growth, dev)
+                L.check(lib.srf_index_clear(L.ptr(lv_out.index), lv_out.ncells, st), 'srf_index_clear')
+                L.check(lib.srf_index_mark_strided(L.ptr(lv_out.index), L.i4(od), L.ptr(lv.coors), lv.cap, L.ptr(lv.count),
+                                                   L.i3(k), L.i3(s), L.i3(p), st), 'srf_index_mark_strided')
+                L.check(lib.srf_index_finalize(L.ptr(lv_out.index), lv_out.ncells, L.ptr(lv_out.count), st), 'srf_index_finalize')
+                L.check(lib.srf_index_emit_coors(L.ptr(lv_out.index), L.i4(od), L.ptr(lv_out.coors), lv_out.cap, st),
+                        'srf_index_emit_coors')
+                nbr, mask = self._rulebook(lv, lv_out, k, s, p, dev)
+                levels.append(lv_out)
+            if save_id:
+                identity = x
+            a = L.ConvArgs()
+            a.in_ = L.ptr(x)
+            a.in_dtype = x_dtype
+            a.cin, a.cout, a.kvol = conv.in_channels, conv.out_channels, k[0] * k[1] * k[2]
+            a.nbr, a.tile_mask = L.ptr(nbr), L.ptr(mask)
+            a.cap_out = lv_out.cap
+            a.d_n_out = L.ptr(lv_out.count)
+            a.w, a.bias = L.ptr(pk['w']), L.ptr(pk['bias'])
+            a.residual = L.ptr(identity) if add_id else None
+            a.relu = 1
+            a.out_dtype = act_dtype
+            for j in range(4):
+                a.out_dims[j] = lv_out.dims[j]
+            if last:
+                dense = torch.zeros((batch_size, conv.out_channels * lv_out.dims[1], lv_out.dims[2], lv_out.dims[3]),
+                                    dtype=torch.float32, device=dev)
+                a.dense = L.ptr(dense)
+                a.out_coors = L.ptr(lv_out.coors)
+                a.out = None
+                y = None
+            else:
+                y = torch.empty((lv_out.cap, conv.out_channels), dtype=act_torch, device=dev)
+                a.out = L.ptr(y)
+            if pk['umma']:
+                assert x_dtype == L.BF16
+                L.check(lib.srf_spconv_bf16(ctypes.byref(a), st), 'srf_spconv_bf16')
+            else:
+                L.check(lib.srf_spconv_f32(ctypes.byref(a), st), 'srf_spconv_f32')
+            x, x_dtype, lv = y, act_dtype, lv_out
+        self.last_counts = [l.count for l in levels]
+        if return_levels:
+            return dense, levels
+        return dense

