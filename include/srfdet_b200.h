@@ -228,6 +228,7 @@ typedef struct srf_pyramid {
   float stride[4];      /* featmap_strides */
   int32_t n_levels;     /* pooler.num_inputs */
   int32_t channels;
+  int32_t channels_last; /* 1: maps are (n_img, H_l, W_l, C) in memory (torch.channels_last tensors, C % 4 == 0) */
 } srf_pyramid;
 
 /* Generic SingleRoIExtractor + RoIAlign(7x7, sampling_ratio 2, avg, aligned): replaces

@@ -40,7 +40,7 @@ class ConvArgs(Structure):
 
 class Pyramid(Structure):
     _fields_ = [('feat', c_void_p * 4), ('h', c_int32 * 4), ('w', c_int32 * 4), ('stride', c_float * 4),
-                ('n_levels', c_int32), ('channels', c_int32)]
+                ('n_levels', c_int32), ('channels', c_int32), ('channels_last', c_int32)]
 
 
 _I4 = c_int32 * 4

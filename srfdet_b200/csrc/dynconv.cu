@@ -80,9 +80,133 @@ __global__ void __launch_bounds__(256) dynconv_interact_kernel(const TR* __restr
   for (int e = threadIdx.x; e < DC_ROWS * c; e += blockDim.x) st_f<TO>(o + e, sF[e]);
 }
 
+// Register-tiled variant for the production shapes (C,D) = (128,32), (256,64): each thread
+// owns RPT rows x 1 column of F.P1 and RPT rows x 4 columns of f.P2, operands are read from
+// shared memory as float4 (row operands broadcast), ~4 FMA per shared-memory load.
+template <int C, int D, typename TR, typename TP, typename TO>
+__global__ void __launch_bounds__(256) dynconv_interact_tiled_kernel(const TR* __restrict__ roi, const TP* __restrict__ params,
+                                                                    const float* __restrict__ ln1_w, const float* __restrict__ ln1_b,
+                                                                    const float* __restrict__ ln2_w, const float* __restrict__ ln2_b,
+                                                                    TO* __restrict__ out) {
+  constexpr int G1 = 256 / D;                         // row groups in phase 1
+  constexpr int RPT1 = (DC_ROWS + G1 - 1) / G1;
+  constexpr int G2 = 256 / (C / 4);                   // row groups in phase 3
+  constexpr int RPT2 = (DC_ROWS + G2 - 1) / G2;
+  constexpr int FP = C + 4;                           // padded row pitch of F (keeps float4 alignment)
+  constexpr int TP_ = D + 4;
+  extern __shared__ __align__(16) float sm[];
+  float* sF = sm;                      // 52 x FP (rows >= 49 zero)
+  float* sP1 = sF + 52 * FP;           // C x D
+  float* sP2 = sP1 + C * D;            // D x C
+  float* sT = sP2 + C * D;             // 52 x TP_
+  const int k = blockIdx.x;
+  const TR* r = roi + (size_t)k * DC_ROWS * C;
+  const TP* p = params + (size_t)k * 2 * C * D;
+  for (int e = threadIdx.x; e < 52 * C; e += 256) {
+    int s = e / C, i = e - s * C;
+    sF[s * FP + i] = s < DC_ROWS ? to_f<TR>(r[e]) : 0.f;
+  }
+  for (int e = threadIdx.x; e < 2 * C * D; e += 256) sP1[e] = to_f<TP>(p[e]);
+  __syncthreads();
+  {  // phase 1: T = F . P1
+    const int j = threadIdx.x % D, g = threadIdx.x / D;
+    float acc[RPT1];
+#pragma unroll
+    for (int q = 0; q < RPT1; ++q) acc[q] = 0.f;
+    const int r0 = g * RPT1;
+    for (int i = 0; i < C; i += 4) {
+      const float b0 = sP1[(i + 0) * D + j], b1 = sP1[(i + 1) * D + j], b2 = sP1[(i + 2) * D + j], b3 = sP1[(i + 3) * D + j];
+#pragma unroll
+      for (int q = 0; q < RPT1; ++q) {
+        const int row = min(r0 + q, 51);
+        const float4 f = *reinterpret_cast<const float4*>(sF + row * FP + i);
+        acc[q] = fmaf(f.x, b0, fmaf(f.y, b1, fmaf(f.z, b2, fmaf(f.w, b3, acc[q]))));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RPT1; ++q)
+      if (r0 + q < 52) sT[(r0 + q) * TP_ + j] = acc[q];
+  }
+  __syncthreads();
+  {  // LayerNorm(D) + ReLU per row, one warp per row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int row = warp; row < DC_ROWS; row += 8) {
+      float* x = sT + row * TP_;
+      float s = 0.f;
+      for (int j = lane; j < D; j += 32) s += x[j];
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / D;
+      float v = 0.f;
+      for (int j = lane; j < D; j += 32) { float d = x[j] - mean; v += d * d; }
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const float rstd = rsqrtf(v / D + 1e-5f);
+      for (int j = lane; j < D; j += 32) x[j] = fmaxf((x[j] - mean) * rstd * __ldg(ln1_w + j) + __ldg(ln1_b + j), 0.f);
+    }
+  }
+  __syncthreads();
+  {  // phase 3: G = T . P2  -> sF (F is dead)
+    const int jc = (threadIdx.x % (C / 4)) * 4, g = threadIdx.x / (C / 4);
+    float acc[RPT2][4];
+#pragma unroll
+    for (int q = 0; q < RPT2; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
+    const int r0 = g * RPT2;
+    for (int i = 0; i < D; i += 4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(sP2 + (i + 0) * C + jc);
+      const float4 w1 = *reinterpret_cast<const float4*>(sP2 + (i + 1) * C + jc);
+      const float4 w2 = *reinterpret_cast<const float4*>(sP2 + (i + 2) * C + jc);
+      const float4 w3 = *reinterpret_cast<const float4*>(sP2 + (i + 3) * C + jc);
+#pragma unroll
+      for (int q = 0; q < RPT2; ++q) {
+        const int row = min(r0 + q, 51);
+        const float4 t = *reinterpret_cast<const float4*>(sT + row * TP_ + i);
+        acc[q][0] = fmaf(t.x, w0.x, fmaf(t.y, w1.x, fmaf(t.z, w2.x, fmaf(t.w, w3.x, acc[q][0]))));
+        acc[q][1] = fmaf(t.x, w0.y, fmaf(t.y, w1.y, fmaf(t.z, w2.y, fmaf(t.w, w3.y, acc[q][1]))));
+        acc[q][2] = fmaf(t.x, w0.z, fmaf(t.y, w1.z, fmaf(t.z, w2.z, fmaf(t.w, w3.z, acc[q][2]))));
+        acc[q][3] = fmaf(t.x, w0.w, fmaf(t.y, w1.w, fmaf(t.z, w2.w, fmaf(t.w, w3.w, acc[q][3]))));
+      }
+    }
+    __syncthreads();   // every thread is done reading sF-independent data; now overwrite F rows
+#pragma unroll
+    for (int q = 0; q < RPT2; ++q)
+      if (r0 + q < DC_ROWS) *reinterpret_cast<float4*>(sF + (r0 + q) * FP + jc) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+  }
+  __syncthreads();
+  {  // LayerNorm(C) + ReLU per row, write out
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TO* o = out + (size_t)k * DC_ROWS * C;
+    for (int row = warp; row < DC_ROWS; row += 8) {
+      const float* x = sF + row * FP;
+      float s = 0.f;
+      for (int j = lane; j < C; j += 32) s += x[j];
+      for (int o2 = 16; o2; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+      const float mean = s / C;
+      float v = 0.f;
+      for (int j = lane; j < C; j += 32) { float d = x[j] - mean; v += d * d; }
+      for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+      const float rstd = rsqrtf(v / C + 1e-5f);
+      for (int j = lane; j < C; j += 32)
+        st_f<TO>(o + (size_t)row * C + j, fmaxf((x[j] - mean) * rstd * __ldg(ln2_w + j) + __ldg(ln2_b + j), 0.f));
+    }
+  }
+}
+
+template <int C, int D, typename TR, typename TP, typename TO>
+static int launch_dc_tiled(const void* roi, const void* params, int k, const float* a, const float* b, const float* e,
+                           const float* f, void* out, cudaStream_t st) {
+  size_t smem = (size_t)(52 * (C + 4) + 2 * C * D + 52 * (D + 4)) * sizeof(float);
+  auto kern = dynconv_interact_tiled_kernel<C, D, TR, TP, TO>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) { set_error("dynconv: cannot get %zu B shared memory: %s", smem, cudaGetErrorString(err)); return SRF_ERR_CUDA; }
+  SRF_COUNT(1);
+  kern<<<k, 256, smem, st>>>((const TR*)roi, (const TP*)params, a, b, e, f, (TO*)out);
+  return SRF_OK;
+}
+
 template <typename TR, typename TP, typename TO>
 static int launch_dc(const void* roi, const void* params, int k, int c, int d, const float* a, const float* b,
                      const float* e, const float* f, void* out, cudaStream_t st) {
+  if (c == 128 && d == 32) return launch_dc_tiled<128, 32, TR, TP, TO>(roi, params, k, a, b, e, f, out, st);
+  if (c == 256 && d == 64) return launch_dc_tiled<256, 64, TR, TP, TO>(roi, params, k, a, b, e, f, out, st);
   size_t smem = (size_t)(DC_ROWS * c + 2 * c * d + DC_ROWS * d) * sizeof(float);
   auto kern = dynconv_interact_kernel<TR, TP, TO>;
   if (smem > 48 * 1024) {

@@ -115,7 +115,7 @@ struct IgemmArgs {
   int D, H, W;
 };
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool SPARSE>
 struct Cfg {
   static constexpr int CH = CIN / 8;  // 16-byte chunks per A row
   static constexpr int A_PAD = CH == 2 ? 64 : (CH == 4 ? 32 : 16);
@@ -123,26 +123,36 @@ struct Cfg {
   static constexpr int A_BYTES = CH * A_LBO;
   static constexpr int B_LBO = COUT * 16;
   static constexpr int B_BYTES = CH * B_LBO;
-  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
-  static constexpr int BUDGET = (STAGE_BYTES * 3 > 96 * 1024) ? 200 * 1024 : 96 * 1024;
-  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  // sparse conv with small channel counts: all 27 weight tiles stay resident in shared
+  // memory for the CTA's lifetime instead of being re-streamed with every ring slot
+  static constexpr bool WRES = SPARSE && (27 * B_BYTES <= 56 * 1024);
+  static constexpr int W_BYTES = WRES ? 27 * B_BYTES : 0;
+  static constexpr int STAGE_BYTES = (A_BYTES + (WRES ? 0 : B_BYTES) + 127) / 128 * 128;
+  static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES > 100 * 1024) ? 200 * 1024 : 104 * 1024;
+  static constexpr int STAGES_RAW = (BUDGET - W_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int LAG = STAGES - 1;
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 128;
+  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
   // kind::f16: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), K-major both, N>>3 @17, M>>4 @24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
 };
 
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
-  using C = Cfg<CIN, COUT>;
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int CIN, int COUT, bool SPARSE>
+__global__ void __launch_bounds__(288, (Cfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1)
+igemm_umma_kernel(const IgemmArgs a) {
+  using C = Cfg<CIN, COUT, SPARSE>;
   constexpr int S = C::STAGES;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-  uint8_t* stage_base = smem;
-  uint64_t* bars = (uint64_t*)(smem + S * C::STAGE_BYTES);
+  uint8_t* w_res = smem;
+  uint8_t* stage_base = smem + C::W_BYTES;
+  uint64_t* bars = (uint64_t*)(stage_base + S * C::STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * S + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_rows = a.nbr ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
+  const int m_rows = SPARSE ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
   const int m_tiles = (m_rows + 127) >> 7;
   const int total_tiles = m_tiles * a.n_tiles;
 
@@ -163,6 +173,14 @@ __global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (C::WRES) {
+    // resident weights: packed global image == shared image ([k][CIN/8][COUT][8] bf16)
+    const uint4* wsrc = reinterpret_cast<const uint4*>(a.w);
+    uint4* wdst = reinterpret_cast<uint4*>(w_res);
+    const int n16 = a.kvol * (C::B_BYTES / 16);
+    for (int j = threadIdx.x; j < n16; j += blockDim.x) wdst[j] = __ldg(wsrc + j);
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -176,24 +194,33 @@ __global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile % m_tiles, nt = tile / m_tiles;
       const int row = mt * 128 + pt;
-      const uint32_t mask = (a.nbr && a.tile_mask) ? __ldg(a.tile_mask + mt) : 0xffffffffu;
-      for (int k = 0; k < a.kvol; ++k) {
-        if (a.nbr && !((mask >> k) & 1u)) continue;
+      uint32_t mask = 0xffffffffu;
+      int idx[27];
+      if (SPARSE) {
+        // all neighbour indices of this row are fetched up front (27 independent loads in
+        // flight) so the ring never waits on an index -> address dependency
+        if (a.tile_mask) mask = __ldg(a.tile_mask + mt);
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+          idx[k] = -1;
+          if (k < a.kvol && ((mask >> k) & 1u) && row < m_rows) idx[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
+        }
+      }
+      auto fill = [&](int k, int src_row) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        int idx;
-        if (a.nbr) idx = row < m_rows ? __ldg(a.nbr + (size_t)k * a.cap_out + row) : -1;
-        else idx = row < m_rows ? row : -1;
-        const __nv_bfloat16* src = idx >= 0 ? a.in + (size_t)idx * a.in_stride + (size_t)k * a.k_stride : a.in;
-        const uint32_t nbytes = idx >= 0 ? 16u : 0u;
+        const __nv_bfloat16* src = src_row >= 0 ? a.in + (size_t)src_row * a.in_stride + (size_t)k * a.k_stride : a.in;
+        const uint32_t nbytes = src_row >= 0 ? 16u : 0u;
         const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < C::CH; ++c) cp_async16(sa + c * C::A_LBO + pt * 16, src + c * 8, nbytes);
-        const uint32_t sb = sa + C::A_BYTES;
-        const __nv_bfloat16* wsrc = a.w + ((size_t)nt * a.kvol + k) * (size_t)(CIN * COUT);
+        for (int c = 0; c < C::CH; ++c) cp_async16_ca(sa + c * C::A_LBO + pt * 16, src + c * 8, nbytes);
+        if (!C::WRES) {
+          const uint32_t sb = sa + C::A_BYTES;
+          const __nv_bfloat16* wsrc = a.w + ((size_t)nt * a.kvol + k) * (size_t)(CIN * COUT);
 #pragma unroll
-        for (int j = pt; j < C::CH * COUT; j += 128) cp_async16(sb + j * 16, wsrc + (size_t)j * 8, 16u);
+          for (int j = pt; j < C::CH * COUT; j += 128) cp_async16(sb + j * 16, wsrc + (size_t)j * 8, 16u);
+        }
         cp_async_commit();
         if (it >= C::LAG) {
           cp_async_wait<C::LAG>();
@@ -201,6 +228,15 @@ __global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
           mbar_arrive(full_bar((it - C::LAG) % S));
         }
         ++it;
+      };
+      if (SPARSE) {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+          if (k < a.kvol && ((mask >> k) & 1u)) fill(k, idx[k]);
+        }
+      } else {
+        const int src_row = row < m_rows ? row : -1;
+        for (int k = 0; k < a.kvol; ++k) fill(k, src_row);
       }
     }
     cp_async_wait<0>();
@@ -211,7 +247,7 @@ __global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
     int it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile % m_tiles;
-      const uint32_t mask = (a.nbr && a.tile_mask) ? __ldg(a.tile_mask + mt) : 0xffffffffu;
+      const uint32_t mask = (SPARSE && a.tile_mask) ? __ldg(a.tile_mask + mt) : 0xffffffffu;
       const int buf = tcount & 1;
       const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
       mbar_wait(tempty_bar(buf), tph ^ 1u);
@@ -219,14 +255,14 @@ __global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * COUT);
       uint32_t accumulate = 0;
       for (int k = 0; k < a.kvol; ++k) {
-        if (a.nbr && !((mask >> k) & 1u)) continue;
+        if (SPARSE && !((mask >> k) & 1u)) continue;
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t sb = C::WRES ? smem_u32(w_res) + (uint32_t)k * C::B_BYTES : sa + C::A_BYTES;
 #pragma unroll
           for (int j = 0; j < CIN / 16; ++j) {
             uint64_t ad = make_desc(sa + j * 2 * C::A_LBO, C::A_LBO, 128);
@@ -337,12 +373,12 @@ __global__ void __launch_bounds__(288, 1) igemm_umma_kernel(const IgemmArgs a) {
   }
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool SPARSE>
 static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
-  using C = Cfg<CIN, COUT>;
+  using C = Cfg<CIN, COUT, SPARSE>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_umma_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm_umma_kernel<CIN, COUT, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("igemm<%d,%d>: cannot set %d B dynamic smem: %s", CIN, COUT, C::SMEM_BYTES, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
     configured = true;
   }
@@ -355,14 +391,15 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   if (grid > host_tiles) grid = host_tiles;
   if (grid < 1) grid = 1;
   SRF_COUNT(1);
-  igemm_umma_kernel<CIN, COUT><<<grid, 288, C::SMEM_BYTES, st>>>(a);
+  igemm_umma_kernel<CIN, COUT, SPARSE><<<grid, 288, C::SMEM_BYTES, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("igemm<%d,%d> launch failed: %s", CIN, COUT, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
   return SRF_OK;
 }
 
+template <bool SPARSE>
 static int dispatch_igemm(int cin, int cout, const IgemmArgs& a, int host_tiles, cudaStream_t st) {
-#define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm<ci, co>(a, host_tiles, st);
+#define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm<ci, co, SPARSE>(a, host_tiles, st);
   SRF_CASE(16, 16) SRF_CASE(16, 32) SRF_CASE(32, 32) SRF_CASE(32, 64) SRF_CASE(64, 64) SRF_CASE(64, 128)
   SRF_CASE(128, 128) SRF_CASE(16, 128) SRF_CASE(32, 128) SRF_CASE(64, 32) SRF_CASE(128, 64) SRF_CASE(128, 32)
   SRF_CASE(64, 16) SRF_CASE(32, 16) SRF_CASE(16, 64) SRF_CASE(128, 16)
@@ -408,7 +445,7 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
   a.D = c->out_dims[1];
   a.H = c->out_dims[2];
   a.W = c->out_dims[3];
-  return dispatch_igemm(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream);
+  return dispatch_igemm<true>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream);
 }
 
 int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
@@ -435,7 +472,7 @@ int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_pack
   a.out = out;
   a.out_bf16 = out_dtype == SRF_BF16;
   a.out_stride = n;
-  return dispatch_igemm(tk, tn, a, cdiv(m, 128) * (n / tn), (cudaStream_t)stream);
+  return dispatch_igemm<false>(tk, tn, a, cdiv(m, 128) * (n / tn), (cudaStream_t)stream);
 }
 
 }  // extern "C"

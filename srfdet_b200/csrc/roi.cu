@@ -19,6 +19,7 @@ struct Pyr {
   int h[4], w[4];
   float scale[4];  // 1 / stride
   int n_levels, channels;
+  int channels_last;  // maps are (n_img, H, W, C) in memory (torch channels_last) instead of (n_img, C, H, W)
 };
 
 struct Taps {
@@ -237,6 +238,161 @@ __global__ void __launch_bounds__(256) img_roi_kernel(Pyr p, const float* __rest
   }
 }
 
+// ---------------------------------------------------------------- channels-last maps
+// (n_img, H, W, C) memory order: a bilinear tap is one contiguous C-vector, so lanes own
+// channels (float4 per lane = 128 channels per warp pass, one 512-byte coalesced request per
+// tap), warps stride over the 49 bins and the (K,49,C) output is written with float4 stores.
+struct RoiGeom {
+  int lvl, H, W, live;
+  float x1s, y1s, bw, bh;
+};
+
+__device__ __forceinline__ RoiGeom roi_geom(const Pyr& p, float x1, float y1, float x2, float y2) {
+  RoiGeom g;
+  g.lvl = roi_level(x1, y1, x2, y2, p.n_levels);
+  g.H = p.h[g.lvl];
+  g.W = p.w[g.lvl];
+  const float sc = p.scale[g.lvl];
+  g.x1s = x1 * sc - 0.5f;
+  g.y1s = y1 * sc - 0.5f;
+  const float x2s = x2 * sc - 0.5f, y2s = y2 * sc - 0.5f;
+  g.bw = (x2s - g.x1s) / (float)POOL;
+  g.bh = (y2s - g.y1s) / (float)POOL;
+  g.live = !(x2s < -1.f || g.x1s > (float)g.W || y2s < -1.f || g.y1s > (float)g.H) && (x2s >= g.x1s) && (y2s >= g.y1s);
+  return g;
+}
+
+// accumulate one bin of one RoI into acc[NP] (float4 = 4 channels per lane per pass)
+template <int NP>
+__device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_base, const RoiGeom& g, int bin, int C,
+                                                  int lane, float4* acc) {
+  Taps t;
+  bin_taps(bin, g.x1s, g.y1s, g.bw, g.bh, g.H, g.W, t);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    if (t.wt[q] == 0.f) continue;
+    const float w = t.wt[q] * 0.25f;
+    const float4* src = reinterpret_cast<const float4*>(img_base + (size_t)t.off[q] * C) + lane;
+#pragma unroll
+    for (int pss = 0; pss < NP; ++pss) {
+      if ((pss * 32 + lane) * 4 < C) {
+        const float4 v = __ldg(src + pss * 32);
+        acc[pss].x = fmaf(w, v.x, acc[pss].x);
+        acc[pss].y = fmaf(w, v.y, acc[pss].y);
+        acc[pss].z = fmaf(w, v.z, acc[pss].z);
+        acc[pss].w = fmaf(w, v.w, acc[pss].w);
+      }
+    }
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void store_bin_cl(float* __restrict__ out, int k, int bin, int C, int lane, int channel_last,
+                                             const float4* acc) {
+#pragma unroll
+  for (int pss = 0; pss < NP; ++pss) {
+    const int c = (pss * 32 + lane) * 4;
+    if (c >= C) continue;
+    if (channel_last) {
+      *reinterpret_cast<float4*>(out + ((size_t)k * NBIN + bin) * C + c) = acc[pss];
+    } else {
+      float* o = out + ((size_t)k * C + c) * NBIN + bin;
+      o[0] = acc[pss].x; o[NBIN] = acc[pss].y; o[2 * NBIN] = acc[pss].z; o[3 * NBIN] = acc[pss].w;
+    }
+  }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256) bev_roi_cl_kernel(Pyr p, float* __restrict__ boxes, const float* __restrict__ rois_in,
+                                                        int n_prop, int box_dim, Range rg, int mutate, float* __restrict__ out,
+                                                        int channel_last, float* __restrict__ rois_out) {
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float x1, y1, x2, y2;
+  int img;
+  if (rois_in) {   // generic SingleRoIExtractor form
+    const float* r = rois_in + (size_t)k * 5;
+    img = (int)r[0]; x1 = r[1]; y1 = r[2]; x2 = r[3]; y2 = r[4];
+  } else {
+    float* b = boxes + (size_t)k * box_dim;
+    float bx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bx[j] = b[j];
+    __syncthreads();
+    const float cx = bx[0] * rg.span[0] + rg.lo[0], cy = bx[1] * rg.span[1] + rg.lo[1], cz = bx[2] * rg.span[2] + rg.lo[2];
+    if (mutate && threadIdx.x == 0) { b[0] = cx; b[1] = cy; b[2] = cz; }
+    float cor[8][3];
+    box_corners(cx, cy, cz, bx[3], bx[4], bx[5], bx[6], bx[7], cor);
+    x1 = INFINITY; y1 = INFINITY; x2 = -INFINITY; y2 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = (cor[i][0] - rg.lo[0]) / rg.vs[0], y = (cor[i][1] - rg.lo[1]) / rg.vs[1];
+      x1 = fminf(x1, x); x2 = fmaxf(x2, x); y1 = fminf(y1, y); y2 = fmaxf(y2, y);
+    }
+    img = k / n_prop;
+    if (rois_out && threadIdx.x == 0) {
+      float* r = rois_out + (size_t)k * 5;
+      r[0] = (float)img; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
+    }
+  }
+  RoiGeom g = roi_geom(p, x1, y1, x2, y2);
+  g.live = 1;   // single-map form: out-of-range samples already carry zero weight
+  const float* base = p.feat[g.lvl] + (size_t)img * g.H * g.W * p.channels;
+  for (int bin = warp; bin < NBIN; bin += 8) {
+    float4 acc[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bin_accumulate_cl<NP>(base, g, bin, p.channels, lane, acc);
+    store_bin_cl<NP>(out, k, bin, p.channels, lane, channel_last, acc);
+  }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256) img_roi_cl_kernel(Pyr p, const float* __restrict__ boxes, int n_prop, int box_dim,
+                                                        const float* __restrict__ lidar2img, int n_cam, Range rg,
+                                                        float* __restrict__ out, int channel_last, float* __restrict__ rois_out) {
+  __shared__ RoiGeom sg[16];
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < n_cam) {
+    const int cam = threadIdx.x;
+    const float* b = boxes + (size_t)k * box_dim;
+    const float cx = b[0] * rg.span[0] + rg.lo[0], cy = b[1] * rg.span[1] + rg.lo[1], cz = b[2] * rg.span[2] + rg.lo[2];
+    float cor[8][3];
+    box_corners(cx, cy, cz, b[3], b[4], b[5], b[6], b[7], cor);
+    const float* L = lidar2img + (size_t)cam * 16;
+    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float X = cor[i][0], Y = cor[i][1], Z = cor[i][2];
+      float u = __ldg(L + 0) * X + __ldg(L + 1) * Y + __ldg(L + 2) * Z + __ldg(L + 3);
+      float v = __ldg(L + 4) * X + __ldg(L + 5) * Y + __ldg(L + 6) * Z + __ldg(L + 7);
+      float d = __ldg(L + 8) * X + __ldg(L + 9) * Y + __ldg(L + 10) * Z + __ldg(L + 11);
+      d = fmaxf(d, 1e-5f);
+      u = u / d; v = v / d;
+      x1 = fminf(x1, u); x2 = fmaxf(x2, u); y1 = fminf(y1, v); y2 = fmaxf(y2, v);
+    }
+    if (rois_out) {
+      float* r = rois_out + ((size_t)cam * n_prop + k) * 5;
+      r[0] = (float)cam; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
+    }
+    sg[cam] = roi_geom(p, x1, y1, x2, y2);
+  }
+  __syncthreads();
+  for (int bin = warp; bin < NBIN; bin += 8) {
+    float4 acc[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int cam = 0; cam < n_cam; ++cam) {
+      const RoiGeom g = sg[cam];
+      if (!g.live) continue;
+      const float* base = p.feat[g.lvl] + (size_t)cam * g.H * g.W * p.channels;
+      bin_accumulate_cl<NP>(base, g, bin, p.channels, lane, acc);
+    }
+    store_bin_cl<NP>(out, k, bin, p.channels, lane, channel_last, acc);
+  }
+}
+
 static int make_pyr(Pyr* d, const srf_pyramid* p) {
   if (!p || p->n_levels < 1 || p->n_levels > 4 || p->channels < 1) return -1;
   for (int l = 0; l < 4; ++l) {
@@ -249,6 +405,8 @@ static int make_pyr(Pyr* d, const srf_pyramid* p) {
   }
   d->n_levels = p->n_levels;
   d->channels = p->channels;
+  d->channels_last = p->channels_last;
+  if (p->channels_last && (p->channels % 4 != 0 || p->channels > 256)) return -1;
   return 0;
 }
 
@@ -281,6 +439,13 @@ int srf_roi_extract(const srf_pyramid* p, const float* rois, int32_t k, float* o
   SRF_CHECK_ARG(rois && out && k >= 0, "srf_roi_extract: bad args");
   if (k == 0) return SRF_OK;
   SRF_COUNT(1);
+  if (d.channels_last) {
+    Range rg = {};
+    if (d.channels <= 128) bev_roi_cl_kernel<1><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, out, channel_last, nullptr);
+    else bev_roi_cl_kernel<2><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, out, channel_last, nullptr);
+    SRF_LAUNCH_CHECK();
+    return SRF_OK;
+  }
   roi_extract_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(d, rois, k, out, channel_last);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
@@ -296,6 +461,12 @@ int srf_bev_roi_features(const srf_pyramid* p, float* boxes, int32_t batch, int3
   Range rg;
   make_range(&rg, pc_range, voxel_size);
   SRF_COUNT(1);
+  if (d.channels_last) {
+    if (d.channels <= 128) bev_roi_cl_kernel<1><<<batch * n_prop, 256, 0, (cudaStream_t)stream>>>(d, boxes, nullptr, n_prop, box_dim, rg, mutate, out, channel_last, rois_out);
+    else bev_roi_cl_kernel<2><<<batch * n_prop, 256, 0, (cudaStream_t)stream>>>(d, boxes, nullptr, n_prop, box_dim, rg, mutate, out, channel_last, rois_out);
+    SRF_LAUNCH_CHECK();
+    return SRF_OK;
+  }
   bev_roi_kernel<<<batch * n_prop, 256, 0, (cudaStream_t)stream>>>(d, boxes, n_prop, box_dim, rg, mutate, out, channel_last, rois_out);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
@@ -313,6 +484,13 @@ int srf_img_roi_features(const srf_pyramid* p, const float* boxes, int32_t n_pro
   make_range(&rg, pc_range, nullptr);
   cudaStream_t st = (cudaStream_t)stream;
   SRF_COUNT(1);
+  if (d.channels_last) {
+    SRF_CHECK_ARG(n_cam <= 16, "srf_img_roi_features: at most 16 cameras");
+    if (d.channels <= 128) img_roi_cl_kernel<1><<<n_prop, 256, 0, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
+    else img_roi_cl_kernel<2><<<n_prop, 256, 0, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
+    SRF_LAUNCH_CHECK();
+    return SRF_OK;
+  }
   if (d.channels <= 128)
     img_roi_kernel<16><<<n_prop, 256, 0, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
   else

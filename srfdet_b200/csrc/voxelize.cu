@@ -293,6 +293,7 @@ int srf_geom_init(srf_geom* g, const float vs[3], const float range[6]) {
 
 int srf_dynamic_voxelize(const float* points, int32_t n, int32_t c, const srf_geom* g, int32_t batch_idx,
                          int32_t* coors, void* stream) {
+  if (n == 0) return SRF_OK;
   SRF_CHECK_ARG(points && g && coors && n >= 0 && c >= 3, "srf_dynamic_voxelize: bad args");
   GeomDev gd;
   SRF_CHECK_ARG(fill_geom(&gd, g) == 0, "srf_dynamic_voxelize: bad geometry");
@@ -313,7 +314,12 @@ int srf_hard_voxelize(const float* points, int32_t n, int32_t c, const srf_geom*
                       int32_t max_voxels, int32_t batch_idx, float* voxels, int32_t* coors,
                       int32_t* num_points, float* mean, int32_t* point2voxel, int32_t* d_voxel_num,
                       void* ws, size_t ws_bytes, void* stream) {
-  SRF_CHECK_ARG(points && g && coors && num_points && d_voxel_num && ws, "srf_hard_voxelize: null arg");
+  SRF_CHECK_ARG(g && d_voxel_num, "srf_hard_voxelize: null arg");
+  if (n == 0) {
+    SRF_CUDA(cudaMemsetAsync(d_voxel_num, 0, 4, (cudaStream_t)stream));
+    return SRF_OK;
+  }
+  SRF_CHECK_ARG(points && coors && num_points && ws, "srf_hard_voxelize: null arg");
   SRF_CHECK_ARG(n >= 0 && c >= 3 && c <= 8, "srf_hard_voxelize: need 3 <= c <= 8 (got %d)", c);
   SRF_CHECK_ARG(max_points > 0 && max_voxels > 0, "srf_hard_voxelize: max_points/max_voxels must be > 0");
   GeomDev gd;

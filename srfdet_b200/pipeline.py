@@ -80,7 +80,7 @@ class RegionFeaturePipeline:
     projection of srfdet_voxel_nusc_LC.  Weights: torch.manual_seed(0) random init with
     non-trivial BatchNorm statistics (no checkpoints offline)."""
 
-    def __init__(self, kind='nusc', fusion=False, device='cuda', precision=None, seed=0):
+    def __init__(self, kind='nusc', fusion=False, device='cuda', precision=None, seed=0, channels_last=True):
         self.kind, self.fusion, self.device = kind, fusion, torch.device(device)
         self.precision = precision or registry.get_precision()
         h = HEAD_CFG[kind]
@@ -97,10 +97,14 @@ class RegionFeaturePipeline:
         self.fuse = [torch.nn.Linear(2 * self.C, self.C).to(self.device).eval() for _ in range(N_STAGES)] if fusion else None
         self._fuse_cache = [dict() for _ in range(N_STAGES)]
         # synthetic FPN pyramids (stand-ins for the dense backbones)
-        self.bev_feats = [torch.as_tensor(f).to(self.device) for f in synth.feature_pyramid(seed + 10, self.C, h['bev_hw'], 4)]
+        # channels_last=True: the maps are torch.channels_last tensors (logical NCHW, NHWC in memory),
+        # i.e. what a channels_last FPN emits for free; False = the reference's contiguous NCHW.
+        self.channels_last = channels_last
+        fmt = (lambda t: t.contiguous(memory_format=torch.channels_last)) if channels_last else (lambda t: t)
+        self.bev_feats = [fmt(torch.as_tensor(f).to(self.device)) for f in synth.feature_pyramid(seed + 10, self.C, h['bev_hw'], 4)]
         self.img_feats = self.lidar2img = None
         if fusion:
-            self.img_feats = [torch.as_tensor(f).to(self.device)
+            self.img_feats = [fmt(torch.as_tensor(f[0]).to(self.device)).unsqueeze(0)
                               for f in synth.feature_pyramid(seed + 11, self.C, (232, 400), 4, lead=(1, 6))]
             self.lidar2img = torch.as_tensor(synth.lidar2img(6, 1)[0]).to(self.device)
         self.stage_boxes = [torch.as_tensor(synth.proposals(seed + 20 + s, N_PROP, self.box_dim, 1)).to(self.device)
@@ -114,8 +118,8 @@ class RegionFeaturePipeline:
                     vfe=sd(self.detector.pts_voxel_encoder),
                     dynconv=[sd(m) for m in self.dynconvs],
                     fuse=[sd(m) for m in self.fuse] if self.fusion else None,
-                    bev_feats=[f.cpu().numpy() for f in self.bev_feats],
-                    img_feats=[f.cpu().numpy() for f in self.img_feats] if self.fusion else None,
+                    bev_feats=[f.contiguous().cpu().numpy() for f in self.bev_feats],
+                    img_feats=[f.contiguous().cpu().numpy() for f in self.img_feats] if self.fusion else None,
                     lidar2img=self.lidar2img.cpu().numpy() if self.fusion else None,
                     stage_boxes=[b.cpu().numpy() for b in self.stage_boxes], prop0=self.prop0.cpu().numpy())
 

@@ -25,10 +25,16 @@ def _pyramid(feats, strides, n_levels):
     n_levels = min(n_levels, len(feats))
     c = feats[0].shape[-3]
     keep = []
+    # torch.channels_last maps (NHWC in memory) are consumed in place by the coalesced kernels
+    cl = c % 4 == 0 and c <= 256 and all(
+        f.dim() == 4 and f.shape[1] > 1 and not f.is_contiguous() and f.is_contiguous(memory_format=torch.channels_last)
+        for f in feats[:n_levels])
+    p.channels_last = int(cl)
     for l in range(n_levels):
         f = feats[l]
         assert f.dtype == torch.float32 and f.shape[-3] == c, 'feature maps must be fp32 with equal channels'
-        f = f.contiguous()
+        if not cl:
+            f = f.contiguous()
         keep.append(f)
         p.feat[l] = f.data_ptr()
         p.h[l], p.w[l] = f.shape[-2], f.shape[-1]

@@ -111,6 +111,7 @@ class SparseEncoderCustom(nn.Module):
                                                conv_type='SparseConv3d')
         self._packed = {}
         self.last_counts = None
+        self.profile = None   # set to a list to record per-conv CUDA events (bench.py roofline pass)
 
     def make_encoder_layers(self, make_block, norm_cfg, in_channels, block_type='conv_module',
                             conv_cfg=dict(type='SubMConv3d')):
@@ -285,11 +286,19 @@ class SparseEncoderCustom(nn.Module):
             else:
                 y = torch.empty((lv_out.cap, conv.out_channels), dtype=act_torch, device=dev)
                 a.out = L.ptr(y)
+            if self.profile is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             if pk['umma']:
                 assert x_dtype == L.BF16
                 L.check(lib.srf_spconv_bf16(ctypes.byref(a), st), 'srf_spconv_bf16')
             else:
                 L.check(lib.srf_spconv_f32(ctypes.byref(a), st), 'srf_spconv_f32')
+            if self.profile is not None:
+                ev1.record()
+                self.profile.append(dict(layer=li, subm=conv.subm, cin=conv.in_channels, cout=conv.out_channels, kvol=a.kvol,
+                                         umma=pk['umma'], nbr=nbr, n_in=lv.count, n_out=lv_out.count, start=ev0, end=ev1,
+                                         in_bytes=2 if x_dtype == L.BF16 else 4, out_bytes=4 if last else (2 if act_dtype == L.BF16 else 4)))
             x, x_dtype, lv = y, act_dtype, lv_out
         self.last_counts = [l.count for l in levels]
         if return_levels:
