@@ -131,7 +131,6 @@ struct Cfg {
   static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES > 100 * 1024) ? 200 * 1024 : 104 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - W_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int LAG = STAGES - 1;
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
@@ -191,21 +190,29 @@ igemm_umma_kernel(const IgemmArgs a) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 128;
     int it = 0;
+    // neighbour indices of this thread's row for the current tile (idx) and the next one
+    // (nxt): 27 independent loads issued a whole tile ahead, so the ring never stalls on an
+    // index -> address dependency.
+    int idx[27], nxt[27];
+    uint32_t mask = 0xffffffffu, mask_nxt = 0xffffffffu;
+    auto load_idx = [&](int tile, int* dst, uint32_t& m) {
+      m = 0xffffffffu;
+      if (!SPARSE) return;
+      const bool live = tile < total_tiles;
+      const int mt = live ? tile % m_tiles : 0;
+      const int row = mt * 128 + pt;
+      if (a.tile_mask) m = live ? __ldg(a.tile_mask + mt) : 0u;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        dst[k] = -1;
+        if (live && k < a.kvol && ((m >> k) & 1u) && row < m_rows) dst[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
+      }
+    };
+    load_idx(blockIdx.x, idx, mask);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile % m_tiles, nt = tile / m_tiles;
       const int row = mt * 128 + pt;
-      uint32_t mask = 0xffffffffu;
-      int idx[27];
-      if (SPARSE) {
-        // all neighbour indices of this row are fetched up front (27 independent loads in
-        // flight) so the ring never waits on an index -> address dependency
-        if (a.tile_mask) mask = __ldg(a.tile_mask + mt);
-#pragma unroll
-        for (int k = 0; k < 27; ++k) {
-          idx[k] = -1;
-          if (k < a.kvol && ((mask >> k) & 1u) && row < m_rows) idx[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
-        }
-      }
+      load_idx(tile + gridDim.x, nxt, mask_nxt);
       auto fill = [&](int k, int src_row) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -221,12 +228,9 @@ igemm_umma_kernel(const IgemmArgs a) {
 #pragma unroll
           for (int j = pt; j < C::CH * COUT; j += 128) cp_async16(sb + j * 16, wsrc + (size_t)j * 8, 16u);
         }
-        cp_async_commit();
-        if (it >= C::LAG) {
-          cp_async_wait<C::LAG>();
-          fence_proxy_async();
-          mbar_arrive(full_bar((it - C::LAG) % S));
-        }
+        // the hardware arrives on full[s] for this thread when its copies have landed
+        // (cutlass::arch::cpasync_barrier_arrive_noinc pattern): producers never wait on data
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
         ++it;
       };
       if (SPARSE) {
@@ -234,14 +238,15 @@ igemm_umma_kernel(const IgemmArgs a) {
         for (int k = 0; k < 27; ++k) {
           if (k < a.kvol && ((mask >> k) & 1u)) fill(k, idx[k]);
         }
+#pragma unroll
+        for (int k = 0; k < 27; ++k) idx[k] = nxt[k];
+        mask = mask_nxt;
       } else {
         const int src_row = row < m_rows ? row : -1;
         for (int k = 0; k < a.kvol; ++k) fill(k, src_row);
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = it > C::LAG ? it - C::LAG : 0; j < it; ++j) mbar_arrive(full_bar(j % S));
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
     int it = 0, tcount = 0;
