@@ -168,8 +168,9 @@ int srf_rulebook_build(const void* in_index, const int32_t in_dims_host[4], cons
  * `out` (needs out_coors + out_dims_host).
  * ---------------------------------------------------------------------------------- */
 typedef struct srf_conv_args {
-  const void* in;          /* (n_in, cin) f32 | bf16 */
+  const void* in;          /* (in_rows, cin) f32 | bf16 */
   int32_t in_dtype;        /* SRF_F32 | SRF_BF16 */
+  int32_t in_rows;         /* rows allocated behind `in` (TMA bounds; 0 = unknown) */
   int32_t cin, cout, kvol;
   const int32_t* nbr;      /* (kvol, cap_out) */
   const uint32_t* tile_mask;

@@ -31,7 +31,7 @@ class VfeParams(Structure):
 
 
 class ConvArgs(Structure):
-    _fields_ = [('in_', c_void_p), ('in_dtype', c_int32), ('cin', c_int32), ('cout', c_int32), ('kvol', c_int32),
+    _fields_ = [('in_', c_void_p), ('in_dtype', c_int32), ('in_rows', c_int32), ('cin', c_int32), ('cout', c_int32), ('kvol', c_int32),
                 ('nbr', c_void_p), ('tile_mask', c_void_p), ('cap_out', c_int32), ('d_n_out', c_void_p),
                 ('w', c_void_p), ('bias', c_void_p), ('residual', c_void_p), ('relu', c_int32),
                 ('out', c_void_p), ('out_dtype', c_int32), ('dense', c_void_p), ('out_coors', c_void_p),

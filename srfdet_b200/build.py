@@ -27,7 +27,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, 'common.cuh'),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'igemm_common.cuh'),
                                                         os.path.join(HERE, '..', 'include', 'srfdet_b200.h')]
     return any(os.path.getmtime(d) > t for d in deps)
 

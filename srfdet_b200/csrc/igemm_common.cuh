@@ -1,0 +1,183 @@
+// Shared pieces of the tcgen05 implicit-GEMM kernels: PTX wrappers, argument block, fused epilogue.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace srf {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i <- lane (base_lane + i)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ int k_first(int tile, int kvol) { return (int)(((unsigned)tile * 11u) % (unsigned)kvol); }
+
+struct IgemmArgs {
+  const __nv_bfloat16* in;
+  long long in_stride;  // elements between A rows
+  long long k_stride;   // element offset of the k-th slice inside a row (0 for sparse conv)
+  const int32_t* nbr;   // (kvol, cap_out) or null (dense: identity rows)
+  const uint32_t* tile_mask;
+  const int32_t* d_n_out;
+  int cap_out;  // rows bound (multiple of 128 for the sparse path)
+  int m_rows;   // dense: number of rows
+  int kvol;
+  int n_tiles;
+  const __nv_bfloat16* w;  // packed [n_tile][k][CIN/8][COUT][8]
+  const float* bias;
+  const void* residual;
+  int relu, ln;
+  const float *ln_w, *ln_b;
+  void* out;
+  int out_bf16;
+  long long out_stride;
+  float* dense;
+  const int4* out_coors;
+  int D, H, W;
+  int dbg;  // profiling only (SRF_IGEMM_DBG): 1 skip A copies, 2 skip B copies, 4 skip MMA issue, 8 skip epilogue math/stores
+};
+
+// bias / residual / LayerNorm / ReLU and the store of one output row held in registers
+template <int COUT>
+__device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt, float* v) {
+    const int col0 = nt * COUT;
+    if (a.bias) {
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) v[c] += __ldg(a.bias + col0 + c);
+    }
+    if (a.residual) {
+      if (a.out_bf16) {
+        const uint4* rp = (const uint4*)((const __nv_bfloat16*)a.residual + (size_t)row * a.out_stride + col0);
+#pragma unroll
+        for (int c = 0; c < COUT; c += 8) {
+          uint4 u = __ldg(rp + c / 8);
+          uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            v[c + 2 * q] += __uint_as_float(w4[q] << 16);
+            v[c + 2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+          }
+        }
+      } else {
+        const float4* rp = (const float4*)((const float*)a.residual + (size_t)row * a.out_stride + col0);
+#pragma unroll
+        for (int c = 0; c < COUT; c += 4) {
+          float4 u = __ldg(rp + c / 4);
+          v[c] += u.x; v[c + 1] += u.y; v[c + 2] += u.z; v[c + 3] += u.w;
+        }
+      }
+    }
+    if (a.ln) {
+      float mean = 0.f;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) mean += v[c];
+      mean *= (1.f / COUT);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) { float d = v[c] - mean; var += d * d; }
+      const float rstd = rsqrtf(var * (1.f / COUT) + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) v[c] = (v[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) v[c] = fmaxf(v[c], 0.f);
+    }
+    if (a.dense) {
+      const int4 q = __ldg(a.out_coors + row);
+      const size_t hw = (size_t)a.H * a.W;
+      float* dp = a.dense + ((size_t)q.x * COUT * a.D + q.y) * hw + (size_t)q.z * a.W + q.w;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) dp[(size_t)c * a.D * hw] = v[c];
+    } else if (a.out_bf16) {
+      uint4* op = (uint4*)((__nv_bfloat16*)a.out + (size_t)row * a.out_stride + col0);
+#pragma unroll
+      for (int c = 0; c < COUT; c += 8) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[c + 2 * q], v[c + 2 * q + 1]);
+          w4[q] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        op[c / 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    } else {
+      float4* op = (float4*)((float*)a.out + (size_t)row * a.out_stride + col0);
+#pragma unroll
+      for (int c = 0; c < COUT; c += 4) op[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+
+}  // namespace srf

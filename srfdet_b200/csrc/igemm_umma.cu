@@ -22,124 +22,59 @@
 // TMA cannot express this gather (row indices are data dependent and -1 rows must read
 // zeros), hence cp.async into the canonical no-swizzle K-major core-matrix layout:
 //   operand byte offset(row r, 16B chunk c) = c * LBO + r * 16     (SBO = 128)
-#include "common.cuh"
+#include "igemm_common.cuh"
 
 namespace srf {
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns: thread i <- lane (base_lane + i)
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=0
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
-}
-
-struct IgemmArgs {
-  const __nv_bfloat16* in;
-  long long in_stride;  // elements between A rows
-  long long k_stride;   // element offset of the k-th slice inside a row (0 for sparse conv)
-  const int32_t* nbr;   // (kvol, cap_out) or null (dense: identity rows)
-  const uint32_t* tile_mask;
-  const int32_t* d_n_out;
-  int cap_out;  // rows bound (multiple of 128 for the sparse path)
-  int m_rows;   // dense: number of rows
-  int kvol;
-  int n_tiles;
-  const __nv_bfloat16* w;  // packed [n_tile][k][CIN/8][COUT][8]
-  const float* bias;
-  const void* residual;
-  int relu, ln;
-  const float *ln_w, *ln_b;
-  void* out;
-  int out_bf16;
-  long long out_stride;
-  float* dense;
-  const int4* out_coors;
-  int D, H, W;
-};
-
 template <int CIN, int COUT, bool SPARSE>
 struct Cfg {
   static constexpr int CH = CIN / 8;  // 16-byte chunks per A row
+  // For Cin < 64 one ring slot carries G = 64/Cin kernel offsets concatenated along K: the
+  // fixed per-slot handshake (~0.3 us: two mbarrier round trips + tcgen05.commit, measured
+  // with the copies and MMAs stubbed out) is then paid once per 64 input channels.
+  static constexpr int G = SPARSE ? (CIN >= 64 ? 1 : 64 / CIN) : 1;
+  static constexpr int PPT = CH * G;  // 16-byte pieces per producer thread per slot
   static constexpr int A_PAD = CH == 2 ? 64 : (CH == 4 ? 32 : 16);
   static constexpr int A_LBO = 128 * 16 + A_PAD;
-  static constexpr int A_BYTES = CH * A_LBO;
+  static constexpr int A_MEMBER = CH * A_LBO;
+  static constexpr int A_BYTES = G * A_MEMBER;
   static constexpr int B_LBO = COUT * 16;
-  static constexpr int B_BYTES = CH * B_LBO;
-  // sparse conv with small channel counts: all 27 weight tiles stay resident in shared
-  // memory for the CTA's lifetime instead of being re-streamed with every ring slot
-  static constexpr bool WRES = SPARSE && (27 * B_BYTES <= 56 * 1024);
-  static constexpr int W_BYTES = WRES ? 27 * B_BYTES : 0;
-  static constexpr int STAGE_BYTES = (A_BYTES + (WRES ? 0 : B_BYTES) + 127) / 128 * 128;
-  static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES > 100 * 1024) ? 200 * 1024 : 104 * 1024;
-  static constexpr int STAGES_RAW = (BUDGET - W_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int B_MEMBER = CH * B_LBO;
+  // tiny weight sets stay resident in shared memory; otherwise W_k arrives by bulk copy
+  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= 16 * 1024);
+  static constexpr int W_BYTES = WRES ? (27 * B_MEMBER + 127) / 128 * 128 : 0;
+  static constexpr int B_BYTES = WRES ? 0 : G * B_MEMBER;
+  static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
+  static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024;
+  static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
+  static constexpr int SMEM_BYTES = W_BYTES + IDX_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
   // kind::f16: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), K-major both, N>>3 @17, M>>4 @24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
 };
 
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+// next group of up to G active kernel offsets from the remaining-offset bit mask
+template <int G>
+struct Group {
+  int n;
+  int k[G];
+};
+template <int G>
+__device__ __forceinline__ Group<G> pop_group(uint64_t& rem) {
+  Group<G> g;
+  g.n = 0;
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    g.k[i] = 0;
+    if (rem) {
+      g.k[i] = __ffsll((long long)rem) - 1;
+      rem &= rem - 1;
+      g.n = i + 1;
+    }
+  }
+  return g;
 }
 
 template <int CIN, int COUT, bool SPARSE>
@@ -147,10 +82,12 @@ __global__ void __launch_bounds__(288, (Cfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 11
 igemm_umma_kernel(const IgemmArgs a) {
   using C = Cfg<CIN, COUT, SPARSE>;
   constexpr int S = C::STAGES;
+  constexpr int G = C::G;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint8_t* w_res = smem;
-  uint8_t* stage_base = smem + C::W_BYTES;
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem + C::W_BYTES);   // [27][128]
+  uint8_t* stage_base = smem + C::W_BYTES + C::IDX_BYTES;
   uint64_t* bars = (uint64_t*)(stage_base + S * C::STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
   const uint32_t bar0 = smem_u32(bars);
@@ -163,9 +100,10 @@ igemm_umma_kernel(const IgemmArgs a) {
   const int m_rows = SPARSE ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
   const int m_tiles = (m_rows + 127) >> 7;
   const int total_tiles = m_tiles * a.n_tiles;
+  const uint64_t all_k = a.kvol >= 64 ? ~0ull : ((1ull << a.kvol) - 1ull);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 128 + (C::WRES ? 0 : 1)); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -177,7 +115,7 @@ igemm_umma_kernel(const IgemmArgs a) {
     // resident weights: packed global image == shared image ([k][CIN/8][COUT][8] bf16)
     const uint4* wsrc = reinterpret_cast<const uint4*>(a.w);
     uint4* wdst = reinterpret_cast<uint4*>(w_res);
-    const int n16 = a.kvol * (C::B_BYTES / 16);
+    const int n16 = a.kvol * (C::B_MEMBER / 16);
     for (int j = threadIdx.x; j < n16; j += blockDim.x) wdst[j] = __ldg(wsrc + j);
     fence_proxy_async();
   }
@@ -190,43 +128,69 @@ igemm_umma_kernel(const IgemmArgs a) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 128;
     int it = 0;
-    // neighbour indices of this thread's row for the current tile (idx) and the next one
-    // (nxt): 27 independent loads issued a whole tile ahead, so the ring never stalls on an
-    // index -> address dependency.
-    int idx[27], nxt[27];
-    uint32_t mask = 0xffffffffu, mask_nxt = 0xffffffffu;
-    auto load_idx = [&](int tile, int* dst, uint32_t& m) {
-      m = 0xffffffffu;
+    // Neighbour indices: thread pt prefetches the 27 indices of row pt one tile ahead into
+    // registers (27 independent loads in flight), then publishes them to shared memory at
+    // the tile boundary, because the copy mapping below spreads a row over several lanes.
+    int cur[27];
+    uint32_t mask = 0xffffffffu;
+    auto load_idx = [&](int tile) {
+      mask = 0xffffffffu;
       if (!SPARSE) return;
       const bool live = tile < total_tiles;
       const int mt = live ? tile % m_tiles : 0;
       const int row = mt * 128 + pt;
-      if (a.tile_mask) m = live ? __ldg(a.tile_mask + mt) : 0u;
+      if (a.tile_mask) mask = live ? __ldg(a.tile_mask + mt) : 0u;
 #pragma unroll
       for (int k = 0; k < 27; ++k) {
-        dst[k] = -1;
-        if (live && k < a.kvol && ((m >> k) & 1u) && row < m_rows) dst[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
+        cur[k] = -1;
+        if (live && k < a.kvol && ((mask >> k) & 1u) && row < m_rows) cur[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
       }
     };
-    load_idx(blockIdx.x, idx, mask);
+    load_idx(blockIdx.x);
+    // copy mapping: the 128*CH 16-byte pieces of a stage are dealt out so that consecutive
+    // lanes take consecutive pieces of the SAME row (coalesced: a warp instruction touches
+    // 32/CH rows x one contiguous row segment each instead of 32 different rows)
+    constexpr int CHS = C::CH == 2 ? 1 : (C::CH == 4 ? 2 : (C::CH == 8 ? 3 : 4));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile % m_tiles, nt = tile / m_tiles;
-      const int row = mt * 128 + pt;
-      load_idx(tile + gridDim.x, nxt, mask_nxt);
-      auto fill = [&](int k, int src_row) {
+      uint32_t tmask = mask;
+      if (SPARSE) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's indices no longer read
+#pragma unroll
+        for (int k = 0; k < 27; ++k) idx_s[k * 128 + pt] = cur[k];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        load_idx(tile + gridDim.x);                       // next tile's indices, in flight during the fills
+      }
+      auto fill = [&](const Group<G>& g) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const __nv_bfloat16* src = src_row >= 0 ? a.in + (size_t)src_row * a.in_stride + (size_t)k * a.k_stride : a.in;
-        const uint32_t nbytes = src_row >= 0 ? 16u : 0u;
         const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < C::CH; ++c) cp_async16_ca(sa + c * C::A_LBO + pt * 16, src + c * 8, nbytes);
-        if (!C::WRES) {
-          const uint32_t sb = sa + C::A_BYTES;
-          const __nv_bfloat16* wsrc = a.w + ((size_t)nt * a.kvol + k) * (size_t)(CIN * COUT);
+        for (int i = 0; i < C::PPT; ++i) {
+          const int m = i / C::CH;
+          if (m >= g.n || (a.dbg & 1)) continue;
+          const int q = (i % C::CH) * 128 + pt;
+          const int r = q >> CHS, c = q & (C::CH - 1);
+          int src_row;
+          if (SPARSE) src_row = idx_s[g.k[m] * 128 + r];
+          else src_row = (mt * 128 + r < m_rows) ? mt * 128 + r : -1;
+          const __nv_bfloat16* src = src_row >= 0 ? a.in + (size_t)src_row * a.in_stride + (size_t)g.k[m] * a.k_stride + c * 8 : a.in;
+          cp_async16_ca(sa + (m * C::CH + c) * C::A_LBO + r * 16, src, src_row >= 0 ? 16u : 0u);
+        }
+        if (!C::WRES && pt == 0) {
+          // the W_k tiles (packed global image == shared image) arrive by bulk copy (UBLKCP),
+          // tracked by the same barrier through its transaction count
+          const uint32_t fb = full_bar(s);
+          if (a.dbg & 2) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+          } else {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(g.n * C::B_MEMBER)) : "memory");
 #pragma unroll
-          for (int j = pt; j < C::CH * COUT; j += 128) cp_async16(sb + j * 16, wsrc + (size_t)j * 8, 16u);
+            for (int m = 0; m < G; ++m)
+              if (m < g.n)
+                bulk_g2s(sa + C::A_BYTES + m * C::B_MEMBER, a.w + ((size_t)nt * a.kvol + g.k[m]) * (size_t)(CIN * COUT), C::B_MEMBER, fb);
+          }
         }
         // the hardware arrives on full[s] for this thread when its copies have landed
         // (cutlass::arch::cpasync_barrier_arrive_noinc pattern): producers never wait on data
@@ -234,16 +198,18 @@ igemm_umma_kernel(const IgemmArgs a) {
         ++it;
       };
       if (SPARSE) {
-#pragma unroll
-        for (int k = 0; k < 27; ++k) {
-          if (k < a.kvol && ((mask >> k) & 1u)) fill(k, idx[k]);
+        uint64_t rem = (uint64_t)tmask & all_k;
+        while (rem) {
+          const Group<G> g = pop_group<G>(rem);
+          fill(g);
         }
-#pragma unroll
-        for (int k = 0; k < 27; ++k) idx[k] = nxt[k];
-        mask = mask_nxt;
-      } else {
-        const int src_row = row < m_rows ? row : -1;
-        for (int k = 0; k < a.kvol; ++k) fill(k, src_row);
+      } else {               // dense linear: every K slice, in order (kvol may exceed 64)
+        Group<G> g;
+        g.n = 1;
+        for (int k = 0; k < a.kvol; ++k) {
+          g.k[0] = k;
+          fill(g);
+        }
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -259,21 +225,34 @@ igemm_umma_kernel(const IgemmArgs a) {
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * COUT);
       uint32_t accumulate = 0;
-      for (int k = 0; k < a.kvol; ++k) {
-        if (SPARSE && !((mask >> k) & 1u)) continue;
+      uint64_t rem = SPARSE ? ((uint64_t)mask & all_k) : 0ull;
+      int kd = 0;             // dense linear: K-slice counter
+      while (SPARSE ? (rem != 0) : (kd < a.kvol)) {
+        Group<G> g;
+        if (SPARSE) {
+          g = pop_group<G>(rem);
+        } else {
+          g.n = 1;
+          g.k[0] = kd++;
+        }
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
-          const uint32_t sb = C::WRES ? smem_u32(w_res) + (uint32_t)k * C::B_BYTES : sa + C::A_BYTES;
 #pragma unroll
-          for (int j = 0; j < CIN / 16; ++j) {
-            uint64_t ad = make_desc(sa + j * 2 * C::A_LBO, C::A_LBO, 128);
-            uint64_t bd = make_desc(sb + j * 2 * C::B_LBO, C::B_LBO, 128);
-            tc_mma_bf16(tmem_d, ad, bd, C::IDESC, accumulate);
-            accumulate = 1;
+          for (int m = 0; m < G; ++m) {
+            if (m < g.n) {
+              const uint32_t sb = C::WRES ? smem_u32(w_res) + (uint32_t)g.k[m] * C::B_MEMBER : sa + C::A_BYTES + m * C::B_MEMBER;
+#pragma unroll
+              for (int j = 0; j < CIN / 16; ++j) {
+                uint64_t ad = make_desc(sa + (m * C::CH + 2 * j) * C::A_LBO, C::A_LBO, 128);
+                uint64_t bd = make_desc(sb + j * 2 * C::B_LBO, C::B_LBO, 128);
+                if (!(a.dbg & 4)) tc_mma_bf16(tmem_d, ad, bd, C::IDESC, accumulate);
+                accumulate = 1;
+              }
+            }
           }
           tc_commit(empty_bar(s));
         }
@@ -301,74 +280,7 @@ igemm_umma_kernel(const IgemmArgs a) {
       // accumulator is in registers: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
-      if (row < m_rows) {
-        const int col0 = nt * COUT;
-        if (a.bias) {
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) v[c] += __ldg(a.bias + col0 + c);
-        }
-        if (a.residual) {
-          if (a.out_bf16) {
-            const uint4* rp = (const uint4*)((const __nv_bfloat16*)a.residual + (size_t)row * a.out_stride + col0);
-#pragma unroll
-            for (int c = 0; c < COUT; c += 8) {
-              uint4 u = __ldg(rp + c / 8);
-              uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[c + 2 * q] += __uint_as_float(w4[q] << 16);
-                v[c + 2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
-              }
-            }
-          } else {
-            const float4* rp = (const float4*)((const float*)a.residual + (size_t)row * a.out_stride + col0);
-#pragma unroll
-            for (int c = 0; c < COUT; c += 4) {
-              float4 u = __ldg(rp + c / 4);
-              v[c] += u.x; v[c + 1] += u.y; v[c + 2] += u.z; v[c + 3] += u.w;
-            }
-          }
-        }
-        if (a.ln) {
-          float mean = 0.f;
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) mean += v[c];
-          mean *= (1.f / COUT);
-          float var = 0.f;
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) { float d = v[c] - mean; var += d * d; }
-          const float rstd = rsqrtf(var * (1.f / COUT) + 1e-5f);
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) v[c] = (v[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
-        }
-        if (a.relu) {
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) v[c] = fmaxf(v[c], 0.f);
-        }
-        if (a.dense) {
-          const int4 q = __ldg(a.out_coors + row);
-          const size_t hw = (size_t)a.H * a.W;
-          float* dp = a.dense + ((size_t)q.x * COUT * a.D + q.y) * hw + (size_t)q.z * a.W + q.w;
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) dp[(size_t)c * a.D * hw] = v[c];
-        } else if (a.out_bf16) {
-          uint4* op = (uint4*)((__nv_bfloat16*)a.out + (size_t)row * a.out_stride + col0);
-#pragma unroll
-          for (int c = 0; c < COUT; c += 8) {
-            uint32_t w4[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[c + 2 * q], v[c + 2 * q + 1]);
-              w4[q] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            op[c / 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-          }
-        } else {
-          float4* op = (float4*)((float*)a.out + (size_t)row * a.out_stride + col0);
-#pragma unroll
-          for (int c = 0; c < COUT; c += 4) op[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        }
-      }
+      if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v);
     }
   }
   tc_fence_before();
@@ -402,6 +314,308 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   return SRF_OK;
 }
 
+// =====================================================================================
+// TMA variant: the A operand is gathered by the TMA unit itself
+// (cp.async.bulk.tensor.2d ... tile::gather4: four independent row coordinates per
+// instruction, out-of-range / negative rows are zero-filled by the hardware) straight into
+// the 128B/64B/32B-swizzled K-major layout tcgen05 reads, and the W_k tile arrives with one
+// cp.async.bulk.  No LSU instruction touches operand data: on B200 the LDGSTS path tops out
+// near 20-25 B/clk/SM (profiles/), which was the limiter of the cp.async variant above.
+//   warps 0-3 epilogue | warps 4-7 neighbour-index prefetch (+ warp 4 issues all TMA) | warp 8 MMA
+// =====================================================================================
+template <int CIN, int COUT, bool SPARSE>
+struct TCfg {
+  static constexpr int KP = CIN >= 64 ? 64 : CIN;   // elements per swizzled panel row
+  static constexpr int ROWB = KP * 2;               // 128 / 64 / 32 bytes
+  static constexpr int NP = CIN / KP;               // K panels per stage
+  static constexpr int PANEL_BYTES = 128 * ROWB;
+  static constexpr int A_BYTES = NP * PANEL_BYTES;
+  static constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);  // UMMA::LayoutType
+  static constexpr int SBO = 8 * ROWB;
+  static constexpr int CH = CIN / 8;
+  static constexpr int B_LBO = COUT * 16;
+  static constexpr int B_BYTES = CH * B_LBO;
+  static constexpr bool WRES = SPARSE && (27 * B_BYTES <= 56 * 1024);
+  static constexpr int W_BYTES = WRES ? (27 * B_BYTES + 1023) / 1024 * 1024 : 0;
+  static constexpr int IDX_BYTES = SPARSE ? 14 * 1024 : 0;
+  static constexpr int STAGE_BYTES = (A_BYTES + (WRES ? 0 : B_BYTES) + 1023) / 1024 * 1024;
+  static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 200 * 1024 : 104 * 1024;
+  static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = W_BYTES + IDX_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr uint32_t TX_BYTES = A_BYTES + (WRES ? 0 : B_BYTES);
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+// K-major swizzled operand descriptor: LBO is ignored (encoded 1), SBO = 8 rows
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) |
+         (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int col, int4 rows) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(col), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w)
+      : "memory");
+}
+
+template <int CIN, int COUT, bool SPARSE>
+__global__ void __launch_bounds__(288, (TCfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1)
+igemm_tma_kernel(const __grid_constant__ CUtensorMap tmapA, const IgemmArgs a) {
+  using C = TCfg<CIN, COUT, SPARSE>;
+  constexpr int S = C::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_res = smem;
+  int32_t* idx_s = reinterpret_cast<int32_t*>(smem + C::W_BYTES);   // [27][128]
+  uint8_t* stage_base = smem + C::W_BYTES + C::IDX_BYTES;
+  uint64_t* bars = (uint64_t*)(stage_base + S * C::STAGE_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * S + 2 + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_rows = SPARSE ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
+  const int m_tiles = (m_rows + 127) >> 7;
+  const int total_tiles = m_tiles * a.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (C::WRES) {
+    const uint4* wsrc = reinterpret_cast<const uint4*>(a.w);
+    uint4* wdst = reinterpret_cast<uint4*>(w_res);
+    const int n16 = a.kvol * (C::B_BYTES / 16);
+    for (int j = threadIdx.x; j < n16; j += blockDim.x) wdst[j] = __ldg(wsrc + j);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------ index prefetch + TMA issue
+    const int pt = threadIdx.x - 128;
+    int it = 0;
+    int cur[27];
+    uint32_t mask = 0xffffffffu;
+    auto load_idx = [&](int tile) {
+      mask = 0xffffffffu;
+      if (!SPARSE) return;
+      const bool live = tile < total_tiles;
+      const int mt = live ? tile % m_tiles : 0;
+      const int row = mt * 128 + pt;
+      if (a.tile_mask) mask = live ? __ldg(a.tile_mask + mt) : 0u;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        cur[k] = -1;
+        if (live && k < a.kvol && ((mask >> k) & 1u) && row < m_rows) cur[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
+      }
+    };
+    load_idx(blockIdx.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const uint32_t tmask = mask;
+      if (SPARSE) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // warp 4 has issued every stage of the previous tile
+#pragma unroll
+        for (int k = 0; k < 27; ++k) idx_s[k * 128 + pt] = cur[k];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        load_idx(tile + gridDim.x);
+      }
+      if (warp == 4) {
+        int k = k_first(tile, a.kvol);
+        for (int j = 0; j < a.kvol; ++j, k = (k + 1 == a.kvol) ? 0 : k + 1) {
+          if (SPARSE && !((tmask >> k) & 1u)) continue;
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
+          if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(s)), "r"(C::TX_BYTES) : "memory");
+            if (!C::WRES) bulk_g2s(sa + C::A_BYTES, a.w + ((size_t)nt * a.kvol + k) * (size_t)(CIN * COUT), C::B_BYTES, full_bar(s));
+          }
+          __syncwarp();
+          int4 r4;
+          if (SPARSE) {
+            r4 = *reinterpret_cast<const int4*>(idx_s + k * 128 + 4 * lane);
+          } else {
+            const int r0 = mt * 128 + 4 * lane;
+            r4 = make_int4(r0, r0 + 1, r0 + 2, r0 + 3);
+          }
+          const int col0 = (int)((long long)k * a.k_stride);
+#pragma unroll
+          for (int p = 0; p < C::NP; ++p)
+            tma_gather4(sa + p * C::PANEL_BYTES + lane * 4 * C::ROWB, &tmapA, full_bar(s), col0 + p * C::KP, r4);
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile % m_tiles;
+      const uint32_t mask = (SPARSE && a.tile_mask) ? __ldg(a.tile_mask + mt) : 0xffffffffu;
+      const int buf = tcount & 1;
+      const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
+      mbar_wait(tempty_bar(buf), tph ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * COUT);
+      uint32_t accumulate = 0;
+      int k = k_first(tile, a.kvol);
+      for (int j = 0; j < a.kvol; ++j, k = (k + 1 == a.kvol) ? 0 : k + 1) {
+        if (SPARSE && !((mask >> k) & 1u)) continue;
+        const int s = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
+          const uint32_t sb = C::WRES ? smem_u32(w_res) + (uint32_t)k * C::B_BYTES : sa + C::A_BYTES;
+#pragma unroll
+          for (int j = 0; j < CIN / 16; ++j) {
+            const int p = (j * 16) / C::KP, off = ((j * 16) % C::KP) * 2;
+            uint64_t ad = make_desc_sw(sa + p * C::PANEL_BYTES + off, C::SBO, C::LAYOUT);
+            uint64_t bd = make_desc(sb + j * 2 * C::B_LBO, C::B_LBO, 128);
+            if (!(a.dbg & 4)) tc_mma_bf16(tmem_d, ad, bd, C::IDESC, accumulate);
+            accumulate = 1;
+          }
+          tc_commit(empty_bar(s));
+        }
+        __syncwarp();
+        accumulate = 1;
+        ++it;
+      }
+      if (lane == 0) tc_commit(tfull_bar(buf));
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int buf = tcount & 1;
+      const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), tph);
+      tc_fence_after();
+      const int row = mt * 128 + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * COUT);
+      float v[COUT];
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 16) tc_ld16(taddr + c0, v + c0);
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major (rows, cols) tensor, box = {box_cols, 1}: the gather4 form (each of the
+// four row coordinates of an instruction fetches one box)
+static int make_gather_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, long long row_stride_elems,
+                            int box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return SRF_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)row_stride_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld stride=%lld box=%d", (int)r, rows, cols, row_stride_elems, box_cols); return SRF_ERR_CUDA; }
+  return SRF_OK;
+}
+
+template <int CIN, int COUT, bool SPARSE>
+static int launch_igemm_tma(const IgemmArgs& a, int host_tiles, long long in_rows, long long in_cols, cudaStream_t st) {
+  using C = TCfg<CIN, COUT, SPARSE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tma_kernel<CIN, COUT, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("igemm_tma<%d,%d>: cannot set %d B dynamic smem: %s", CIN, COUT, C::SMEM_BYTES, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
+    configured = true;
+  }
+  alignas(64) CUtensorMap tmap;
+  int rc = make_gather_tmap(&tmap, a.in, in_rows, in_cols, a.in_stride, C::KP);
+  if (rc) return rc;
+  int per_sm = (227 * 1024) / (C::SMEM_BYTES + 1024);
+  int by_tmem = 512 / C::TMEM_COLS;
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = sm_count() * per_sm;
+  if (grid > host_tiles) grid = host_tiles;
+  if (grid < 1) grid = 1;
+  SRF_COUNT(1);
+  igemm_tma_kernel<CIN, COUT, SPARSE><<<grid, 288, C::SMEM_BYTES, st>>>(tmap, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("igemm_tma<%d,%d> launch failed: %s", CIN, COUT, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
+  return SRF_OK;
+}
+
+template <bool SPARSE>
+static int dispatch_igemm_tma(int cin, int cout, const IgemmArgs& a, int host_tiles, long long in_rows, long long in_cols, cudaStream_t st) {
+#define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm_tma<ci, co, SPARSE>(a, host_tiles, in_rows, in_cols, st);
+  SRF_CASE(16, 16) SRF_CASE(16, 32) SRF_CASE(32, 32) SRF_CASE(32, 64) SRF_CASE(64, 64) SRF_CASE(64, 128)
+  SRF_CASE(128, 128) SRF_CASE(16, 128) SRF_CASE(32, 128) SRF_CASE(64, 32) SRF_CASE(128, 64) SRF_CASE(128, 32)
+  SRF_CASE(64, 16) SRF_CASE(32, 16) SRF_CASE(16, 64) SRF_CASE(128, 16)
+#undef SRF_CASE
+  set_error("igemm_tma: unsupported channel pair cin=%d cout=%d (each must be 16/32/64/128)", cin, cout);
+  return SRF_ERR_UNSUPPORTED;
+}
+
+// The TMA-gather variant is correct but measured SLOWER on B200 (gather4 issues at ~45 clk per
+// instruction = <= 11 B/clk/SM for 128-byte rows; profiles/r01_notes.md), so the cp.async
+// gather + bulk-copied weights variant is the default.  SRF_IGEMM_TMA=1 selects the TMA one.
+static bool use_ldgsts() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SRF_IGEMM_TMA");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+// NOTE: a register-staged variant (LDG.128 -> registers -> STS.128 + fence.proxy.async, 4 barrier
+// arrivals per slot) was built and measured 1.5x SLOWER than the cp.async ring on B200
+// (profiles/r01_notes.md), so it is not part of the build.
+
 template <bool SPARSE>
 static int dispatch_igemm(int cin, int cout, const IgemmArgs& a, int host_tiles, cudaStream_t st) {
 #define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm<ci, co, SPARSE>(a, host_tiles, st);
@@ -429,6 +643,7 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
   SRF_CHECK_ARG(c->cap_out > 0 && c->cap_out % 128 == 0, "srf_spconv_bf16: cap_out must be a multiple of 128");
   SRF_CHECK_ARG(!c->dense || c->out_coors, "srf_spconv_bf16: dense output needs out_coors");
   IgemmArgs a = {};
+  { const char* e = getenv("SRF_IGEMM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.in = (const __nv_bfloat16*)c->in;
   a.in_stride = c->cin;
   a.k_stride = 0;
@@ -450,6 +665,10 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
   a.D = c->out_dims[1];
   a.H = c->out_dims[2];
   a.W = c->out_dims[3];
+  if (!use_ldgsts()) {
+    const long long in_rows = c->in_rows > 0 ? c->in_rows : (1ll << 30);
+    return dispatch_igemm_tma<true>(c->cin, c->cout, a, c->cap_out / 128, in_rows, c->cin, (cudaStream_t)stream);
+  }
   return dispatch_igemm<true>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream);
 }
 
@@ -461,6 +680,7 @@ int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_pack
   SRF_CHECK_ARG(k % tk == 0 && n % tn == 0, "srf_linear_bf16: n=%d k=%d not tileable", n, k);
   SRF_CHECK_ARG(!(epi & 2) || (n == tn && ln_w && ln_b), "srf_linear_bf16: fused LayerNorm needs n <= 128 and ln weights");
   IgemmArgs a = {};
+  { const char* e = getenv("SRF_IGEMM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.in = (const __nv_bfloat16*)a_bf16;
   a.in_stride = k;
   a.k_stride = tk;
@@ -477,6 +697,7 @@ int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_pack
   a.out = out;
   a.out_bf16 = out_dtype == SRF_BF16;
   a.out_stride = n;
+  if (!use_ldgsts()) return dispatch_igemm_tma<false>(tk, tn, a, cdiv(m, 128) * (n / tn), m, k, (cudaStream_t)stream);
   return dispatch_igemm<false>(tk, tn, a, cdiv(m, 128) * (n / tn), (cudaStream_t)stream);
 }
 

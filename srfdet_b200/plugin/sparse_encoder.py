@@ -266,6 +266,7 @@ class SparseEncoderCustom(nn.Module):
             a = L.ConvArgs()
             a.in_ = L.ptr(x)
             a.in_dtype = x_dtype
+            a.in_rows = x.shape[0]
             a.cin, a.cout, a.kvol = conv.in_channels, conv.out_channels, k[0] * k[1] * k[2]
             a.nbr, a.tile_mask = L.ptr(nbr), L.ptr(mask)
             a.cap_out = lv_out.cap
