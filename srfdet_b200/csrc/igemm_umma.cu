@@ -99,7 +99,10 @@ igemm_umma_kernel(const IgemmArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_rows = SPARSE ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
   const int m_tiles = (m_rows + 127) >> 7;
-  const int total_tiles = m_tiles * a.n_tiles;
+  const int ksp = SPARSE ? 1 : max(a.k_splits, 1);
+  const int kper = (a.kvol + ksp - 1) / ksp;   // K slices per split
+  const int mn_tiles = m_tiles * a.n_tiles;
+  const int total_tiles = mn_tiles * ksp;
   const uint64_t all_k = a.kvol >= 64 ? ~0ull : ((1ull << a.kvol) - 1ull);
 
   if (threadIdx.x == 0) {
@@ -152,7 +155,7 @@ igemm_umma_kernel(const IgemmArgs a) {
     // 32/CH rows x one contiguous row segment each instead of 32 different rows)
     constexpr int CHS = C::CH == 2 ? 1 : (C::CH == 4 ? 2 : (C::CH == 8 ? 3 : 4));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int mt = tile % m_tiles, nt = (tile % mn_tiles) / m_tiles, ks = tile / mn_tiles;
       uint32_t tmask = mask;
       if (SPARSE) {
         asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's indices no longer read
@@ -206,7 +209,7 @@ igemm_umma_kernel(const IgemmArgs a) {
       } else {               // dense linear: every K slice, in order (kvol may exceed 64)
         Group<G> g;
         g.n = 1;
-        for (int k = 0; k < a.kvol; ++k) {
+        for (int k = ks * kper; k < min(a.kvol, (ks + 1) * kper); ++k) {
           g.k[0] = k;
           fill(g);
         }
@@ -226,8 +229,9 @@ igemm_umma_kernel(const IgemmArgs a) {
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * COUT);
       uint32_t accumulate = 0;
       uint64_t rem = SPARSE ? ((uint64_t)mask & all_k) : 0ull;
-      int kd = 0;             // dense linear: K-slice counter
-      while (SPARSE ? (rem != 0) : (kd < a.kvol)) {
+      int kd = (tile / mn_tiles) * kper;             // dense linear: K-slice counter of this split
+      const int kd_end = min(a.kvol, (tile / mn_tiles + 1) * kper);
+      while (SPARSE ? (rem != 0) : (kd < kd_end)) {
         Group<G> g;
         if (SPARSE) {
           g = pop_group<G>(rem);
@@ -267,7 +271,7 @@ igemm_umma_kernel(const IgemmArgs a) {
     // ------------------------------------------------------------------ epilogue
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int mt = tile % m_tiles, nt = (tile % mn_tiles) / m_tiles;
       const int buf = tcount & 1;
       const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
       mbar_wait(tfull_bar(buf), tph);
@@ -673,7 +677,8 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
 }
 
 int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
-                    int32_t epi, const float* ln_w, const float* ln_b, void* out, int32_t out_dtype, void* stream) {
+                    int32_t epi, const float* ln_w, const float* ln_b, void* out, int32_t out_dtype, int32_t k_splits,
+                    void* stream) {
   SRF_CHECK_ARG(a_bf16 && w_packed && out && m >= 0 && k > 0 && n > 0, "srf_linear_bf16: bad args");
   if (m == 0) return SRF_OK;
   int tk = srf_linear_tile_k(k), tn = srf_linear_tile_n(n);
@@ -697,8 +702,14 @@ int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_pack
   a.out = out;
   a.out_bf16 = out_dtype == SRF_BF16;
   a.out_stride = n;
+  a.k_splits = 1;
+  if (k_splits > 1 && use_ldgsts()) {
+    SRF_CHECK_ARG(epi == 0 && !bias && out_dtype == SRF_F32, "srf_linear_bf16: split-K needs epi=0, no bias and a zeroed f32 output");
+    const int kper = (a.kvol + k_splits - 1) / k_splits;
+    a.k_splits = (a.kvol + kper - 1) / kper;   // every split owns at least one K slice
+  }
   if (!use_ldgsts()) return dispatch_igemm_tma<false>(tk, tn, a, cdiv(m, 128) * (n / tn), m, k, (cudaStream_t)stream);
-  return dispatch_igemm<false>(tk, tn, a, cdiv(m, 128) * (n / tn), (cudaStream_t)stream);
+  return dispatch_igemm<false>(tk, tn, a, cdiv(m, 128) * (n / tn) * a.k_splits, (cudaStream_t)stream);
 }
 
 }  // extern "C"

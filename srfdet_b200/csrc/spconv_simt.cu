@@ -100,6 +100,63 @@ __global__ void __launch_bounds__(128) spconv_f32_kernel(ConvDev a) {
   }
 }
 
+// First layer of the encoder (conv_input: Cin = 4/5 raw voxel features -> 16): far too few
+// input channels for a tensor-core tile.  One thread per output row keeps the COUT
+// accumulators in registers, the whole (kvol, cin, COUT) weight set lives in shared memory
+// and is read as broadcast float4; offsets without a neighbour are skipped per lane.
+template <int COUT>
+__global__ void __launch_bounds__(128) spconv_smallcin_kernel(ConvDev a) {
+  extern __shared__ __align__(16) float sW[];   // kvol * cin * COUT
+  const int nw = a.kvol * a.cin * COUT;
+  for (int e = threadIdx.x; e < nw; e += blockDim.x) sW[e] = a.w[e];
+  __syncthreads();
+  const int n_out = a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out;
+  const float* in = (const float*)a.in;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_out; row += gridDim.x * blockDim.x) {
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = a.bias ? __ldg(a.bias + c) : 0.f;
+    for (int k = 0; k < a.kvol; ++k) {
+      const int src = __ldg(a.nbr + (size_t)k * a.cap_out + row);
+      if (src < 0) continue;
+      const float* x = in + (size_t)src * a.cin;
+      const float4* wk = reinterpret_cast<const float4*>(sW + (size_t)k * a.cin * COUT);
+      for (int ci = 0; ci < a.cin; ++ci) {
+        const float xv = __ldg(x + ci);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 w = wk[ci * (COUT / 4) + q];
+          acc[4 * q + 0] = fmaf(xv, w.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
+        }
+      }
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    }
+    if (a.out_bf16) {
+      uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)a.out + (size_t)row * COUT);
+#pragma unroll
+      for (int c = 0; c < COUT; c += 8) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(acc[c + 2 * q], acc[c + 2 * q + 1]);
+          w4[q] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        op[c / 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    } else {
+      float4* op = reinterpret_cast<float4*>((float*)a.out + (size_t)row * COUT);
+#pragma unroll
+      for (int c = 0; c < COUT; c += 4) op[c / 4] = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+    }
+  }
+}
+
 // (kvol, cin, cout) f32 -> bf16 in UMMA "core matrix" order:
 //   [k][ci/8][co][ci%8]   (one 16-byte K-chunk per output channel row)
 __global__ void pack_weight_kernel(const float* __restrict__ w, int kvol, int cin, int cout,
@@ -197,22 +254,24 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 
 // row-wise LayerNorm (+ReLU), one warp per row; in/out f32 or bf16
 template <typename T>
-__global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, int n, const float* __restrict__ g,
-                                      const float* __restrict__ b, float eps, int relu, T* __restrict__ out) {
+__global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, int n, const float* __restrict__ bias,
+                                      const float* __restrict__ g, const float* __restrict__ b, float eps, int relu,
+                                      T* __restrict__ out) {
   int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* x = in + row * n;
+  auto val = [&](int j) { return (float)x[j] + (bias ? bias[j] : 0.f); };
   float s = 0.f;
-  for (int j = lane; j < n; j += 32) s += (float)x[j];
+  for (int j = lane; j < n; j += 32) s += val(j);
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float mean = s / n;
   float v = 0.f;
-  for (int j = lane; j < n; j += 32) { float d = (float)x[j] - mean; v += d * d; }
+  for (int j = lane; j < n; j += 32) { float d = val(j) - mean; v += d * d; }
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   float rstd = rsqrtf(v / n + eps);
   for (int j = lane; j < n; j += 32) {
-    float y = ((float)x[j] - mean) * rstd * g[j] + b[j];
+    float y = (val(j) - mean) * rstd * g[j] + b[j];
     if (relu) y = fmaxf(y, 0.f);
     out[row * n + j] = (T)y;
   }
@@ -260,6 +319,16 @@ int srf_spconv_f32(const srf_conv_args* a, void* stream) {
   if (grid > ntiles) grid = ntiles;
   cudaStream_t st = (cudaStream_t)stream;
   SRF_COUNT(1);
+  if (a->in_dtype == SRF_F32 && a->cin <= 8 && (a->cout == 16 || a->cout == 32) && !a->residual && !a->dense) {
+    // tiny-Cin first layer: thread-per-row kernel, weights in shared memory
+    const size_t smem = (size_t)a->kvol * a->cin * a->cout * sizeof(float);
+    int g2 = cdiv(a->cap_out, 128);
+    if (g2 > sm_count() * 16) g2 = sm_count() * 16;
+    if (a->cout == 16) spconv_smallcin_kernel<16><<<g2, 128, smem, st>>>(d);
+    else spconv_smallcin_kernel<32><<<g2, 128, smem, st>>>(d);
+    SRF_LAUNCH_CHECK();
+    return SRF_OK;
+  }
   int rc = a->in_dtype == SRF_BF16 ? launch_conv_f32<__nv_bfloat16>(d, a->cout, grid, st)
                                    : launch_conv_f32<float>(d, a->cout, grid, st);
   if (rc) return rc;
@@ -320,17 +389,17 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
   return SRF_OK;
 }
 
-int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, const float* gamma, const float* beta,
-                  float eps, int32_t relu, void* out, void* stream) {
+int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, const float* bias, const float* gamma,
+                  const float* beta, float eps, int32_t relu, void* out, void* stream) {
   SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
   if (rows == 0) return SRF_OK;
   SRF_COUNT(1);
   int wpb = 8;
   int grid = (int)((rows + wpb - 1) / wpb);
   if (dtype == SRF_BF16)
-    layernorm_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, gamma, beta, eps, relu, (__nv_bfloat16*)out);
+    layernorm_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, bias, gamma, beta, eps, relu, (__nv_bfloat16*)out);
   else
-    layernorm_rows_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, gamma, beta, eps, relu, (float*)out);
+    layernorm_rows_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, bias, gamma, beta, eps, relu, (float*)out);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }

@@ -24,7 +24,7 @@ def _run(m, k, n, relu=False, ln=False, out_bf16=False, seed=0):
     out = torch.empty((m, n), dtype=torch.bfloat16 if out_bf16 else torch.float32, device='cuda')
     epi = (1 if relu else 0) | (2 if ln else 0)
     L.check(lib.srf_linear_bf16(L.ptr(ab), m, k, L.ptr(wp), n, L.ptr(bias), epi, L.ptr(lnw) if ln else None,
-                                L.ptr(lnb) if ln else None, L.ptr(out), L.BF16 if out_bf16 else L.F32, st), 'linear')
+                                L.ptr(lnb) if ln else None, L.ptr(out), L.BF16 if out_bf16 else L.F32, 1, st), 'linear')
     torch.cuda.synchronize()
     ref = ab.float() @ w.to(torch.bfloat16).float().t() + bias
     if ln:
@@ -48,3 +48,19 @@ def test_linear_bf16_epilogues():
     assert rel_err(got, ref) < 1e-2
     got, ref = _run(333, 128, 128, relu=False, ln=True, out_bf16=True)
     assert rel_err(got, ref) < 1e-2
+
+
+@pytest.mark.parametrize('m,k,n,splits', [(900, 6272, 128, 18), (300, 12544, 256, 9), (100, 1024, 64, 8)])
+def test_linear_bf16_split_k(m, k, n, splits):
+    from srfdet_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(3)
+    a = (torch.randn(m, k, generator=g) * 0.5).cuda().to(torch.bfloat16).contiguous()
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).cuda()
+    wp = torch.empty(n * k, dtype=torch.bfloat16, device='cuda')
+    st = L.stream_ptr()
+    L.check(lib.srf_pack_linear_bf16(L.ptr(w), n, k, L.ptr(wp), st), 'pack')
+    out = torch.zeros((m, n), dtype=torch.float32, device='cuda')
+    L.check(lib.srf_linear_bf16(L.ptr(a), m, k, L.ptr(wp), n, None, 0, None, None, L.ptr(out), L.F32, splits, st), 'linear')
+    ref = a.float() @ w.to(torch.bfloat16).float().t()
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-3
