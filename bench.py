@@ -192,6 +192,7 @@ def main():
     ap.add_argument('--workload', default='nusc_L', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying a CUDA graph of the frame')
     ap.add_argument('--nchw', action='store_true', help='RoI stage samples contiguous NCHW maps (reference layout) instead of channels_last')
     ap.add_argument('--layers-out', default=None, help='write the per-layer sparse-conv table (JSON) here')
     args = ap.parse_args()
@@ -216,6 +217,7 @@ def main():
     pk = peaks()
     kind = wl['kind']
     pipe = RegionFeaturePipeline(kind, fusion=wl['fusion'], precision=args.precision, channels_last=not args.nchw)
+    eager = pipe._run_frame_eager
     # distinct frames per rank, resident on the device (value) and in pinned host memory (e2e)
     clouds_np = [synth.cloud(kind, 1000 * (rank + 1) + i) for i in range(N_CLOUDS)]
     clouds_dev = [torch.as_tensor(c).cuda() for c in clouds_np]
@@ -246,9 +248,11 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    eager(clouds_dev[0])
     n0 = lib.srf_launch_count()
-    pipe.run_frame(clouds_dev[0])
-    launches_per_frame = int(lib.srf_launch_count() - n0)
+    eager(clouds_dev[0])
+    launches_per_frame = int(lib.srf_launch_count() - n0)      # this library's kernels per frame (counted eagerly)
+    pipe.use_graph = not args.no_graph
     ms_dev = timed(pipe.run_frame, clouds_dev, args.steps, args.warmup)
     ms_e2e = timed(pipe.run_frame_host, clouds_pin, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
@@ -256,6 +260,7 @@ def main():
     fps_e2e = world * args.steps / (ms_e2e * 1e-3)
 
     roof = rows = cpu = None
+    pipe.use_graph = False
     if rank == 0:
         roof, rows = conv_roofline(pipe, clouds_dev[0], pk, torch)
         if args.layers_out:
@@ -282,6 +287,7 @@ def main():
                             parallelism=f'{world} independent frame replica(s), no data-path collective',
                             l2='512 MiB flush written between timed steps; 8 distinct clouds cycled',
                             roi_map_layout='NCHW contiguous' if args.nchw else 'torch.channels_last (NHWC in memory)',
+                            launch='eager' if args.no_graph else 'one CUDA graph per frame (captured once, replayed)',
                             excluded='dense BEV backbone/FPN, image backbone, attention/FFN rows of the head (SURVEY 8f): RoI stage samples synthetic FPN maps'),
                 clocks=clocks,
                 e2e=dict(value=round(fps_e2e, 2), unit='frames/s', h2d_bytes_per_step=int(n_pts * c_pts * 4),

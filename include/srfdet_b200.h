@@ -201,11 +201,14 @@ int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, voi
  * epi: bit0 relu, bit1 layernorm over n (requires n == tile n <= 128) with ln_w/ln_b.
  * k multiple of 16 (and of 128 when k > 128); n multiple of 16 (of 128 when n > 128).
  * k_splits > 1 (few output tiles, long K, e.g. DynamicConv.out_layer 900x6272x128): the K
- * slices are dealt to k_splits CTAs per tile and fp32 partials are atomically added into a
- * ZEROED f32 `out`; epi must be 0 and bias NULL (srf_layernorm then applies bias/LN/ReLU).
+ * slices are dealt to k_splits CTAs per tile; split s writes its fp32 partial to slab s of
+ * `out` (k_splits, m, n); epi must be 0 and bias NULL.  srf_layernorm(n_partials=k_splits) sums
+ * the slabs in order (deterministic) and applies bias/LN/ReLU.  The effective split count is
+ * ceil(kvol / ceil(kvol / k_splits)) with kvol = k / min(k,128) (srf_linear_splits).
  * ---------------------------------------------------------------------------------- */
 int srf_linear_tile_k(int32_t k); /* host: K-slice width used by the packer (min(k,128)) */
 int srf_linear_tile_n(int32_t n); /* host: N tile width (min(n,128)) */
+int srf_linear_splits(int32_t k, int32_t k_splits); /* host: effective split count used for (k, k_splits) */
 int srf_pack_linear_bf16(const float* w_f32, int32_t n, int32_t k, void* w_packed, void* stream);
 int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n,
                     const float* bias, int32_t epi, const float* ln_w, const float* ln_b,
@@ -214,11 +217,12 @@ int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_pack
 /* FP32-mode linear (SIMT FFMA): out = relu?(A (m,k) . W(n,k)^T + bias), any n, k. */
 int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t n, const float* bias,
                    int32_t relu, float* out, void* stream);
-/* Row-wise LayerNorm (+ReLU) of (x + bias) over (rows, n); bias nullable; dtype SRF_F32 | SRF_BF16.
+/* Row-wise LayerNorm (+ReLU) of (sum_p x[p] + bias) over (rows, n); `in` holds n_partials slabs
+ * of (rows, n) (split-K partials, summed in slab order; 1 = plain); bias nullable; dtype SRF_F32 | SRF_BF16.
  * Used where the norm cannot be fused into a GEMM epilogue (n > 128, FP32 mode). */
-int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, const float* bias,
-                  const float* gamma, const float* beta, float eps, int32_t relu, void* out,
-                  void* stream);
+int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials,
+                  const float* bias, const float* gamma, const float* beta, float eps, int32_t relu,
+                  void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------- *
  * Region features.

@@ -202,6 +202,144 @@ static int launch_dc_tiled(const void* roi, const void* params, int k, const flo
   return SRF_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// Tensor-core variant for the BF16 mode (params and output bf16): the two per-proposal GEMMs
+// are 64x128x32 / 64x32x128-sized, far below a tcgen05 tile, so they run on warp-level
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with ldmatrix-fed fragments; 8 warps =
+// 4 row tiles x 2 column halves.  LayerNorms run on the fp32 accumulators staged in smem.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// warp-tile GEMM: acc[NT][4] += A(16 x K, smem pitch lda) . B(K x (NT*8), smem pitch ldb, row-major [k][n])
+template <int K, int NT>
+__device__ __forceinline__ void warp_gemm(const __nv_bfloat16* sA, int lda, const __nv_bfloat16* sB, int ldb, float (*acc)[4]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    uint32_t a0, a1, a2, a3;
+    ldsm_x4((uint32_t)__cvta_generic_to_shared(sA + (size_t)((lane & 7) + ((lane >> 3) & 1) * 8) * lda + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+#pragma unroll
+    for (int nt = 0; nt < NT; nt += 2) {
+      uint32_t b0, b1, b2, b3;   // (k 0-7, n-tile nt), (k 8-15, nt), (k 0-7, nt+1), (k 8-15, nt+1)
+      ldsm_x4_t((uint32_t)__cvta_generic_to_shared(sB + (size_t)(k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ldb + (nt + (lane >> 4)) * 8), b0, b1, b2, b3);
+      mma_bf16_16816(acc[nt], a0, a1, a2, a3, b0, b1);
+      mma_bf16_16816(acc[nt + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+}
+
+template <int C, int D, typename TR>
+__global__ void __launch_bounds__(256) dynconv_interact_mma_kernel(const TR* __restrict__ roi, const __nv_bfloat16* __restrict__ params,
+                                                                  const float* __restrict__ ln1_w, const float* __restrict__ ln1_b,
+                                                                  const float* __restrict__ ln2_w, const float* __restrict__ ln2_b,
+                                                                  __nv_bfloat16* __restrict__ out) {
+  constexpr int LDF = C + 8, LDP1 = D + 8, LDP2 = C + 8, LDT = D + 8;   // bf16 pitches (odd multiples of 16 B)
+  constexpr int LT1 = D + 1, LT2 = C + 4;                                // fp32 pitches
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __nv_bfloat16* sF = reinterpret_cast<__nv_bfloat16*>(smraw);          // 64 x LDF (rows >= 49 zero)
+  __nv_bfloat16* sP1 = sF + 64 * LDF;                                    // C x LDP1
+  __nv_bfloat16* sP2 = sP1 + C * LDP1;                                   // D x LDP2
+  __nv_bfloat16* sTb = sP2 + D * LDP2;                                   // 64 x LDT  (relu(LN(T1)) in bf16)
+  float* sT = reinterpret_cast<float*>(sTb + 64 * LDT);                  // 64 x LT2 fp32 staging (T1 uses pitch LT1)
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const TR* r = roi + (size_t)k * DC_ROWS * C;
+  const __nv_bfloat16* p = params + (size_t)k * 2 * C * D;
+  for (int e = threadIdx.x; e < 64 * C; e += 256) {
+    const int s = e / C, i = e - s * C;
+    sF[s * LDF + i] = s < DC_ROWS ? __float2bfloat16(to_f<TR>(r[e])) : __float2bfloat16(0.f);
+  }
+  for (int e = threadIdx.x; e < C * D / 8; e += 256) {          // 16-byte pieces of P1 (C x D) and P2 (D x C)
+    const int row1 = (e * 8) / D, col1 = (e * 8) % D;
+    *reinterpret_cast<uint4*>(sP1 + row1 * LDP1 + col1) = __ldg(reinterpret_cast<const uint4*>(p) + e);
+    const int row2 = (e * 8) / C, col2 = (e * 8) % C;
+    *reinterpret_cast<uint4*>(sP2 + row2 * LDP2 + col2) = __ldg(reinterpret_cast<const uint4*>(p + C * D) + e);
+  }
+  __syncthreads();
+  const int mt = warp >> 1, nh = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
+  {  // T1 = F . P1   (64 x D), warp tile 16 x D/2
+    constexpr int NT = D / 16;
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    warp_gemm<C, NT>(sF + mt * 16 * LDF, LDF, sP1 + nh * (D / 2), LDP1, acc);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int col = nh * (D / 2) + i * 8 + 2 * t;
+      sT[(mt * 16 + g) * LT1 + col] = acc[i][0];
+      sT[(mt * 16 + g) * LT1 + col + 1] = acc[i][1];
+      sT[(mt * 16 + g + 8) * LT1 + col] = acc[i][2];
+      sT[(mt * 16 + g + 8) * LT1 + col + 1] = acc[i][3];
+    }
+  }
+  __syncthreads();
+  for (int row = warp; row < 64; row += 8) {   // LayerNorm(D) + ReLU -> bf16 A operand of the second GEMM
+    const float* x = sT + row * LT1;
+    float s = 0.f;
+    for (int j = lane; j < D; j += 32) s += x[j];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / D;
+    float v = 0.f;
+    for (int j = lane; j < D; j += 32) { float d = x[j] - mean; v += d * d; }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / D + 1e-5f);
+    for (int j = lane; j < D; j += 32)
+      sTb[row * LDT + j] = __float2bfloat16(row < DC_ROWS ? fmaxf((x[j] - mean) * rstd * __ldg(ln1_w + j) + __ldg(ln1_b + j), 0.f) : 0.f);
+  }
+  __syncthreads();
+  {  // G = T . P2   (64 x C), warp tile 16 x C/2
+    constexpr int NT = C / 16;
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    warp_gemm<D, NT>(sTb + mt * 16 * LDT, LDT, sP2 + nh * (C / 2), LDP2, acc);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int col = nh * (C / 2) + i * 8 + 2 * t;
+      *reinterpret_cast<float2*>(sT + (mt * 16 + g) * LT2 + col) = make_float2(acc[i][0], acc[i][1]);
+      *reinterpret_cast<float2*>(sT + (mt * 16 + g + 8) * LT2 + col) = make_float2(acc[i][2], acc[i][3]);
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* o = out + (size_t)k * DC_ROWS * C;
+  for (int row = warp; row < DC_ROWS; row += 8) {   // LayerNorm(C) + ReLU, write out
+    const float* x = sT + row * LT2;
+    float s = 0.f;
+    for (int j = lane; j < C; j += 32) s += x[j];
+    for (int o2 = 16; o2; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    const float mean = s / C;
+    float v = 0.f;
+    for (int j = lane; j < C; j += 32) { float d = x[j] - mean; v += d * d; }
+    for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+    const float rstd = rsqrtf(v / C + 1e-5f);
+    for (int j = lane; j < C; j += 32)
+      o[(size_t)row * C + j] = __float2bfloat16(fmaxf((x[j] - mean) * rstd * __ldg(ln2_w + j) + __ldg(ln2_b + j), 0.f));
+  }
+}
+
+template <int C, int D, typename TR>
+static int launch_dc_mma(const void* roi, const void* params, int k, const float* a, const float* b, const float* e,
+                         const float* f, void* out, cudaStream_t st) {
+  // the T1 (pitch D+1) and T2 (pitch C+4) fp32 stagings share one buffer sized for T2
+  size_t smem = (size_t)(64 * (C + 8) + C * (D + 8) + D * (C + 8) + 64 * (D + 8)) * 2 + (size_t)64 * (C + 4) * 4;
+  auto kern = dynconv_interact_mma_kernel<C, D, TR>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) { set_error("dynconv mma: cannot get %zu B shared memory: %s", smem, cudaGetErrorString(err)); return SRF_ERR_CUDA; }
+  SRF_COUNT(1);
+  kern<<<k, 256, smem, st>>>((const TR*)roi, (const __nv_bfloat16*)params, a, b, e, f, (__nv_bfloat16*)out);
+  return SRF_OK;
+}
+
 template <typename TR, typename TP, typename TO>
 static int launch_dc(const void* roi, const void* params, int k, int c, int d, const float* a, const float* b,
                      const float* e, const float* f, void* out, cudaStream_t st) {
@@ -233,7 +371,13 @@ int srf_dynconv_interact(const void* roi, int32_t roi_dtype, const void* params,
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   const bool rb = roi_dtype == SRF_BF16, pb = param_dtype == SRF_BF16, ob = out_dtype == SRF_BF16;
-  if (!rb && !pb && !ob) rc = launch_dc<float, float, float>(roi, params, k, c, d, ln1_w, ln1_b, ln2_w, ln2_b, out, st);
+  if (pb && ob && c == 128 && d == 32)
+    rc = rb ? launch_dc_mma<128, 32, __nv_bfloat16>(roi, params, k, ln1_w, ln1_b, ln2_w, ln2_b, out, st)
+            : launch_dc_mma<128, 32, float>(roi, params, k, ln1_w, ln1_b, ln2_w, ln2_b, out, st);
+  else if (pb && ob && c == 256 && d == 64)
+    rc = rb ? launch_dc_mma<256, 64, __nv_bfloat16>(roi, params, k, ln1_w, ln1_b, ln2_w, ln2_b, out, st)
+            : launch_dc_mma<256, 64, float>(roi, params, k, ln1_w, ln1_b, ln2_w, ln2_b, out, st);
+  else if (!rb && !pb && !ob) rc = launch_dc<float, float, float>(roi, params, k, c, d, ln1_w, ln1_b, ln2_w, ln2_b, out, st);
   else if (rb && pb && ob) rc = launch_dc<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(roi, params, k, c, d, ln1_w, ln1_b, ln2_w, ln2_b, out, st);
   else if (!rb && pb && ob) rc = launch_dc<float, __nv_bfloat16, __nv_bfloat16>(roi, params, k, c, d, ln1_w, ln1_b, ln2_w, ln2_b, out, st);
   else if (rb && !pb && ob) rc = launch_dc<__nv_bfloat16, float, __nv_bfloat16>(roi, params, k, c, d, ln1_w, ln1_b, ln2_w, ln2_b, out, st);

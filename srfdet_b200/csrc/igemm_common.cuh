@@ -96,17 +96,17 @@ struct IgemmArgs {
   float* dense;
   const int4* out_coors;
   int D, H, W;
-  int k_splits;  // dense linear only: K slices are dealt to k_splits CTAs per output tile, fp32 partials atomically added
+  int k_splits;  // dense linear only: K slices are dealt to k_splits CTAs per output tile, fp32 partials in k_splits slabs
   int dbg;  // profiling only (SRF_IGEMM_DBG): 1 skip A copies, 2 skip B copies, 4 skip MMA issue, 8 skip epilogue math/stores
 };
 
 // bias / residual / LayerNorm / ReLU and the store of one output row held in registers
 template <int COUT>
-__device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt, float* v) {
-  if (a.k_splits > 1) {   // partial sum of one K range: bias / norm / activation run in a follow-up pass
-    float* op = (float*)a.out + (size_t)row * a.out_stride + nt * COUT;
+__device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt, float* v, int ks = 0) {
+  if (a.k_splits > 1) {   // partial sum of one K range -> its own (m, n) slab; summed in fixed order by srf_layernorm
+    float4* op = (float4*)((float*)a.out + ((size_t)ks * a.m_rows + row) * a.out_stride + nt * COUT);
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) atomicAdd(op + c, v[c]);
+    for (int c = 0; c < COUT; c += 4) op[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
     return;
   }
     const int col0 = nt * COUT;

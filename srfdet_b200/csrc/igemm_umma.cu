@@ -284,7 +284,7 @@ igemm_umma_kernel(const IgemmArgs a) {
       // accumulator is in registers: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
-      if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v);
+      if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v, tile / mn_tiles);
     }
   }
   tc_fence_before();
@@ -676,6 +676,13 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
   return dispatch_igemm<true>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream);
 }
 
+int srf_linear_splits(int32_t k, int32_t k_splits) {
+  const int kvol = k / srf_linear_tile_k(k);
+  if (k_splits <= 1 || kvol <= 1) return 1;
+  const int kper = (kvol + k_splits - 1) / k_splits;
+  return (kvol + kper - 1) / kper;
+}
+
 int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
                     int32_t epi, const float* ln_w, const float* ln_b, void* out, int32_t out_dtype, int32_t k_splits,
                     void* stream) {
@@ -704,7 +711,7 @@ int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_pack
   a.out_stride = n;
   a.k_splits = 1;
   if (k_splits > 1 && use_ldgsts()) {
-    SRF_CHECK_ARG(epi == 0 && !bias && out_dtype == SRF_F32, "srf_linear_bf16: split-K needs epi=0, no bias and a zeroed f32 output");
+    SRF_CHECK_ARG(epi == 0 && !bias && out_dtype == SRF_F32, "srf_linear_bf16: split-K needs epi=0, no bias and an f32 output of k_splits slabs");
     const int kper = (a.kvol + k_splits - 1) / k_splits;
     a.k_splits = (a.kvol + kper - 1) / kper;   // every split owns at least one K slice
   }

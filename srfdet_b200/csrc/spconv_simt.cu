@@ -254,14 +254,19 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 
 // row-wise LayerNorm (+ReLU), one warp per row; in/out f32 or bf16
 template <typename T>
-__global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, int n, const float* __restrict__ bias,
-                                      const float* __restrict__ g, const float* __restrict__ b, float eps, int relu,
-                                      T* __restrict__ out) {
+__global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, int n, int n_partials,
+                                      const float* __restrict__ bias, const float* __restrict__ g,
+                                      const float* __restrict__ b, float eps, int relu, T* __restrict__ out) {
   int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* x = in + row * n;
-  auto val = [&](int j) { return (float)x[j] + (bias ? bias[j] : 0.f); };
+  // split-K partial slabs (n_partials, rows, n) are summed here, in slab order (deterministic)
+  auto val = [&](int j) {
+    float t = (float)x[j];
+    for (int p = 1; p < n_partials; ++p) t += (float)x[(size_t)p * rows * n + j];
+    return t + (bias ? bias[j] : 0.f);
+  };
   float s = 0.f;
   for (int j = lane; j < n; j += 32) s += val(j);
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -389,17 +394,18 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
   return SRF_OK;
 }
 
-int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, const float* bias, const float* gamma,
-                  const float* beta, float eps, int32_t relu, void* out, void* stream) {
+int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
+                  const float* gamma, const float* beta, float eps, int32_t relu, void* out, void* stream) {
+  if (n_partials < 1) n_partials = 1;
   SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
   if (rows == 0) return SRF_OK;
   SRF_COUNT(1);
   int wpb = 8;
   int grid = (int)((rows + wpb - 1) / wpb);
   if (dtype == SRF_BF16)
-    layernorm_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, bias, gamma, beta, eps, relu, (__nv_bfloat16*)out);
+    layernorm_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (__nv_bfloat16*)out);
   else
-    layernorm_rows_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, bias, gamma, beta, eps, relu, (float*)out);
+    layernorm_rows_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (float*)out);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }

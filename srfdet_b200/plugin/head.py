@@ -37,7 +37,7 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_bf16=None):
         fuse_relu = relu and ln is None
         L.check(lib.srf_linear_f32(L.ptr(x), m, k, L.ptr(w), n, L.ptr(bias), int(fuse_relu), L.ptr(out), st), 'srf_linear_f32')
         if ln is not None:
-            L.check(lib.srf_layernorm(L.ptr(out), L.F32, m, n, None, L.ptr(ln.weight.detach().float().contiguous()),
+            L.check(lib.srf_layernorm(L.ptr(out), L.F32, m, n, 1, None, L.ptr(ln.weight.detach().float().contiguous()),
                                       L.ptr(ln.bias.detach().float().contiguous()), ln.eps, int(relu), L.ptr(out), st),
                     'srf_layernorm')
         return out
@@ -56,11 +56,12 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_bf16=None):
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
     kvol = k // min(k, 128)
     if ln is not None and tiles * 4 <= 148 and kvol >= 8:
-        splits = min(kvol, max(1, 148 // tiles))
-        acc = torch.zeros((m, n), dtype=torch.float32, device=dev)
-        L.check(lib.srf_linear_bf16(L.ptr(x.contiguous()), m, k, L.ptr(cache[key]), n, None, 0, None, None, L.ptr(acc), L.F32,
+        splits = lib.srf_linear_splits(k, min(kvol, max(1, 148 // tiles)))
+        part = torch.empty((splits, m, n), dtype=torch.float32, device=dev)
+        L.check(lib.srf_linear_bf16(L.ptr(x.contiguous()), m, k, L.ptr(cache[key]), n, None, 0, None, None, L.ptr(part), L.F32,
                                     splits, st), 'srf_linear_bf16')
-        L.check(lib.srf_layernorm(L.ptr(acc), L.F32, m, n, L.ptr(bias), L.ptr(ln.weight.detach().float().contiguous()),
+        acc = torch.empty((m, n), dtype=torch.float32, device=dev)
+        L.check(lib.srf_layernorm(L.ptr(part), L.F32, m, n, splits, L.ptr(bias), L.ptr(ln.weight.detach().float().contiguous()),
                                   L.ptr(ln.bias.detach().float().contiguous()), ln.eps, int(relu), L.ptr(acc), st), 'srf_layernorm')
         return acc.to(torch.bfloat16) if out_bf16 else acc
     out = torch.empty((m, n), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
@@ -71,7 +72,7 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_bf16=None):
     L.check(lib.srf_linear_bf16(L.ptr(x.contiguous()), m, k, L.ptr(cache[key]), n, L.ptr(bias), epi, L.ptr(lnw), L.ptr(lnb),
                                 L.ptr(out), L.BF16 if out_bf16 else L.F32, 1, st), 'srf_linear_bf16')
     if ln is not None and not fuse_ln:
-        L.check(lib.srf_layernorm(L.ptr(out), L.BF16 if out_bf16 else L.F32, m, n, None,
+        L.check(lib.srf_layernorm(L.ptr(out), L.BF16 if out_bf16 else L.F32, m, n, 1, None,
                                   L.ptr(ln.weight.detach().float().contiguous()), L.ptr(ln.bias.detach().float().contiguous()),
                                   ln.eps, int(relu), L.ptr(out), st), 'srf_layernorm')
     return out

@@ -60,7 +60,14 @@ def test_linear_bf16_split_k(m, k, n, splits):
     wp = torch.empty(n * k, dtype=torch.bfloat16, device='cuda')
     st = L.stream_ptr()
     L.check(lib.srf_pack_linear_bf16(L.ptr(w), n, k, L.ptr(wp), st), 'pack')
-    out = torch.zeros((m, n), dtype=torch.float32, device='cuda')
-    L.check(lib.srf_linear_bf16(L.ptr(a), m, k, L.ptr(wp), n, None, 0, None, None, L.ptr(out), L.F32, splits, st), 'linear')
+    eff = lib.srf_linear_splits(k, splits)
+    part = torch.empty((eff, m, n), dtype=torch.float32, device='cuda')
+    L.check(lib.srf_linear_bf16(L.ptr(a), m, k, L.ptr(wp), n, None, 0, None, None, L.ptr(part), L.F32, splits, st), 'linear')
     ref = a.float() @ w.to(torch.bfloat16).float().t()
-    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+    assert rel_err(part.sum(0).cpu().numpy(), ref.cpu().numpy()) < 2e-3
+    # slabs are summed in order with bias + LayerNorm + ReLU by srf_layernorm
+    bias = torch.randn(n, generator=g).cuda(); lw = (torch.rand(n, generator=g) + 0.5).cuda(); lb = torch.randn(n, generator=g).cuda()
+    out = torch.empty((m, n), dtype=torch.float32, device='cuda')
+    L.check(lib.srf_layernorm(L.ptr(part), L.F32, m, n, eff, L.ptr(bias), L.ptr(lw), L.ptr(lb), 1e-5, 1, L.ptr(out), st), 'ln')
+    ref2 = torch.relu(torch.nn.functional.layer_norm(ref + bias, (n,), lw, lb))
+    assert rel_err(out.cpu().numpy(), ref2.cpu().numpy()) < 2e-3
