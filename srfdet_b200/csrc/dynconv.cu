@@ -254,9 +254,21 @@ __global__ void __launch_bounds__(256) dynconv_interact_mma_kernel(const TR* __r
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TR* r = roi + (size_t)k * DC_ROWS * C;
   const __nv_bfloat16* p = params + (size_t)k * 2 * C * D;
-  for (int e = threadIdx.x; e < 64 * C; e += 256) {
-    const int s = e / C, i = e - s * C;
-    sF[s * LDF + i] = s < DC_ROWS ? __float2bfloat16(to_f<TR>(r[e])) : __float2bfloat16(0.f);
+  for (int e = threadIdx.x; e < 64 * C / 8; e += 256) {          // 8 channels per thread-step
+    const int s = (e * 8) / C, i = (e * 8) % C;
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    if (s < DC_ROWS) {
+      if (sizeof(TR) == 2) {
+        pk = __ldg(reinterpret_cast<const uint4*>(r) + e);
+      } else {
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(r) + 2 * e), f1 = __ldg(reinterpret_cast<const float4*>(r) + 2 * e + 1);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f0.x, f0.y), h1 = __floats2bfloat162_rn(f0.z, f0.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f1.x, f1.y), h3 = __floats2bfloat162_rn(f1.z, f1.w);
+        pk = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                        *reinterpret_cast<uint32_t*>(&h3));
+      }
+    }
+    *reinterpret_cast<uint4*>(sF + s * LDF + i) = pk;
   }
   for (int e = threadIdx.x; e < C * D / 8; e += 256) {          // 16-byte pieces of P1 (C x D) and P2 (D x C)
     const int row1 = (e * 8) / D, col1 = (e * 8) % D;

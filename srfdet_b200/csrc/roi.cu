@@ -262,17 +262,42 @@ __device__ __forceinline__ RoiGeom roi_geom(const Pyr& p, float x1, float y1, fl
   return g;
 }
 
-// accumulate one bin of one RoI into acc[NP] (float4 = 4 channels per lane per pass)
+// bilinear taps of ONE sample point (bin, iy, ix): 4 (offset, weight) pairs, weights already
+// divided by the 4 samples of a bin.  Staged in shared memory once per (proposal, camera) so
+// the channel loops only do  LDS + LDG.128 + 4 FFMA  per tap.
+__device__ __forceinline__ void sample_taps(int smp, const RoiGeom& g, int* off, float* wt) {
+  const int bin = smp >> 2, iy = (smp >> 1) & 1, ix = smp & 1;
+  const int ph = bin / POOL, pw = bin - ph * POOL;
+  const float y = g.y1s + ph * g.bh + (iy + .5f) * g.bh / 2.f;
+  const float x = g.x1s + pw * g.bw + (ix + .5f) * g.bw / 2.f;
+  const int H = g.H, W = g.W;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { off[q] = 0; wt[q] = 0.f; }
+    return;
+  }
+  float yy = y <= 0.f ? 0.f : y, xx = x <= 0.f ? 0.f : x;
+  int yl = (int)yy, xl = (int)xx, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; yy = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; xx = (float)xl; } else xh = xl + 1;
+  const float ly = yy - yl, lx = xx - xl, hy = 1.f - ly, hx = 1.f - lx;
+  off[0] = yl * W + xl; wt[0] = hy * hx * 0.25f;
+  off[1] = yl * W + xh; wt[1] = hy * lx * 0.25f;
+  off[2] = yh * W + xl; wt[2] = ly * hx * 0.25f;
+  off[3] = yh * W + xh; wt[3] = ly * lx * 0.25f;
+}
+
+constexpr int NTAP = NBIN * 16;   // taps per RoI: 49 bins x 4 samples x 4 corners
+
+// accumulate one bin from staged taps into acc[NP] (float4 = 4 channels per lane per pass)
 template <int NP>
-__device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_base, const RoiGeom& g, int bin, int C,
-                                                  int lane, float4* acc) {
-  Taps t;
-  bin_taps(bin, g.x1s, g.y1s, g.bw, g.bh, g.H, g.W, t);
+__device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_base, const int* __restrict__ s_off,
+                                                  const float* __restrict__ s_wt, int bin, int C, int lane, float4* acc) {
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    if (t.wt[q] == 0.f) continue;
-    const float w = t.wt[q] * 0.25f;
-    const float4* src = reinterpret_cast<const float4*>(img_base + (size_t)t.off[q] * C) + lane;
+    const float w = s_wt[bin * 16 + q];
+    if (w == 0.f) continue;
+    const float4* src = reinterpret_cast<const float4*>(img_base + (size_t)s_off[bin * 16 + q] * C) + lane;
 #pragma unroll
     for (int pss = 0; pss < NP; ++pss) {
       if ((pss * 32 + lane) * 4 < C) {
@@ -306,6 +331,8 @@ template <int NP>
 __global__ void __launch_bounds__(256) bev_roi_cl_kernel(Pyr p, float* __restrict__ boxes, const float* __restrict__ rois_in,
                                                         int n_prop, int box_dim, Range rg, int mutate, float* __restrict__ out,
                                                         int channel_last, float* __restrict__ rois_out) {
+  __shared__ int s_off[NTAP];
+  __shared__ float s_wt[NTAP];
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float x1, y1, x2, y2;
@@ -335,23 +362,29 @@ __global__ void __launch_bounds__(256) bev_roi_cl_kernel(Pyr p, float* __restric
       r[0] = (float)img; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
     }
   }
-  RoiGeom g = roi_geom(p, x1, y1, x2, y2);
-  g.live = 1;   // single-map form: out-of-range samples already carry zero weight
+  const RoiGeom g = roi_geom(p, x1, y1, x2, y2);
+  if (threadIdx.x < NBIN * 4) sample_taps(threadIdx.x, g, s_off + threadIdx.x * 4, s_wt + threadIdx.x * 4);
+  __syncthreads();
   const float* base = p.feat[g.lvl] + (size_t)img * g.H * g.W * p.channels;
   for (int bin = warp; bin < NBIN; bin += 8) {
     float4 acc[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    bin_accumulate_cl<NP>(base, g, bin, p.channels, lane, acc);
+    bin_accumulate_cl<NP>(base, s_off, s_wt, bin, p.channels, lane, acc);
     store_bin_cl<NP>(out, k, bin, p.channels, lane, channel_last, acc);
   }
 }
+
+constexpr int IMG_MAX_CAM = 8;
 
 template <int NP>
 __global__ void __launch_bounds__(256) img_roi_cl_kernel(Pyr p, const float* __restrict__ boxes, int n_prop, int box_dim,
                                                         const float* __restrict__ lidar2img, int n_cam, Range rg,
                                                         float* __restrict__ out, int channel_last, float* __restrict__ rois_out) {
-  __shared__ RoiGeom sg[16];
+  extern __shared__ __align__(16) uint8_t sm_img[];
+  int* s_off = reinterpret_cast<int*>(sm_img);                 // [n_cam][NTAP]
+  float* s_wt = reinterpret_cast<float*>(s_off + n_cam * NTAP);
+  __shared__ RoiGeom sg[IMG_MAX_CAM];
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < n_cam) {
@@ -379,15 +412,19 @@ __global__ void __launch_bounds__(256) img_roi_cl_kernel(Pyr p, const float* __r
     sg[cam] = roi_geom(p, x1, y1, x2, y2);
   }
   __syncthreads();
+  for (int e = threadIdx.x; e < n_cam * NBIN * 4; e += blockDim.x) {
+    const int cam = e / (NBIN * 4), smp = e - cam * (NBIN * 4);
+    if (sg[cam].live) sample_taps(smp, sg[cam], s_off + cam * NTAP + smp * 4, s_wt + cam * NTAP + smp * 4);
+  }
+  __syncthreads();
   for (int bin = warp; bin < NBIN; bin += 8) {
     float4 acc[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int cam = 0; cam < n_cam; ++cam) {
-      const RoiGeom g = sg[cam];
-      if (!g.live) continue;
-      const float* base = p.feat[g.lvl] + (size_t)cam * g.H * g.W * p.channels;
-      bin_accumulate_cl<NP>(base, g, bin, p.channels, lane, acc);
+      if (!sg[cam].live) continue;
+      const float* base = p.feat[sg[cam].lvl] + (size_t)cam * sg[cam].H * sg[cam].W * p.channels;
+      bin_accumulate_cl<NP>(base, s_off + cam * NTAP, s_wt + cam * NTAP, bin, p.channels, lane, acc);
     }
     store_bin_cl<NP>(out, k, bin, p.channels, lane, channel_last, acc);
   }
@@ -485,9 +522,14 @@ int srf_img_roi_features(const srf_pyramid* p, const float* boxes, int32_t n_pro
   cudaStream_t st = (cudaStream_t)stream;
   SRF_COUNT(1);
   if (d.channels_last) {
-    SRF_CHECK_ARG(n_cam <= 16, "srf_img_roi_features: at most 16 cameras");
-    if (d.channels <= 128) img_roi_cl_kernel<1><<<n_prop, 256, 0, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
-    else img_roi_cl_kernel<2><<<n_prop, 256, 0, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
+    SRF_CHECK_ARG(n_cam <= IMG_MAX_CAM, "srf_img_roi_features: at most %d cameras", IMG_MAX_CAM);
+    const size_t smem = (size_t)n_cam * NTAP * 8;
+    if (smem > 48 * 1024) {
+      SRF_CUDA(cudaFuncSetAttribute(img_roi_cl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SRF_CUDA(cudaFuncSetAttribute(img_roi_cl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (d.channels <= 128) img_roi_cl_kernel<1><<<n_prop, 256, smem, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
+    else img_roi_cl_kernel<2><<<n_prop, 256, smem, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }

@@ -252,7 +252,9 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
   }
 }
 
-// row-wise LayerNorm (+ReLU), one warp per row; in/out f32 or bf16
+// row-wise LayerNorm (+ReLU) of (sum of split-K slabs + bias), one warp per row; f32 or bf16.
+// The row is read once into registers (n <= 32*LN_MAXPL), then reduced with shuffles.
+constexpr int LN_MAXPL = 16;   // values per lane -> n <= 512
 template <typename T>
 __global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, int n, int n_partials,
                                       const float* __restrict__ bias, const float* __restrict__ g,
@@ -261,24 +263,35 @@ __global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, in
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* x = in + row * n;
-  // split-K partial slabs (n_partials, rows, n) are summed here, in slab order (deterministic)
-  auto val = [&](int j) {
-    float t = (float)x[j];
-    for (int p = 1; p < n_partials; ++p) t += (float)x[(size_t)p * rows * n + j];
-    return t + (bias ? bias[j] : 0.f);
-  };
+  float v[LN_MAXPL];
   float s = 0.f;
-  for (int j = lane; j < n; j += 32) s += val(j);
+#pragma unroll
+  for (int i = 0; i < LN_MAXPL; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = 0.f;
+    if (j < n) {
+      float t = (float)x[j];
+      for (int p = 1; p < n_partials; ++p) t += (float)x[(size_t)p * rows * n + j];   // slab order: deterministic
+      v[i] = t + (bias ? bias[j] : 0.f);
+      s += v[i];
+    }
+  }
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  float mean = s / n;
-  float v = 0.f;
-  for (int j = lane; j < n; j += 32) { float d = val(j) - mean; v += d * d; }
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  float rstd = rsqrtf(v / n + eps);
-  for (int j = lane; j < n; j += 32) {
-    float y = (val(j) - mean) * rstd * g[j] + b[j];
-    if (relu) y = fmaxf(y, 0.f);
-    out[row * n + j] = (T)y;
+  const float mean = s / n;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXPL; ++i)
+    if (lane + 32 * i < n) { float d = v[i] - mean; q += d * d; }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / n + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXPL; ++i) {
+    const int j = lane + 32 * i;
+    if (j < n) {
+      float y = (v[i] - mean) * rstd * g[j] + b[j];
+      if (relu) y = fmaxf(y, 0.f);
+      out[row * n + j] = (T)y;
+    }
   }
 }
 
@@ -398,9 +411,10 @@ int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_
                   const float* gamma, const float* beta, float eps, int32_t relu, void* out, void* stream) {
   if (n_partials < 1) n_partials = 1;
   SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
+  SRF_CHECK_ARG(n <= 32 * LN_MAXPL, "srf_layernorm: n must be <= %d", 32 * LN_MAXPL);
   if (rows == 0) return SRF_OK;
   SRF_COUNT(1);
-  int wpb = 8;
+  int wpb = 4;
   int grid = (int)((rows + wpb - 1) / wpb);
   if (dtype == SRF_BF16)
     layernorm_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (__nv_bfloat16*)out);
