@@ -81,7 +81,7 @@ class SparseBasicBlock(nn.Module):
 
 
 class _Level:
-    __slots__ = ('dims', 'ncells', 'cap', 'index', 'coors', 'count', 'nbr', 'mask')
+    __slots__ = ('dims', 'ncells', 'cap', 'index', 'coors', 'count', 'nbr', 'mask', 'ready')
 
 
 @MIDDLE_ENCODERS.register_module()
@@ -112,6 +112,8 @@ class SparseEncoderCustom(nn.Module):
         self._packed = {}
         self.last_counts = None
         self.profile = None   # set to a list to record per-conv CUDA events (bench.py roofline pass)
+        self.overlap_geometry = True   # build coarse-level indices / rulebooks on a side stream
+        self._aux = {}
 
     def make_encoder_layers(self, make_block, norm_cfg, in_channels, block_type='conv_module',
                             conv_cfg=dict(type='SubMConv3d')):
@@ -177,6 +179,12 @@ class SparseEncoderCustom(nn.Module):
         self._packed[key] = packed
         return packed
 
+    def _side_stream(self, dev):
+        key = str(dev)
+        if key not in self._aux:
+            self._aux[key] = torch.cuda.Stream(device=dev)
+        return self._aux[key]
+
     @staticmethod
     def _out_dims(dims, k, s, p):
         return [dims[0]] + [(dims[1 + j] + 2 * p[j] - k[j]) // s[j] + 1 for j in range(3)]
@@ -191,6 +199,7 @@ class SparseEncoderCustom(nn.Module):
         lv.count = torch.zeros((1,), dtype=torch.int32, device=device)
         lv.nbr = None
         lv.mask = None
+        lv.ready = None
         return lv
 
     def _rulebook(self, lv_in, lv_out, k, s, p, device):
@@ -238,29 +247,61 @@ class SparseEncoderCustom(nn.Module):
         levels = [lv]
         identity = None
         dense = None
+
+        # ---- geometry of every layer (indices of the coarser levels, rulebooks).  It depends
+        # only on the coordinates, never on features, so everything past level 0 is enqueued
+        # on a side stream and overlaps the convolutions of the finer levels; each conv waits
+        # on the event of the tables it reads.
+        main = torch.cuda.current_stream()
+        capturing = torch.cuda.is_current_stream_capturing()
+        aux = self._side_stream(dev) if self.overlap_geometry else main
+        ev0 = main.record_event()
+        aux.wait_event(ev0)
+        geo = []
+        cur = lv
+        with torch.cuda.stream(aux):
+            for li, (conv, bn, save_id, add_id) in enumerate(plan):
+                k, s, p = conv.kernel_size, conv.stride, conv.padding
+                if conv.subm:
+                    if cur.nbr is None:
+                        if cur is lv:          # level 0: needed by the very first conv -> main stream
+                            with torch.cuda.stream(main):
+                                cur.nbr, cur.mask = self._rulebook(cur, cur, k, s, p, dev)
+                            cur.ready = None
+                        else:
+                            cur.nbr, cur.mask = self._rulebook(cur, cur, k, s, p, dev)
+                            cur.ready = aux.record_event() if aux is not main else None
+                    geo.append((cur.nbr, cur.mask, cur, cur.ready))
+                else:
+                    st_a = L.stream_ptr()
+                    od = self._out_dims(cur.dims, k, s, p)
+                    growth = 1
+                    for j in range(3):
+                        growth *= min(k[j], (k[j] + s[j] - 1) // s[j])
+                    lv_out = self._new_level(od, cur.cap * growth, dev)
+                    L.check(lib.srf_index_clear(L.ptr(lv_out.index), lv_out.ncells, st_a), 'srf_index_clear')
+                    L.check(lib.srf_index_mark_strided(L.ptr(lv_out.index), L.i4(od), L.ptr(cur.coors), cur.cap, L.ptr(cur.count),
+                                                       L.i3(k), L.i3(s), L.i3(p), st_a), 'srf_index_mark_strided')
+                    L.check(lib.srf_index_finalize(L.ptr(lv_out.index), lv_out.ncells, L.ptr(lv_out.count), st_a), 'srf_index_finalize')
+                    L.check(lib.srf_index_emit_coors(L.ptr(lv_out.index), L.i4(od), L.ptr(lv_out.coors), lv_out.cap, st_a),
+                            'srf_index_emit_coors')
+                    nbr, mask = self._rulebook(cur, lv_out, k, s, p, dev)
+                    ready = aux.record_event() if aux is not main else None
+                    geo.append((nbr, mask, lv_out, ready))
+                    levels.append(lv_out)
+                    cur = lv_out
+        if aux is not main and not capturing:   # tensors born on the side stream are consumed on main
+            for nbr, mask, lv_o, _ in geo:
+                for t in (nbr, mask, lv_o.index, lv_o.coors, lv_o.count):
+                    t.record_stream(main)
+        st = L.stream_ptr()
         for li, (conv, bn, save_id, add_id) in enumerate(plan):
             pk = packed[li]
             k, s, p = conv.kernel_size, conv.stride, conv.padding
             last = li == len(plan) - 1
-            if conv.subm:
-                lv_out = lv
-                if lv.nbr is None:
-                    lv.nbr, lv.mask = self._rulebook(lv, lv, k, s, p, dev)
-                nbr, mask = lv.nbr, lv.mask
-            else:
-                od = self._out_dims(lv.dims, k, s, p)
-                growth = 1
-                for j in range(3):
-                    growth *= min(k[j], (k[j] + s[j] - 1) // s[j])
-                lv_out = self._new_level(od, lv.cap * growth, dev)
-                L.check(lib.srf_index_clear(L.ptr(lv_out.index), lv_out.ncells, st), 'srf_index_clear')
-                L.check(lib.srf_index_mark_strided(L.ptr(lv_out.index), L.i4(od), L.ptr(lv.coors), lv.cap, L.ptr(lv.count),
-                                                   L.i3(k), L.i3(s), L.i3(p), st), 'srf_index_mark_strided')
-                L.check(lib.srf_index_finalize(L.ptr(lv_out.index), lv_out.ncells, L.ptr(lv_out.count), st), 'srf_index_finalize')
-                L.check(lib.srf_index_emit_coors(L.ptr(lv_out.index), L.i4(od), L.ptr(lv_out.coors), lv_out.cap, st),
-                        'srf_index_emit_coors')
-                nbr, mask = self._rulebook(lv, lv_out, k, s, p, dev)
-                levels.append(lv_out)
+            nbr, mask, lv_out, ready = geo[li]
+            if ready is not None:
+                main.wait_event(ready)
             if save_id:
                 identity = x
             a = L.ConvArgs()
