@@ -101,6 +101,66 @@ struct IgemmArgs {
 };
 
 // bias / residual / LayerNorm / ReLU and the store of one output row held in registers
+// Sparse-conv epilogue of NC consecutive output channels [c0, c0+NC) of one row (the row's
+// accumulator is drained from TMEM in chunks to keep the epilogue's register footprint small,
+// which is what lets the kernel afford more gather warps): bias(BN) + residual + ReLU + store.
+template <int COUT, int NC>
+__device__ __forceinline__ void epilogue_chunk(const IgemmArgs& a, int row, int c0, float* v) {
+  if (a.bias) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] += __ldg(a.bias + c0 + c);
+  }
+  if (a.residual) {
+    if (a.out_bf16) {
+      const uint4* rp = (const uint4*)((const __nv_bfloat16*)a.residual + (size_t)row * a.out_stride + c0);
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        uint4 u = __ldg(rp + c / 8);
+        uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[c + 2 * q] += __uint_as_float(w4[q] << 16);
+          v[c + 2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+        }
+      }
+    } else {
+      const float4* rp = (const float4*)((const float*)a.residual + (size_t)row * a.out_stride + c0);
+#pragma unroll
+      for (int c = 0; c < NC; c += 4) {
+        float4 u = __ldg(rp + c / 4);
+        v[c] += u.x; v[c + 1] += u.y; v[c + 2] += u.z; v[c + 3] += u.w;
+      }
+    }
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = fmaxf(v[c], 0.f);
+  }
+  if (a.dense) {
+    const int4 q = __ldg(a.out_coors + row);
+    const size_t hw = (size_t)a.H * a.W;
+    float* dp = a.dense + ((size_t)q.x * COUT * a.D + q.y) * hw + (size_t)q.z * a.W + q.w + (size_t)c0 * a.D * hw;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) dp[(size_t)c * a.D * hw] = v[c];
+  } else if (a.out_bf16) {
+    uint4* op = (uint4*)((__nv_bfloat16*)a.out + (size_t)row * a.out_stride + c0);
+#pragma unroll
+    for (int c = 0; c < NC; c += 8) {
+      uint32_t w4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[c + 2 * q], v[c + 2 * q + 1]);
+        w4[q] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      op[c / 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  } else {
+    float4* op = (float4*)((float*)a.out + (size_t)row * a.out_stride + c0);
+#pragma unroll
+    for (int c = 0; c < NC; c += 4) op[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  }
+}
+
 template <int COUT>
 __device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt, float* v, int ks = 0) {
   if (a.k_splits > 1) {   // partial sum of one K range -> its own (m, n) slab; summed in fixed order by srf_layernorm

@@ -31,8 +31,17 @@ struct Cfg {
   // For Cin < 64 one ring slot carries G = 64/Cin kernel offsets concatenated along K: the
   // fixed per-slot handshake (~0.3 us: two mbarrier round trips + tcgen05.commit, measured
   // with the copies and MMAs stubbed out) is then paid once per 64 input channels.
-  static constexpr int G = SPARSE ? (CIN >= 64 ? 1 : 64 / CIN) : 1;
-  static constexpr int PPT = CH * G;  // 16-byte pieces per producer thread per slot
+  // Narrow rows (Cin <= 32): measured fastest with the plain mapping -- one producer thread per
+  // tile row, its 27 neighbour indices in registers, one offset per slot, 4 gather warps.
+  static constexpr bool ROWMODE = SPARSE && CH <= 4;
+  static constexpr int G = 1;
+  // producer warps: the sparse gather is bound by loads in flight, so it gets 8 gather warps
+  // (the chunked epilogue keeps the register budget for 2 CTAs/SM at 13 warps each)
+  static constexpr int NPW = (SPARSE && !ROWMODE) ? 8 : 4;
+  static constexpr int NPT = NPW * 32;
+  static constexpr int THREADS = 32 * (4 + NPW + 1);
+  static constexpr int MMA_WARP = 4 + NPW;
+  static constexpr int PPT = CH * G * 128 / NPT;  // 16-byte pieces per producer thread per slot
   static constexpr int A_PAD = CH == 2 ? 64 : (CH == 4 ? 32 : 16);
   static constexpr int A_LBO = 128 * 16 + A_PAD;
   static constexpr int A_MEMBER = CH * A_LBO;
@@ -40,10 +49,10 @@ struct Cfg {
   static constexpr int B_LBO = COUT * 16;
   static constexpr int B_MEMBER = CH * B_LBO;
   // tiny weight sets stay resident in shared memory; otherwise W_k arrives by bulk copy
-  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= 16 * 1024);
+  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= (ROWMODE ? 56 : 16) * 1024);
   static constexpr int W_BYTES = WRES ? (27 * B_MEMBER + 127) / 128 * 128 : 0;
   static constexpr int B_BYTES = WRES ? 0 : G * B_MEMBER;
-  static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
+  static constexpr int IDX_BYTES = (SPARSE && !ROWMODE) ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
   static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
@@ -78,7 +87,7 @@ __device__ __forceinline__ Group<G> pop_group(uint64_t& rem) {
 }
 
 template <int CIN, int COUT, bool SPARSE>
-__global__ void __launch_bounds__(288, (Cfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1)
+__global__ void __launch_bounds__(Cfg<CIN, COUT, SPARSE>::THREADS, (Cfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1)
 igemm_umma_kernel(const IgemmArgs a) {
   using C = Cfg<CIN, COUT, SPARSE>;
   constexpr int S = C::STAGES;
@@ -106,11 +115,11 @@ igemm_umma_kernel(const IgemmArgs a) {
   const uint64_t all_k = a.kvol >= 64 ? ~0ull : ((1ull << a.kvol) - 1ull);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 128 + (C::WRES ? 0 : 1)); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), C::NPT + (C::WRES ? 0 : 1)); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == C::MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -127,7 +136,54 @@ igemm_umma_kernel(const IgemmArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (C::ROWMODE && warp >= 4 && warp < 4 + C::NPW) {
+    // ------------------------------------------------------------------ producers, narrow rows
+    const int pt = threadIdx.x - 128;
+    int it = 0;
+    int idx[27], nxt[27];
+    uint32_t mask = 0xffffffffu, mask_nxt = 0xffffffffu;
+    auto load_idx = [&](int tile, int* dst, uint32_t& m) {
+      const bool live = tile < total_tiles;
+      const int mt = live ? tile % m_tiles : 0;
+      const int row = mt * 128 + pt;
+      m = 0xffffffffu;
+      if (a.tile_mask) m = live ? __ldg(a.tile_mask + mt) : 0u;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        dst[k] = -1;
+        if (live && k < a.kvol && ((m >> k) & 1u) && row < m_rows) dst[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
+      }
+    };
+    load_idx(blockIdx.x, idx, mask);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      load_idx(tile + gridDim.x, nxt, mask_nxt);      // next tile's indices: 27 loads in flight during this tile
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        if (k < a.kvol && ((mask >> k) & 1u)) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int src_row = (a.dbg & 1) ? -1 : idx[k];
+          const __nv_bfloat16* src = src_row >= 0 ? a.in + (size_t)src_row * a.in_stride : a.in;
+          const uint32_t nbytes = src_row >= 0 ? 16u : 0u;
+          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < C::CH; ++c) cp_async16_ca(sa + c * C::A_LBO + pt * 16, src + c * 8, nbytes);
+          if (!C::WRES && pt == 0) {
+            const uint32_t fb = full_bar(s);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)C::B_MEMBER) : "memory");
+            bulk_g2s(sa + C::A_BYTES, a.w + (size_t)k * (size_t)(CIN * COUT), C::B_MEMBER, fb);
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+          ++it;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 27; ++k) idx[k] = nxt[k];
+      mask = mask_nxt;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp >= 4 && warp < 4 + C::NPW) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 128;
     int it = 0;
@@ -146,7 +202,7 @@ igemm_umma_kernel(const IgemmArgs a) {
 #pragma unroll
       for (int k = 0; k < 27; ++k) {
         cur[k] = -1;
-        if (live && k < a.kvol && ((mask >> k) & 1u) && row < m_rows) cur[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
+        if (live && pt < 128 && k < a.kvol && ((mask >> k) & 1u) && row < m_rows) cur[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
       }
     };
     load_idx(blockIdx.x);
@@ -158,10 +214,12 @@ igemm_umma_kernel(const IgemmArgs a) {
       const int mt = tile % m_tiles, nt = (tile % mn_tiles) / m_tiles, ks = tile / mn_tiles;
       uint32_t tmask = mask;
       if (SPARSE) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's indices no longer read
+        asm volatile("bar.sync 1, %0;" ::"n"(C::NPT) : "memory");   // previous tile's indices no longer read
+        if (pt < 128) {
 #pragma unroll
-        for (int k = 0; k < 27; ++k) idx_s[k * 128 + pt] = cur[k];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int k = 0; k < 27; ++k) idx_s[k * 128 + pt] = cur[k];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(C::NPT) : "memory");
         load_idx(tile + gridDim.x);                       // next tile's indices, in flight during the fills
       }
       auto fill = [&](const Group<G>& g) {
@@ -171,9 +229,10 @@ igemm_umma_kernel(const IgemmArgs a) {
         const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
 #pragma unroll
         for (int i = 0; i < C::PPT; ++i) {
-          const int m = i / C::CH;
+          const int Q = i * C::NPT + pt;            // piece index inside the slot
+          const int m = Q / (128 * C::CH);            // group member (kernel offset)
           if (m >= g.n || (a.dbg & 1)) continue;
-          const int q = (i % C::CH) * 128 + pt;
+          const int q = Q % (128 * C::CH);
           const int r = q >> CHS, c = q & (C::CH - 1);
           int src_row;
           if (SPARSE) src_row = idx_s[g.k[m] * 128 + r];
@@ -216,7 +275,7 @@ igemm_umma_kernel(const IgemmArgs a) {
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == 8) {
+  } else if (warp == C::MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     int it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -278,18 +337,32 @@ igemm_umma_kernel(const IgemmArgs a) {
       tc_fence_after();
       const int row = mt * 128 + warp * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * COUT);
-      float v[COUT];
+      if (SPARSE) {
+        // drain the accumulator in 32-column chunks (small register footprint)
+        constexpr int NC = COUT < 32 ? COUT : 32;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += NC) {
+          float v[NC];
 #pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 16) tc_ld16(taddr + c0, v + c0);
-      // accumulator is in registers: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(tempty_bar(buf));
-      if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v, tile / mn_tiles);
+          for (int cc = 0; cc < NC; cc += 16) tc_ld16(taddr + c0 + cc, v + cc);
+          if (row < m_rows && !(a.dbg & 8)) epilogue_chunk<COUT, NC>(a, row, c0, v);
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(buf));
+      } else {
+        float v[COUT];
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) tc_ld16(taddr + c0, v + c0);
+        // accumulator is in registers: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        mbar_arrive(tempty_bar(buf));
+        if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v, tile / mn_tiles);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == C::MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
@@ -312,7 +385,7 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   if (grid > host_tiles) grid = host_tiles;
   if (grid < 1) grid = 1;
   SRF_COUNT(1);
-  igemm_umma_kernel<CIN, COUT, SPARSE><<<grid, 288, C::SMEM_BYTES, st>>>(a);
+  igemm_umma_kernel<CIN, COUT, SPARSE><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("igemm<%d,%d> launch failed: %s", CIN, COUT, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
   return SRF_OK;

@@ -208,3 +208,23 @@ def test_frame_graph_replay_equals_eager():
     assert rel_err(ga_obj.cpu().numpy(), ea_obj.cpu().numpy()) < 1e-6
     assert rel_err(gb_obj.cpu().numpy(), eb_obj.cpu().numpy()) < 1e-6
     assert not torch.equal(ea_bev, eb_bev)
+
+
+@pytest.mark.parametrize('kind,fusion', [('nusc', False), ('nusc', True), ('waymo', False), ('kitti', False)])
+def test_full_frame_pipeline_vs_oracle_fp32(kind, fusion):
+    """Whole measured path (voxelize -> VFE -> SparseEncoder -> 5 region-fusion stages) of every
+    BASELINE config vs the CPU oracle pipeline, FP32 mode, reduced cloud size."""
+    from oracle import cpu_pipeline
+    from srfdet_b200.pipeline import RegionFeaturePipeline
+    pipe = RegionFeaturePipeline(kind, fusion=fusion, precision='fp32')
+    pts = synth.cloud(kind, 41, n_points=30000)
+    ref_bev, ref_obj = cpu_pipeline.run_frame(pipe.state(), kind, synth.GEOM[kind], pipe.d, pts)
+    bev, obj = pipe.run_frame(cuda(pts))
+    assert bev.shape == ref_bev.shape
+    assert rel_err(bev.cpu().numpy(), ref_bev) < 1e-4
+    assert rel_err(obj.cpu().numpy(), ref_obj) < 2e-3      # five chained DynamicConv stages (LayerNorm-amplified)
+    # BF16 mode of the same frame
+    pipe.precision = 'bf16'
+    bev16, obj16 = pipe.run_frame(cuda(pts))
+    assert rel_err(bev16.cpu().numpy(), ref_bev) < 2e-2
+    assert rel_err(obj16.cpu().numpy(), ref_obj) < 1e-1
