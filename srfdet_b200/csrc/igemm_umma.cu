@@ -35,9 +35,10 @@ struct Cfg {
   // tile row, its 27 neighbour indices in registers, one offset per slot, 4 gather warps.
   static constexpr bool ROWMODE = SPARSE && CH <= 4;
   static constexpr int G = 1;
-  // producer warps: the sparse gather is bound by loads in flight, so it gets 8 gather warps
-  // (the chunked epilogue keeps the register budget for 2 CTAs/SM at 13 warps each)
-  static constexpr int NPW = (SPARSE && !ROWMODE) ? 8 : 4;
+  // producer warps: the sparse gather is bound by loads in flight: 16 gather warps for Cin=128
+  // (one CTA per SM), 8 for Cin=64 (two CTAs per SM; one CTA with 16 warps and 8 slots measured
+  // 25 % slower); the chunked epilogue keeps the register budget for that many warps
+  static constexpr int NPW = (SPARSE && !ROWMODE) ? (CH >= 16 ? 16 : 8) : 4;
   static constexpr int NPT = NPW * 32;
   static constexpr int THREADS = 32 * (4 + NPW + 1);
   static constexpr int MMA_WARP = 4 + NPW;
