@@ -237,23 +237,65 @@ __device__ __forceinline__ void warp_gemm(const __nv_bfloat16* sA, int lda, cons
   }
 }
 
+// LayerNorm + ReLU applied directly on mma accumulator fragments.  A row of the 64 x N result
+// is spread over the 4 lanes of a quad (columns) and over the 2 warps that own the two column
+// halves; only the per-row partial sums cross warps (through `st`, 64 rows x 2 halves).
+// acc[i][0..1] belong to row r0, acc[i][2..3] to row r0+8; column of acc[i][e] = colbase + i*8 + 2t + (e&1).
+template <int NT, int N, typename Emit>
+__device__ __forceinline__ void fragment_ln_relu(float (*acc)[4], float* st, float* st2, int r0, int nh, int colbase, int t,
+                                                 const float* __restrict__ gw, const float* __restrict__ gb, Emit emit) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { s0 += acc[i][0] + acc[i][1]; s1 += acc[i][2] + acc[i][3]; }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  if (t == 0) { st[r0 * 2 + nh] = s0; st[(r0 + 8) * 2 + nh] = s1; }
+  __syncthreads();
+  const float m0 = (st[r0 * 2] + st[r0 * 2 + 1]) * (1.f / N), m1 = (st[(r0 + 8) * 2] + st[(r0 + 8) * 2 + 1]) * (1.f / N);
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    float d;
+    d = acc[i][0] - m0; q0 += d * d; d = acc[i][1] - m0; q0 += d * d;
+    d = acc[i][2] - m1; q1 += d * d; d = acc[i][3] - m1; q1 += d * d;
+  }
+  q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  if (t == 0) { st2[r0 * 2 + nh] = q0; st2[(r0 + 8) * 2 + nh] = q1; }
+  __syncthreads();
+  const float rs0 = rsqrtf((st2[r0 * 2] + st2[r0 * 2 + 1]) * (1.f / N) + 1e-5f);
+  const float rs1 = rsqrtf((st2[(r0 + 8) * 2] + st2[(r0 + 8) * 2 + 1]) * (1.f / N) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int col = colbase + i * 8 + 2 * t;
+    const float w0 = __ldg(gw + col), w1 = __ldg(gw + col + 1), b0 = __ldg(gb + col), b1 = __ldg(gb + col + 1);
+    emit(r0, col, fmaxf((acc[i][0] - m0) * rs0 * w0 + b0, 0.f), fmaxf((acc[i][1] - m0) * rs0 * w1 + b1, 0.f));
+    emit(r0 + 8, col, fmaxf((acc[i][2] - m1) * rs1 * w0 + b0, 0.f), fmaxf((acc[i][3] - m1) * rs1 * w1 + b1, 0.f));
+  }
+}
+
 template <int C, int D, typename TR>
-__global__ void __launch_bounds__(256) dynconv_interact_mma_kernel(const TR* __restrict__ roi, const __nv_bfloat16* __restrict__ params,
+__global__ void __launch_bounds__(256, C <= 128 ? 3 : 1) dynconv_interact_mma_kernel(const TR* __restrict__ roi, const __nv_bfloat16* __restrict__ params,
                                                                   const float* __restrict__ ln1_w, const float* __restrict__ ln1_b,
                                                                   const float* __restrict__ ln2_w, const float* __restrict__ ln2_b,
                                                                   __nv_bfloat16* __restrict__ out) {
   constexpr int LDF = C + 8, LDP1 = D + 8, LDP2 = C + 8, LDT = D + 8;   // bf16 pitches (odd multiples of 16 B)
-  constexpr int LT1 = D + 1, LT2 = C + 4;                                // fp32 pitches
   extern __shared__ __align__(16) uint8_t smraw[];
   __nv_bfloat16* sF = reinterpret_cast<__nv_bfloat16*>(smraw);          // 64 x LDF (rows >= 49 zero)
   __nv_bfloat16* sP1 = sF + 64 * LDF;                                    // C x LDP1
   __nv_bfloat16* sP2 = sP1 + C * LDP1;                                   // D x LDP2
-  __nv_bfloat16* sTb = sP2 + D * LDP2;                                   // 64 x LDT  (relu(LN(T1)) in bf16)
-  float* sT = reinterpret_cast<float*>(sTb + 64 * LDT);                  // 64 x LT2 fp32 staging (T1 uses pitch LT1)
+  __nv_bfloat16* sTb = sP2 + D * LDP2;                                   // 64 x LDT  relu(LN(F.P1)) in bf16
+  float* st = reinterpret_cast<float*>(sTb + 64 * LDT);                  // 4 x (64 x 2) row partial sums
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const TR* r = roi + (size_t)k * DC_ROWS * C;
   const __nv_bfloat16* p = params + (size_t)k * 2 * C * D;
+  for (int e = threadIdx.x; e < C * D / 8; e += 256) {          // 16-byte pieces of P1 (C x D) and P2 (D x C)
+    const int row1 = (e * 8) / D, col1 = (e * 8) % D;
+    *reinterpret_cast<uint4*>(sP1 + row1 * LDP1 + col1) = __ldg(reinterpret_cast<const uint4*>(p) + e);
+    const int row2 = (e * 8) / C, col2 = (e * 8) % C;
+    *reinterpret_cast<uint4*>(sP2 + row2 * LDP2 + col2) = __ldg(reinterpret_cast<const uint4*>(p + C * D) + e);
+  }
   for (int e = threadIdx.x; e < 64 * C / 8; e += 256) {          // 8 channels per thread-step
     const int s = (e * 8) / C, i = (e * 8) % C;
     uint4 pk = make_uint4(0u, 0u, 0u, 0u);
@@ -270,80 +312,40 @@ __global__ void __launch_bounds__(256) dynconv_interact_mma_kernel(const TR* __r
     }
     *reinterpret_cast<uint4*>(sF + s * LDF + i) = pk;
   }
-  for (int e = threadIdx.x; e < C * D / 8; e += 256) {          // 16-byte pieces of P1 (C x D) and P2 (D x C)
-    const int row1 = (e * 8) / D, col1 = (e * 8) % D;
-    *reinterpret_cast<uint4*>(sP1 + row1 * LDP1 + col1) = __ldg(reinterpret_cast<const uint4*>(p) + e);
-    const int row2 = (e * 8) / C, col2 = (e * 8) % C;
-    *reinterpret_cast<uint4*>(sP2 + row2 * LDP2 + col2) = __ldg(reinterpret_cast<const uint4*>(p + C * D) + e);
-  }
   __syncthreads();
   const int mt = warp >> 1, nh = warp & 1;
   const int g = lane >> 2, t = lane & 3;
-  {  // T1 = F . P1   (64 x D), warp tile 16 x D/2
+  {  // T1 = F . P1 (64 x D), warp tile 16 x D/2; LayerNorm(D) + ReLU on the fragments -> bf16 A operand
     constexpr int NT = D / 16;
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     warp_gemm<C, NT>(sF + mt * 16 * LDF, LDF, sP1 + nh * (D / 2), LDP1, acc);
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      const int col = nh * (D / 2) + i * 8 + 2 * t;
-      sT[(mt * 16 + g) * LT1 + col] = acc[i][0];
-      sT[(mt * 16 + g) * LT1 + col + 1] = acc[i][1];
-      sT[(mt * 16 + g + 8) * LT1 + col] = acc[i][2];
-      sT[(mt * 16 + g + 8) * LT1 + col + 1] = acc[i][3];
-    }
+    fragment_ln_relu<NT, D>(acc, st, st + 128, mt * 16 + g, nh, nh * (D / 2), t, ln1_w, ln1_b,
+                            [&](int row, int col, float y0, float y1) {
+                              if (row >= DC_ROWS) { y0 = 0.f; y1 = 0.f; }
+                              *reinterpret_cast<__nv_bfloat162*>(sTb + row * LDT + col) = __floats2bfloat162_rn(y0, y1);
+                            });
   }
   __syncthreads();
-  for (int row = warp; row < 64; row += 8) {   // LayerNorm(D) + ReLU -> bf16 A operand of the second GEMM
-    const float* x = sT + row * LT1;
-    float s = 0.f;
-    for (int j = lane; j < D; j += 32) s += x[j];
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / D;
-    float v = 0.f;
-    for (int j = lane; j < D; j += 32) { float d = x[j] - mean; v += d * d; }
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const float rstd = rsqrtf(v / D + 1e-5f);
-    for (int j = lane; j < D; j += 32)
-      sTb[row * LDT + j] = __float2bfloat16(row < DC_ROWS ? fmaxf((x[j] - mean) * rstd * __ldg(ln1_w + j) + __ldg(ln1_b + j), 0.f) : 0.f);
-  }
-  __syncthreads();
-  {  // G = T . P2   (64 x C), warp tile 16 x C/2
+  {  // G = T . P2 (64 x C), warp tile 16 x C/2; LayerNorm(C) + ReLU on the fragments -> global bf16
     constexpr int NT = C / 16;
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     warp_gemm<D, NT>(sTb + mt * 16 * LDT, LDT, sP2 + nh * (C / 2), LDP2, acc);
-#pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      const int col = nh * (C / 2) + i * 8 + 2 * t;
-      *reinterpret_cast<float2*>(sT + (mt * 16 + g) * LT2 + col) = make_float2(acc[i][0], acc[i][1]);
-      *reinterpret_cast<float2*>(sT + (mt * 16 + g + 8) * LT2 + col) = make_float2(acc[i][2], acc[i][3]);
-    }
-  }
-  __syncthreads();
-  __nv_bfloat16* o = out + (size_t)k * DC_ROWS * C;
-  for (int row = warp; row < DC_ROWS; row += 8) {   // LayerNorm(C) + ReLU, write out
-    const float* x = sT + row * LT2;
-    float s = 0.f;
-    for (int j = lane; j < C; j += 32) s += x[j];
-    for (int o2 = 16; o2; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
-    const float mean = s / C;
-    float v = 0.f;
-    for (int j = lane; j < C; j += 32) { float d = x[j] - mean; v += d * d; }
-    for (int o2 = 16; o2; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
-    const float rstd = rsqrtf(v / C + 1e-5f);
-    for (int j = lane; j < C; j += 32)
-      o[(size_t)row * C + j] = __float2bfloat16(fmaxf((x[j] - mean) * rstd * __ldg(ln2_w + j) + __ldg(ln2_b + j), 0.f));
+    __nv_bfloat16* o = out + (size_t)k * DC_ROWS * C;
+    fragment_ln_relu<NT, C>(acc, st + 256, st + 384, mt * 16 + g, nh, nh * (C / 2), t, ln2_w, ln2_b,
+                            [&](int row, int col, float y0, float y1) {
+                              if (row < DC_ROWS) *reinterpret_cast<__nv_bfloat162*>(o + (size_t)row * C + col) = __floats2bfloat162_rn(y0, y1);
+                            });
   }
 }
 
 template <int C, int D, typename TR>
 static int launch_dc_mma(const void* roi, const void* params, int k, const float* a, const float* b, const float* e,
                          const float* f, void* out, cudaStream_t st) {
-  // the T1 (pitch D+1) and T2 (pitch C+4) fp32 stagings share one buffer sized for T2
-  size_t smem = (size_t)(64 * (C + 8) + C * (D + 8) + D * (C + 8) + 64 * (D + 8)) * 2 + (size_t)64 * (C + 4) * 4;
+  size_t smem = (size_t)(64 * (C + 8) + C * (D + 8) + D * (C + 8) + 64 * (D + 8)) * 2 + 4 * 128 * sizeof(float);
   auto kern = dynconv_interact_mma_kernel<C, D, TR>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) { set_error("dynconv mma: cannot get %zu B shared memory: %s", smem, cudaGetErrorString(err)); return SRF_ERR_CUDA; }

@@ -295,6 +295,43 @@ __global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, in
   }
 }
 
+// One block per row, one thread per column (n <= 1024): used when split-K slabs have to be
+// summed -- 4-32 warps per row instead of one keeps enough loads in flight.
+template <typename T>
+__global__ void layernorm_cols_kernel(const T* __restrict__ in, int64_t rows, int n, int n_partials,
+                                      const float* __restrict__ bias, const float* __restrict__ g,
+                                      const float* __restrict__ b, float eps, int relu, T* __restrict__ out) {
+  __shared__ float red[2][32];
+  const int64_t row = blockIdx.x;
+  const int j = threadIdx.x, lane = j & 31, w = j >> 5, nw = (blockDim.x + 31) >> 5;
+  float v = 0.f;
+  if (j < n) {
+    const T* x = in + row * n + j;
+    for (int p = 0; p < n_partials; ++p) v += (float)x[(size_t)p * rows * n];   // slab order: deterministic
+    v += bias ? bias[j] : 0.f;
+  }
+  float s = j < n ? v : 0.f;
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[0][w] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < nw; ++i) tot += red[0][i];
+  const float mean = tot / n;
+  float d = j < n ? v - mean : 0.f;
+  float q = d * d;
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if (lane == 0) red[1][w] = q;
+  __syncthreads();
+  float var = 0.f;
+  for (int i = 0; i < nw; ++i) var += red[1][i];
+  const float rstd = rsqrtf(var / n + eps);
+  if (j < n) {
+    float y = d * rstd * g[j] + b[j];
+    if (relu) y = fmaxf(y, 0.f);
+    out[row * n + j] = (T)y;
+  }
+}
+
 static int lgrid2(int64_t n, int threads) {
   int64_t g = (n + threads - 1) / threads;
   int64_t cap = (int64_t)sm_count() * 8;
@@ -411,9 +448,18 @@ int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_
                   const float* gamma, const float* beta, float eps, int32_t relu, void* out, void* stream) {
   if (n_partials < 1) n_partials = 1;
   SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
-  SRF_CHECK_ARG(n <= 32 * LN_MAXPL, "srf_layernorm: n must be <= %d", 32 * LN_MAXPL);
+  SRF_CHECK_ARG(n <= 32 * LN_MAXPL || (n_partials > 1 && n <= 1024), "srf_layernorm: n must be <= %d", 32 * LN_MAXPL);
   if (rows == 0) return SRF_OK;
   SRF_COUNT(1);
+  if (n_partials > 1 && n <= 1024) {
+    const int threads = (n + 31) / 32 * 32;
+    if (dtype == SRF_BF16)
+      layernorm_cols_kernel<__nv_bfloat16><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (__nv_bfloat16*)out);
+    else
+      layernorm_cols_kernel<float><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (float*)out);
+    SRF_LAUNCH_CHECK();
+    return SRF_OK;
+  }
   int wpb = 4;
   int grid = (int)((rows + wpb - 1) / wpb);
   if (dtype == SRF_BF16)
