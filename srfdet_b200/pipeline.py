@@ -84,6 +84,8 @@ class RegionFeaturePipeline:
         self.kind, self.fusion, self.device = kind, fusion, torch.device(device)
         self.use_graph = use_graph
         self._graphs = {}
+        self.overlap_stage = True
+        self._aux = None
         self.precision = precision or registry.get_precision()
         h = HEAD_CFG[kind]
         self.C, self.d, self.box_dim = h['C'], h['d'], h['box_dim']
@@ -132,7 +134,21 @@ class RegionFeaturePipeline:
     @torch.no_grad()
     def region_stages(self):
         prop = self.prop0
+        main = torch.cuda.current_stream() if self.device.type == 'cuda' else None
         for s in range(N_STAGES):
+            # within a stage the parameter generation (needs the proposal features) and the RoI
+            # sampling (needs the boxes) are independent: they run on two streams and join
+            # before the interaction.  Stages themselves stay sequential, as in the head.
+            params = None
+            if main is not None and self.overlap_stage:
+                if self._aux is None:
+                    self._aux = torch.cuda.Stream()
+                self._aux.wait_event(main.record_event())
+                with torch.cuda.stream(self._aux):
+                    params = self.dynconvs[s].make_params(prop, self.precision)
+                    ev_params = self._aux.record_event()
+                if not torch.cuda.is_current_stream_capturing():
+                    params.record_stream(main)
             boxes = self.stage_boxes[s].clone()          # the sampler de-normalises centres in place
             if self.fusion:
                 img_roi = img_feats_sampling_bboxes_roi(self.img_feats, boxes, self.pooler_img, self.lidar2img, self.pc_range,
@@ -144,7 +160,9 @@ class RegionFeaturePipeline:
             else:
                 roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
                                                        channel_last=True)
-            prop = self.dynconvs[s].forward_kc(prop, roi, precision=self.precision)
+            if params is not None:
+                main.wait_event(ev_params)
+            prop = self.dynconvs[s].forward_kc(prop, roi, precision=self.precision, params=params)
         return prop
 
     @torch.no_grad()

@@ -98,7 +98,13 @@ class DynamicConv(nn.Module):
         self._cache = {}
         return super().load_state_dict(*a, **k)
 
-    def forward_kc(self, prop_feats, roi_feats, precision=None):
+    def make_params(self, prop_feats, precision=None):
+        """dynamic_layer(prop_feats): (K,C) -> (K, 2*C*d).  Depends only on the proposal features,
+        so callers may run it concurrently with the RoI sampling of the same stage."""
+        precision = precision or registry.get_precision()
+        return _linear(prop_feats, self.dynamic_layer, precision, self._cache, ('dyn', str(prop_feats.device)))
+
+    def forward_kc(self, prop_feats, roi_feats, precision=None, params=None):
         """prop_feats (K,C); roi_feats (K,49,C) f32|bf16 (channel-last RoI features) -> (K,C) f32."""
         precision = precision or registry.get_precision()
         lib = L.load()
@@ -106,7 +112,8 @@ class DynamicConv(nn.Module):
         d = self.dynamic_dim
         dev = prop_feats.device
         bf = precision == 'bf16'
-        params = _linear(prop_feats, self.dynamic_layer, precision, self._cache, ('dyn', str(dev)))
+        if params is None:
+            params = self.make_params(prop_feats, precision)
         roi_feats = roi_feats.contiguous()
         inter = torch.empty((k, 49 * c), dtype=torch.bfloat16 if bf else torch.float32, device=dev)
         f = lambda t: L.ptr(t.detach().float().contiguous())
