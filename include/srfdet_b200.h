@@ -247,14 +247,26 @@ typedef struct srf_pyramid {
 int srf_roi_extract(const srf_pyramid* p_host, const float* rois, int32_t k, float* out,
                     int32_t channel_last, void* stream);
 
+/* Destination of the fused samplers.  channel_last = 0: (k, C, 7, 7) f32 (reference layout).
+ * channel_last = 1: rows (k*49 + bin) of row_stride channels (0 -> C), written at channel
+ * offset ch_offset, dtype SRF_F32 | SRF_BF16 -- so the image and BEV samplers can fill the two
+ * halves of the concatenated fusion input (srfdet_head.py:2257) directly, in the GEMM's dtype.
+ * bf16 / strided forms need torch.channels_last feature maps. */
+typedef struct srf_roi_out {
+  void* ptr;
+  int32_t channel_last;
+  int32_t dtype;
+  int32_t row_stride;
+  int32_t ch_offset;
+} srf_roi_out;
+
 /* Fused points_feats_sampling_bboxes_roi (srfdet_head.py:2568-2629 / 1627-1688):
  * centre de-normalisation IN PLACE on `boxes` (:2587) when mutate != 0, corners, BEV
  * rectangle, level map, RoIAlign.  boxes (B, P, box_dim).  Maps are (B, C, H_l, W_l).
  * out as in srf_roi_extract (k = B*P).  rois_out (B*P,5) nullable (for parity checks). */
 int srf_bev_roi_features(const srf_pyramid* p_host, float* boxes, int32_t batch, int32_t n_prop,
                          int32_t box_dim, const float pc_range_host[6], const float voxel_size_host[3],
-                         int32_t mutate, float* out, int32_t channel_last, float* rois_out,
-                         void* stream);
+                         int32_t mutate, const srf_roi_out* out_host, float* rois_out, void* stream);
 
 /* Fused img_feats_sampling_bboxes_roi (srfdet_head.py:2424-2565 / 1963-2099), B = 1
  * semantics: projection by lidar2img (n_cam,4,4), per-camera rectangle,
@@ -262,7 +274,7 @@ int srf_bev_roi_features(const srf_pyramid* p_host, float* boxes, int32_t batch,
  * boxes (P, box_dim) normalised centres, NOT mutated.  rois_out (n_cam*P,5) nullable. */
 int srf_img_roi_features(const srf_pyramid* p_host, const float* boxes, int32_t n_prop, int32_t box_dim,
                          const float* lidar2img, int32_t n_cam, const float pc_range_host[6],
-                         float* out, int32_t channel_last, float* rois_out, void* stream);
+                         const srf_roi_out* out_host, float* rois_out, void* stream);
 
 /* DynamicConv interaction core (srfdet_head.py:2679-2686): per proposal
  *   f = relu(LN_d(feats(49,C) . P1(C,d))) ; g = relu(LN_C(f . P2(d,C)))

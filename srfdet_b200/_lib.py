@@ -38,6 +38,10 @@ class ConvArgs(Structure):
                 ('out_dims', c_int32 * 4)]
 
 
+class RoiOut(Structure):
+    _fields_ = [('ptr', c_void_p), ('channel_last', c_int32), ('dtype', c_int32), ('row_stride', c_int32), ('ch_offset', c_int32)]
+
+
 class Pyramid(Structure):
     _fields_ = [('feat', c_void_p * 4), ('h', c_int32 * 4), ('w', c_int32 * 4), ('stride', c_float * 4),
                 ('n_levels', c_int32), ('channels', c_int32), ('channels_last', c_int32)]
@@ -93,9 +97,9 @@ PROTOTYPES = {
     'srf_boxes_to_corners': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     'srf_roi_extract': (c_int32, [POINTER(Pyramid), c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
     'srf_bev_roi_features': (c_int32, [POINTER(Pyramid), c_void_p, c_int32, c_int32, c_int32, POINTER(c_float),
-                                       POINTER(c_float), c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+                                       POINTER(c_float), c_int32, POINTER(RoiOut), c_void_p, c_void_p]),
     'srf_img_roi_features': (c_int32, [POINTER(Pyramid), c_void_p, c_int32, c_int32, c_void_p, c_int32,
-                                       POINTER(c_float), c_void_p, c_int32, c_void_p, c_void_p]),
+                                       POINTER(c_float), POINTER(RoiOut), c_void_p, c_void_p]),
     'srf_dynconv_interact': (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
 }

@@ -22,6 +22,14 @@ struct Pyr {
   int channels_last;  // maps are (n_img, H, W, C) in memory (torch channels_last) instead of (n_img, C, H, W)
 };
 
+struct OutSpec {
+  void* ptr;
+  int channel_last;  // (k,49,C') rows instead of (k,C,7,7)
+  int bf16;          // bf16 output (channel_last only)
+  int row_stride;    // C' = channels of a destination row (>= C): lets two samplers fill one concatenated buffer
+  int ch_offset;     // first destination channel
+};
+
 struct Taps {
   int off[16];
   float wt[16];
@@ -312,25 +320,30 @@ __device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_
 }
 
 template <int NP>
-__device__ __forceinline__ void store_bin_cl(float* __restrict__ out, int k, int bin, int C, int lane, int channel_last,
-                                             const float4* acc) {
+__device__ __forceinline__ void store_bin_cl(const OutSpec& o, int k, int bin, int C, int lane, const float4* acc) {
 #pragma unroll
   for (int pss = 0; pss < NP; ++pss) {
     const int c = (pss * 32 + lane) * 4;
     if (c >= C) continue;
-    if (channel_last) {
-      *reinterpret_cast<float4*>(out + ((size_t)k * NBIN + bin) * C + c) = acc[pss];
+    if (o.channel_last) {
+      const size_t e = ((size_t)k * NBIN + bin) * o.row_stride + o.ch_offset + c;
+      if (o.bf16) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[pss].x, acc[pss].y), h1 = __floats2bfloat162_rn(acc[pss].z, acc[pss].w);
+        *reinterpret_cast<uint2*>((__nv_bfloat16*)o.ptr + e) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      } else {
+        *reinterpret_cast<float4*>((float*)o.ptr + e) = acc[pss];
+      }
     } else {
-      float* o = out + ((size_t)k * C + c) * NBIN + bin;
-      o[0] = acc[pss].x; o[NBIN] = acc[pss].y; o[2 * NBIN] = acc[pss].z; o[3 * NBIN] = acc[pss].w;
+      float* op = (float*)o.ptr + ((size_t)k * C + c) * NBIN + bin;
+      op[0] = acc[pss].x; op[NBIN] = acc[pss].y; op[2 * NBIN] = acc[pss].z; op[3 * NBIN] = acc[pss].w;
     }
   }
 }
 
 template <int NP>
 __global__ void __launch_bounds__(256) bev_roi_cl_kernel(Pyr p, float* __restrict__ boxes, const float* __restrict__ rois_in,
-                                                        int n_prop, int box_dim, Range rg, int mutate, float* __restrict__ out,
-                                                        int channel_last, float* __restrict__ rois_out) {
+                                                        int n_prop, int box_dim, Range rg, int mutate, OutSpec out,
+                                                        float* __restrict__ rois_out) {
   __shared__ int s_off[NTAP];
   __shared__ float s_wt[NTAP];
   const int k = blockIdx.x;
@@ -371,7 +384,7 @@ __global__ void __launch_bounds__(256) bev_roi_cl_kernel(Pyr p, float* __restric
 #pragma unroll
     for (int q = 0; q < NP; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     bin_accumulate_cl<NP>(base, s_off, s_wt, bin, p.channels, lane, acc);
-    store_bin_cl<NP>(out, k, bin, p.channels, lane, channel_last, acc);
+    store_bin_cl<NP>(out, k, bin, p.channels, lane, acc);
   }
 }
 
@@ -380,7 +393,7 @@ constexpr int IMG_MAX_CAM = 8;
 template <int NP>
 __global__ void __launch_bounds__(256) img_roi_cl_kernel(Pyr p, const float* __restrict__ boxes, int n_prop, int box_dim,
                                                         const float* __restrict__ lidar2img, int n_cam, Range rg,
-                                                        float* __restrict__ out, int channel_last, float* __restrict__ rois_out) {
+                                                        OutSpec out, float* __restrict__ rois_out) {
   extern __shared__ __align__(16) uint8_t sm_img[];
   int* s_off = reinterpret_cast<int*>(sm_img);                 // [n_cam][NTAP]
   float* s_wt = reinterpret_cast<float*>(s_off + n_cam * NTAP);
@@ -426,7 +439,7 @@ __global__ void __launch_bounds__(256) img_roi_cl_kernel(Pyr p, const float* __r
       const float* base = p.feat[sg[cam].lvl] + (size_t)cam * sg[cam].H * sg[cam].W * p.channels;
       bin_accumulate_cl<NP>(base, s_off + cam * NTAP, s_wt + cam * NTAP, bin, p.channels, lane, acc);
     }
-    store_bin_cl<NP>(out, k, bin, p.channels, lane, channel_last, acc);
+    store_bin_cl<NP>(out, k, bin, p.channels, lane, acc);
   }
 }
 
@@ -470,6 +483,25 @@ int srf_boxes_to_corners(const float* boxes, int32_t nb, int32_t box_dim, float*
   return SRF_OK;
 }
 
+static int make_out(OutSpec* o, const srf_roi_out* u, int channels, bool cl_maps, const char* who) {
+  if (!u || !u->ptr) { set_error("%s: null output", who); return SRF_ERR_ARG; }
+  o->ptr = u->ptr;
+  o->channel_last = u->channel_last;
+  o->bf16 = u->dtype == SRF_BF16;
+  o->row_stride = u->row_stride > 0 ? u->row_stride : channels;
+  o->ch_offset = u->ch_offset;
+  const bool plain = !o->bf16 && o->row_stride == channels && o->ch_offset == 0;
+  if (!plain && !(cl_maps && o->channel_last)) {
+    set_error("%s: bf16 / strided output needs channel_last output and channels_last feature maps", who);
+    return SRF_ERR_UNSUPPORTED;
+  }
+  if (o->row_stride < o->ch_offset + channels || (o->row_stride % 4) || (o->ch_offset % 4)) {
+    set_error("%s: bad output row stride / channel offset", who);
+    return SRF_ERR_ARG;
+  }
+  return SRF_OK;
+}
+
 int srf_roi_extract(const srf_pyramid* p, const float* rois, int32_t k, float* out, int32_t channel_last, void* stream) {
   Pyr d;
   SRF_CHECK_ARG(make_pyr(&d, p) == 0, "srf_roi_extract: bad pyramid");
@@ -478,8 +510,9 @@ int srf_roi_extract(const srf_pyramid* p, const float* rois, int32_t k, float* o
   SRF_COUNT(1);
   if (d.channels_last) {
     Range rg = {};
-    if (d.channels <= 128) bev_roi_cl_kernel<1><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, out, channel_last, nullptr);
-    else bev_roi_cl_kernel<2><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, out, channel_last, nullptr);
+    OutSpec o{out, channel_last, 0, d.channels, 0};
+    if (d.channels <= 128) bev_roi_cl_kernel<1><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, o, nullptr);
+    else bev_roi_cl_kernel<2><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, o, nullptr);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }
@@ -489,18 +522,22 @@ int srf_roi_extract(const srf_pyramid* p, const float* rois, int32_t k, float* o
 }
 
 int srf_bev_roi_features(const srf_pyramid* p, float* boxes, int32_t batch, int32_t n_prop, int32_t box_dim,
-                         const float pc_range[6], const float voxel_size[3], int32_t mutate, float* out,
-                         int32_t channel_last, float* rois_out, void* stream) {
+                         const float pc_range[6], const float voxel_size[3], int32_t mutate, const srf_roi_out* out_spec,
+                         float* rois_out, void* stream) {
   Pyr d;
   SRF_CHECK_ARG(make_pyr(&d, p) == 0, "srf_bev_roi_features: bad pyramid");
-  SRF_CHECK_ARG(boxes && pc_range && voxel_size && out && batch >= 1 && n_prop >= 0 && box_dim >= 8, "srf_bev_roi_features: bad args");
+  SRF_CHECK_ARG(boxes && pc_range && voxel_size && batch >= 1 && n_prop >= 0 && box_dim >= 8, "srf_bev_roi_features: bad args");
+  OutSpec o;
+  { int rc = make_out(&o, out_spec, d.channels, d.channels_last != 0, "srf_bev_roi_features"); if (rc) return rc; }
+  float* out = (float*)o.ptr;
+  const int channel_last = o.channel_last;
   if (n_prop == 0) return SRF_OK;
   Range rg;
   make_range(&rg, pc_range, voxel_size);
   SRF_COUNT(1);
   if (d.channels_last) {
-    if (d.channels <= 128) bev_roi_cl_kernel<1><<<batch * n_prop, 256, 0, (cudaStream_t)stream>>>(d, boxes, nullptr, n_prop, box_dim, rg, mutate, out, channel_last, rois_out);
-    else bev_roi_cl_kernel<2><<<batch * n_prop, 256, 0, (cudaStream_t)stream>>>(d, boxes, nullptr, n_prop, box_dim, rg, mutate, out, channel_last, rois_out);
+    if (d.channels <= 128) bev_roi_cl_kernel<1><<<batch * n_prop, 256, 0, (cudaStream_t)stream>>>(d, boxes, nullptr, n_prop, box_dim, rg, mutate, o, rois_out);
+    else bev_roi_cl_kernel<2><<<batch * n_prop, 256, 0, (cudaStream_t)stream>>>(d, boxes, nullptr, n_prop, box_dim, rg, mutate, o, rois_out);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }
@@ -510,11 +547,15 @@ int srf_bev_roi_features(const srf_pyramid* p, float* boxes, int32_t batch, int3
 }
 
 int srf_img_roi_features(const srf_pyramid* p, const float* boxes, int32_t n_prop, int32_t box_dim,
-                         const float* lidar2img, int32_t n_cam, const float pc_range[6], float* out,
-                         int32_t channel_last, float* rois_out, void* stream) {
+                         const float* lidar2img, int32_t n_cam, const float pc_range[6], const srf_roi_out* out_spec,
+                         float* rois_out, void* stream) {
   Pyr d;
   SRF_CHECK_ARG(make_pyr(&d, p) == 0, "srf_img_roi_features: bad pyramid");
-  SRF_CHECK_ARG(boxes && lidar2img && pc_range && out && n_prop >= 0 && box_dim >= 8 && n_cam >= 1, "srf_img_roi_features: bad args");
+  SRF_CHECK_ARG(boxes && lidar2img && pc_range && n_prop >= 0 && box_dim >= 8 && n_cam >= 1, "srf_img_roi_features: bad args");
+  OutSpec o;
+  { int rc = make_out(&o, out_spec, d.channels, d.channels_last != 0, "srf_img_roi_features"); if (rc) return rc; }
+  float* out = (float*)o.ptr;
+  const int channel_last = o.channel_last;
   SRF_CHECK_ARG(d.channels <= 256, "srf_img_roi_features: at most 256 channels (got %d)", d.channels);
   if (n_prop == 0) return SRF_OK;
   Range rg;
@@ -528,8 +569,8 @@ int srf_img_roi_features(const srf_pyramid* p, const float* boxes, int32_t n_pro
       SRF_CUDA(cudaFuncSetAttribute(img_roi_cl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SRF_CUDA(cudaFuncSetAttribute(img_roi_cl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (d.channels <= 128) img_roi_cl_kernel<1><<<n_prop, 256, smem, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
-    else img_roi_cl_kernel<2><<<n_prop, 256, smem, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, out, channel_last, rois_out);
+    if (d.channels <= 128) img_roi_cl_kernel<1><<<n_prop, 256, smem, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, o, rois_out);
+    else img_roi_cl_kernel<2><<<n_prop, 256, smem, st>>>(d, boxes, n_prop, box_dim, lidar2img, n_cam, rg, o, rois_out);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }

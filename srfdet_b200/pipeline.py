@@ -15,6 +15,8 @@ box-regression rows of a stage.  The RoI stage therefore samples *synthetic* FPN
 features chain from stage to stage through DynamicConv.
 """
 import numpy as np
+import contextlib
+
 import torch
 
 from . import synth
@@ -86,6 +88,7 @@ class RegionFeaturePipeline:
         self._graphs = {}
         self.overlap_stage = True
         self._aux = None
+        self._aux2 = None
         self.precision = precision or registry.get_precision()
         h = HEAD_CFG[kind]
         self.C, self.d, self.box_dim = h['C'], h['d'], h['box_dim']
@@ -150,7 +153,29 @@ class RegionFeaturePipeline:
                 if not torch.cuda.is_current_stream_capturing():
                     params.record_stream(main)
             boxes = self.stage_boxes[s].clone()          # the sampler de-normalises centres in place
-            if self.fusion:
+            if self.fusion and self.channels_last:
+                # both samplers fill their half of the concatenated fusion input
+                # (cat(img, pts), srfdet_head.py:2257) directly, in the GEMM's dtype, concurrently.
+                # The image sampler reads the still-normalised stage boxes, the BEV one its clone.
+                cat = torch.empty((N_PROP, 49, 2 * self.C), device=self.device,
+                                  dtype=torch.bfloat16 if self.precision == 'bf16' else torch.float32)
+                fork = main is not None and self.overlap_stage
+                if fork:
+                    if self._aux2 is None:
+                        self._aux2 = torch.cuda.Stream()
+                    self._aux2.wait_event(main.record_event())
+                with (torch.cuda.stream(self._aux2) if fork else contextlib.nullcontext()):
+                    img_feats_sampling_bboxes_roi(self.img_feats, self.stage_boxes[s], self.pooler_img, self.lidar2img,
+                                                  self.pc_range, channel_last=True, out=cat, ch_offset=0)
+                    if fork:
+                        ev_img = self._aux2.record_event()
+                points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
+                                                 channel_last=True, out=cat, ch_offset=self.C)
+                if fork:
+                    main.wait_event(ev_img)
+                roi = _head._linear(cat.view(N_PROP * 49, 2 * self.C), self.fuse[s], self.precision, self._fuse_cache[s],
+                                    'fuse').view(N_PROP, 49, self.C)
+            elif self.fusion:
                 img_roi = img_feats_sampling_bboxes_roi(self.img_feats, boxes, self.pooler_img, self.lidar2img, self.pc_range,
                                                         channel_last=True)
                 pts_roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,

@@ -17,7 +17,7 @@ from torch import nn
 from .. import _lib as L
 from . import registry
 from .registry import HEADS
-from .roi import img_feats_sampling_bboxes_roi, points_feats_sampling_bboxes_roi
+from .roi import img_feats_sampling_bboxes_roi, maps_channels_last, points_feats_sampling_bboxes_roi
 
 _DEFAULT_SCALE_CLAMP = math.log(100000.0 / 16)
 
@@ -257,6 +257,19 @@ class SingleSRFDetHead(_SingleHeadBase):
         concat + Linear(2C->C) (srfdet_head.py:2236-2264)."""
         precision = precision or registry.get_precision()
         img_roi = pts_roi = None
+        if (self.use_fusion and img_feats is not None and point_feats is not None
+                and maps_channels_last([f[0] for f in img_feats], pooler_img.num_inputs)
+                and maps_channels_last(point_feats, pooler.num_inputs)):
+            # both samplers write their half of cat(img, pts) (srfdet_head.py:2257) in the GEMM's dtype
+            k, c = bboxes.shape[0] * bboxes.shape[1], point_feats[0].shape[1]
+            cat = torch.empty((k, 49, 2 * c), device=bboxes.device,
+                              dtype=torch.bfloat16 if precision == 'bf16' else torch.float32)
+            img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler_img, lidar2img, self.pc_range_lidar,
+                                          channel_last=True, out=cat, ch_offset=0)
+            points_feats_sampling_bboxes_roi(point_feats, bboxes, pooler, self.pc_range_lidar, self.voxel_size_lidar,
+                                             channel_last=True, out=cat, ch_offset=c)
+            fused = _linear(cat.view(k * 49, 2 * c), self.output_fused_proj, precision, self._cache, ('fuse', str(cat.device)))
+            return fused.view(k, 49, -1)
         if img_feats is not None:
             img_roi = img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler_img, lidar2img, self.pc_range_lidar,
                                                     channel_last=True)

@@ -20,15 +20,22 @@ def bbox2roi(bbox_list):
     return torch.cat(out, 0)
 
 
+def maps_channels_last(feats, n_levels=None):
+    """True when every level is a torch.channels_last tensor (NHWC in memory) the coalesced
+    kernels consume in place."""
+    n_levels = len(feats) if n_levels is None else min(n_levels, len(feats))
+    c = feats[0].shape[-3]
+    return c % 4 == 0 and c <= 256 and all(
+        f.dim() == 4 and f.shape[1] > 1 and not f.is_contiguous() and f.is_contiguous(memory_format=torch.channels_last)
+        for f in feats[:n_levels])
+
+
 def _pyramid(feats, strides, n_levels):
     p = L.Pyramid()
     n_levels = min(n_levels, len(feats))
     c = feats[0].shape[-3]
     keep = []
-    # torch.channels_last maps (NHWC in memory) are consumed in place by the coalesced kernels
-    cl = c % 4 == 0 and c <= 256 and all(
-        f.dim() == 4 and f.shape[1] > 1 and not f.is_contiguous() and f.is_contiguous(memory_format=torch.channels_last)
-        for f in feats[:n_levels])
+    cl = maps_channels_last(feats, n_levels)
     p.channels_last = int(cl)
     for l in range(n_levels):
         f = feats[l]
@@ -92,24 +99,38 @@ class SingleRoIExtractor(nn.Module):
         return out
 
 
+def _roi_out(k, c, channel_last, device, out=None, ch_offset=0):
+    """Destination spec: a fresh (k,C,7,7) / (k,49,C) fp32 tensor, or a caller-provided
+    channel-last (k,49,C') fp32|bf16 buffer filled at channel offset `ch_offset`."""
+    if out is None:
+        out = torch.empty((k, 49, c) if channel_last else (k, c, 7, 7), dtype=torch.float32, device=device)
+        spec = L.RoiOut(out.data_ptr(), int(channel_last), L.F32, c, 0)
+    else:
+        assert out.is_contiguous() and out.dim() == 3 and out.shape[0] == k and out.shape[1] == 49
+        assert out.dtype in (torch.float32, torch.bfloat16)
+        spec = L.RoiOut(out.data_ptr(), 1, L.BF16 if out.dtype == torch.bfloat16 else L.F32, out.shape[2], int(ch_offset))
+    return out, spec
+
+
 def points_feats_sampling_bboxes_roi(points_feats, bboxes, pooler, pc_range, voxel_size, channel_last=False,
-                                     return_rois=False):
+                                     return_rois=False, out=None, ch_offset=0):
     """Fused srfdet_head.py:2568-2629.  bboxes (bs, n_p, >=8) normalised centres; the
-    centres are de-normalised IN PLACE like the reference (:2587).  -> (bs*n_p, C, 7, 7)."""
+    centres are de-normalised IN PLACE like the reference (:2587).  -> (bs*n_p, C, 7, 7)
+    (or channel-last (bs*n_p, 49, C); `out`/`ch_offset`: write into a slice of a caller buffer)."""
     assert bboxes.is_contiguous() and bboxes.dtype == torch.float32
     bs, n_p, d = bboxes.shape
     p, keep = _pyramid(points_feats, pooler.featmap_strides, pooler.num_inputs)
     c = p.channels
     k = bs * n_p
-    out = torch.empty((k, 49, c) if channel_last else (k, c, 7, 7), dtype=torch.float32, device=bboxes.device)
+    out, spec = _roi_out(k, c, channel_last, bboxes.device, out, ch_offset)
     rois = torch.empty((k, 5), dtype=torch.float32, device=bboxes.device) if return_rois else None
     L.check(L.load().srf_bev_roi_features(ctypes.byref(p), L.ptr(bboxes), bs, n_p, d, L.f6(pc_range), L.f3(voxel_size), 1,
-                                          L.ptr(out), int(channel_last), L.ptr(rois), L.stream_ptr()), 'srf_bev_roi_features')
+                                          ctypes.byref(spec), L.ptr(rois), L.stream_ptr()), 'srf_bev_roi_features')
     return (out, rois) if return_rois else out
 
 
 def img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler, lidar2img, pc_range, channel_last=False,
-                                  return_rois=False):
+                                  return_rois=False, out=None, ch_offset=0):
     """Fused srfdet_head.py:2424-2565 (B = 1 semantics).  img_feats: list of
     (1, n_cam, C, H, W); bboxes (1, n_p, >=8) (not mutated); lidar2img (n_cam,4,4) tensor."""
     assert bboxes.shape[0] == 1 and img_feats[0].shape[0] == 1, 'image branch is built for batch size 1 (as the reference is)'
@@ -120,8 +141,8 @@ def img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler, lidar2img, pc_range
     n_cam = flat[0].shape[0]
     l2i = lidar2img.reshape(n_cam, 4, 4).contiguous().float()
     c = p.channels
-    out = torch.empty((n_p, 49, c) if channel_last else (n_p, c, 7, 7), dtype=torch.float32, device=b.device)
+    out, spec = _roi_out(n_p, c, channel_last, b.device, out, ch_offset)
     rois = torch.empty((n_cam * n_p, 5), dtype=torch.float32, device=b.device) if return_rois else None
-    L.check(L.load().srf_img_roi_features(ctypes.byref(p), L.ptr(b), n_p, d, L.ptr(l2i), n_cam, L.f6(pc_range), L.ptr(out),
-                                          int(channel_last), L.ptr(rois), L.stream_ptr()), 'srf_img_roi_features')
+    L.check(L.load().srf_img_roi_features(ctypes.byref(p), L.ptr(b), n_p, d, L.ptr(l2i), n_cam, L.f6(pc_range),
+                                          ctypes.byref(spec), L.ptr(rois), L.stream_ptr()), 'srf_img_roi_features')
     return (out, rois) if return_rois else out

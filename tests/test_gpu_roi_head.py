@@ -113,6 +113,35 @@ def test_channels_last_maps_match_nchw(C):
         assert rel_err(r1.cpu().numpy(), r0.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_samplers_fill_concatenated_buffer(dtype):
+    """out= / ch_offset=: image and BEV samplers write the two halves of cat(img, pts)
+    (srfdet_head.py:2257) into one channel-last buffer, fp32 exact / bf16 rounded."""
+    from srfdet_b200.plugin import img_feats_sampling_bboxes_roi, points_feats_sampling_bboxes_roi
+    C = 128
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+    feats = [cl(cuda(f)) for f in synth.feature_pyramid(7, C, (184, 184), 4, lead=(1,))]
+    ifeats = [cl(cuda(synth.hash_field((6, C, 232 // 2 ** i, 400 // 2 ** i), 60 + i))).unsqueeze(0) for i in range(4)]
+    l2i = cuda(synth.lidar2img(6, 1)[0])
+    boxes = synth.proposals(8, 300, 10, 1)
+    pool, pooli = _pooler([8, 16, 32, 64], C), _pooler([4, 8, 16, 32], C)
+    img = img_feats_sampling_bboxes_roi(ifeats, cuda(boxes.copy()), pooli, l2i, PC, channel_last=True)
+    pts = points_feats_sampling_bboxes_roi(feats, cuda(boxes.copy()), pool, PC, VS, channel_last=True)
+    ref = torch.cat((img, pts), dim=2)
+    cat = torch.full((300, 49, 2 * C), float('nan'), dtype=dtype, device='cuda')
+    r = img_feats_sampling_bboxes_roi(ifeats, cuda(boxes.copy()), pooli, l2i, PC, channel_last=True, out=cat, ch_offset=0)
+    assert r.data_ptr() == cat.data_ptr()
+    points_feats_sampling_bboxes_roi(feats, cuda(boxes.copy()), pool, PC, VS, channel_last=True, out=cat, ch_offset=C)
+    if dtype == torch.float32:
+        assert torch.equal(cat, ref)
+    else:
+        assert torch.equal(cat, ref.to(torch.bfloat16))
+    # NCHW maps cannot take the strided form: loud error, no silent fallback
+    with pytest.raises(RuntimeError):
+        points_feats_sampling_bboxes_roi([f.contiguous() for f in feats], cuda(boxes.copy()), pool, PC, VS,
+                                         channel_last=True, out=cat, ch_offset=C)
+
+
 def test_img_roi_production_size_vs_oracle():
     """6 cameras x 900 proposals (configs/nus/srfdet_voxel_nusc_LC.py), C reduced to 32 to bound
     oracle time; includes behind-camera boxes (degenerate rectangles that must read zeros)."""
@@ -200,13 +229,18 @@ def test_single_head_lidar_golden(golden_dir):
     assert rel_err(pred.cpu().numpy(), z['pred']) < 2e-4
 
 
-def test_single_head_fusion_golden(golden_dir):
-    """SingleSRFDetHead.forward with use_fusion=True (srfdet_head.py:2221-2326): image RoIs + BEV RoIs + fusion."""
+@pytest.mark.parametrize('maps_cl', [False, True])
+def test_single_head_fusion_golden(golden_dir, maps_cl):
+    """SingleSRFDetHead.forward with use_fusion=True (srfdet_head.py:2221-2326): image RoIs + BEV RoIs + fusion.
+    maps_cl: torch.channels_last maps -> the samplers write the concatenated fusion input directly."""
     from srfdet_b200.plugin import SingleSRFDetHead
     z = _z(golden_dir, 'head_fusion.npz')
     head, C = _load_head(SingleSRFDetHead, z, use_fusion=True)
     pf = [cuda(synth.hash_field((2, C, 184 // 2 ** i, 184 // 2 ** i), int(z['feat_seed']) + i)[:1]) for i in range(4)]
     imf = [cuda(synth.hash_field((1, 6, C, 232 // 2 ** i, 400 // 2 ** i), int(z['ifeat_seed']) + i)) for i in range(4)]
+    if maps_cl:
+        pf = [f.contiguous(memory_format=torch.channels_last) for f in pf]
+        imf = [f[0].contiguous(memory_format=torch.channels_last).unsqueeze(0) for f in imf]
     boxes = cuda(z['boxes'].copy())
     metas = [dict(lidar2img=z['lidar2img'][0])]
     with torch.no_grad():
