@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, 'csrc', 'libsrfdet_b200.so')
+# SRFDET_B200_LIB: development variants of the same library (e.g. the -DSRF_IGEMM_PROF build)
+SO_PATH = os.environ.get('SRFDET_B200_LIB') or os.path.join(_HERE, 'csrc', 'libsrfdet_b200.so')
 
 F32, BF16 = 0, 1
 

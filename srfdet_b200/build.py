@@ -32,14 +32,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return SO
+def build(force=False, verbose=False, defines=(), so=SO):
+    """defines/so: development variants (e.g. -DSRF_IGEMM_PROF -> libsrfdet_b200_prof.so, tools/igemm_prof.py)."""
+    if not force and not defines and not needs_build():
+        return so
     objs = []
     procs = []
+    tag = '_' + os.path.basename(so).replace('libsrfdet_b200_', '').replace('.so', '') if defines else ''
     for s in SOURCES:
-        obj = os.path.join(CSRC, s.replace('.cu', '.o'))
-        cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, s), '-o', obj]
+        obj = os.path.join(CSRC, s.replace('.cu', tag + '.o'))
+        if defines and s != 'igemm_umma.cu' and os.path.exists(os.path.join(CSRC, s.replace('.cu', '.o'))):
+            objs.append(os.path.join(CSRC, s.replace('.cu', '.o')))      # variants only touch the igemm kernel
+            continue
+        cmd = ([_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else [])
+               + ['-c', os.path.join(CSRC, s), '-o', obj])
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -50,10 +56,16 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    link = [_nvcc(), '-shared', '-o', SO] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    link = [_nvcc(), '-shared', '-o', so] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.check_call(link)
-    return SO
+    return so
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--variant' in sys.argv:      # python -m srfdet_b200.build --variant NAME MACRO=VALUE ...
+        i = sys.argv.index('--variant')
+        print(build(force=True, defines=tuple(sys.argv[i + 2:]), so=SO.replace('.so', '_' + sys.argv[i + 1] + '.so')))
+    elif '--prof' in sys.argv:
+        print(build(force=True, defines=('SRF_IGEMM_PROF=' + ('2' if '--stages' in sys.argv else '1'),), so=SO.replace('.so', '_prof.so')))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

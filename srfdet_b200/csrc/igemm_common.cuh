@@ -72,6 +72,29 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
          ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
+// one elected lane of a converged warp (ptxas recognises elect.sync and emits the single-thread
+// region without per-instruction broadcast loops around UTCHMMA / UTCBAR)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+
+// descriptor from its two 32-bit halves; the high half of every no-swizzle K-major descriptor used
+// here is constant: SBO = 128 B (>>4 at bit 32) | version 1 (bit 46)
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 __device__ __forceinline__ int k_first(int tile, int kvol) { return (int)(((unsigned)tile * 11u) % (unsigned)kvol); }
 
 struct IgemmArgs {

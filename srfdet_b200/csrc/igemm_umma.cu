@@ -25,24 +25,66 @@
 #include "igemm_common.cuh"
 
 namespace srf {
+// Per-role cycle counters (development builds only: -DSRF_IGEMM_PROF, tools/igemm_prof.py)
+#ifdef SRF_IGEMM_PROF
+__device__ unsigned long long g_prof[1024 * 16];
+__device__ unsigned long long g_prof_t[64 * 1024 * 4];   // [launch % 64][cta] globaltimer: CTA start, main loop start, CTA end
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PROF_T(slot_) if (threadIdx.x == 0) g_prof_t[(((a.dbg >> 16) & 63) * 1024 + (blockIdx.x & 1023)) * 4 + (slot_)] = gtimer()
+// event trace of CTA 0 of every launch: (code << 56 | globaltimer); codes: 1 idx publish begin, 2 publish end,
+// 3 slots of the tile issued, 4 MMA tile begin, 5 MMA tile committed, 6 epilogue begin, 7 epilogue end
+__device__ unsigned long long g_trace[64 * 256];
+__device__ int g_trace_n[64];
+#define PROF_TRACE(code_) do { if (blockIdx.x == 0) { const int l_ = (a.dbg >> 16) & 63; const int i_ = atomicAdd(&g_trace_n[l_], 1); if (i_ < 256) g_trace[l_ * 256 + i_] = ((unsigned long long)(code_) << 56) | (gtimer() & 0x00ffffffffffffffull); } } while (0)
+#define PROF_TBEGIN(v_) v_ -= clock64()
+#define PROF_TEND(v_) v_ += clock64()
+#if SRF_IGEMM_PROF >= 2      // per-stage cycle counters (perturb the loops by ~200 clk per slot)
+#define PROF_DECL(v_) long long v_ = 0
+#define PROF_BEGIN(v_) v_ -= clock64()
+#define PROF_END(v_) v_ += clock64()
+#else
+#define PROF_DECL(v_) long long v_ = 0
+#define PROF_BEGIN(v_)
+#define PROF_END(v_)
+#endif
+#define PROF_STORE(slot_, v_) g_prof[(blockIdx.x & 1023) * 16 + (slot_)] = (unsigned long long)(v_)
+#else
+#define PROF_DECL(v_)
+#define PROF_BEGIN(v_)
+#define PROF_END(v_)
+#define PROF_STORE(slot_, v_)
+#define PROF_T(slot_)
+#define PROF_TBEGIN(v_)
+#define PROF_TEND(v_)
+#define PROF_TRACE(code_)
+#endif
+
+// gather warps per CTA for rows of <= 4 / 8 / 16 chunks (A/B knobs)
+#ifndef SRF_IGEMM_NPW_NARROW
+#define SRF_IGEMM_NPW_NARROW 4
+#endif
+#ifndef SRF_IGEMM_NPW_64
+#define SRF_IGEMM_NPW_64 4
+#endif
+#ifndef SRF_IGEMM_NPW_128
+#define SRF_IGEMM_NPW_128 8
+#endif
+
 template <int CIN, int COUT, bool SPARSE>
 struct Cfg {
   static constexpr int CH = CIN / 8;  // 16-byte chunks per A row
-  // For Cin < 64 one ring slot carries G = 64/Cin kernel offsets concatenated along K: the
-  // fixed per-slot handshake (~0.3 us: two mbarrier round trips + tcgen05.commit, measured
-  // with the copies and MMAs stubbed out) is then paid once per 64 input channels.
-  // Narrow rows (Cin <= 32): measured fastest with the plain mapping -- one producer thread per
-  // tile row, its 27 neighbour indices in registers, one offset per slot, 4 gather warps.
-  static constexpr bool ROWMODE = SPARSE && CH <= 4;
-  static constexpr int G = 1;
+  // For Cin = 16 one ring slot carries G = 4 kernel offsets (K = 64 per slot): the fixed
+  // per-slot cost of the ring (~0.4 us per slot) is then paid once per 64 input channels.
+  // (measured: 16-channel layers -15 %; at Cin = 32 the doubled slot leaves too few slots in 104 KB)
+  static constexpr int G = (SPARSE && CIN == 16) ? 4 : 1;
   // producer warps: the sparse gather is bound by loads in flight: 16 gather warps for Cin=128
   // (one CTA per SM), 8 for Cin=64 (two CTAs per SM; one CTA with 16 warps and 8 slots measured
   // 25 % slower); the chunked epilogue keeps the register budget for that many warps
-  static constexpr int NPW = (SPARSE && !ROWMODE) ? (CH >= 16 ? 16 : 8) : 4;
+  static constexpr int NPW = SPARSE ? (CH >= 16 ? SRF_IGEMM_NPW_128 : (CH >= 8 ? SRF_IGEMM_NPW_64 : SRF_IGEMM_NPW_NARROW)) : 4;
   static constexpr int NPT = NPW * 32;
   static constexpr int THREADS = 32 * (4 + NPW + 1);
   static constexpr int MMA_WARP = 4 + NPW;
-  static constexpr int PPT = CH * G * 128 / NPT;  // 16-byte pieces per producer thread per slot
+  static constexpr int PPT = CH * 128 / NPT;  // 16-byte pieces per producer thread per kernel offset
   static constexpr int A_PAD = CH == 2 ? 64 : (CH == 4 ? 32 : 16);
   static constexpr int A_LBO = 128 * 16 + A_PAD;
   static constexpr int A_MEMBER = CH * A_LBO;
@@ -50,10 +92,10 @@ struct Cfg {
   static constexpr int B_LBO = COUT * 16;
   static constexpr int B_MEMBER = CH * B_LBO;
   // tiny weight sets stay resident in shared memory; otherwise W_k arrives by bulk copy
-  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= (ROWMODE ? 56 : 16) * 1024);
+  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= (CH <= 4 ? 56 : 16) * 1024);
   static constexpr int W_BYTES = WRES ? (27 * B_MEMBER + 127) / 128 * 128 : 0;
   static constexpr int B_BYTES = WRES ? 0 : G * B_MEMBER;
-  static constexpr int IDX_BYTES = (SPARSE && !ROWMODE) ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
+  static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
   static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
@@ -106,6 +148,7 @@ igemm_umma_kernel(const IgemmArgs a) {
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * S + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * S + 2 + b); };
 
+  PROF_T(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_rows = SPARSE ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
   const int m_tiles = (m_rows + 127) >> 7;
@@ -116,7 +159,7 @@ igemm_umma_kernel(const IgemmArgs a) {
   const uint64_t all_k = a.kvol >= 64 ? ~0ull : ((1ull << a.kvol) - 1ull);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), C::NPT + (C::WRES ? 0 : 1)); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), ((SPARSE && (a.dbg & 128)) ? C::NPW : C::NPT) + (C::WRES ? 0 : 1)); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -135,56 +178,13 @@ igemm_umma_kernel(const IgemmArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // (the OR-reduction is a no-op on the value: it tells the compiler the address is warp-uniform,
+  // which keeps the MMA issue sequence free of per-instruction broadcast loops)
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+  const uint32_t stage_u32 = smem_u32(stage_base), wres_u32 = smem_u32(w_res);
+  PROF_T(1);
 
-  if (C::ROWMODE && warp >= 4 && warp < 4 + C::NPW) {
-    // ------------------------------------------------------------------ producers, narrow rows
-    const int pt = threadIdx.x - 128;
-    int it = 0;
-    int idx[27], nxt[27];
-    uint32_t mask = 0xffffffffu, mask_nxt = 0xffffffffu;
-    auto load_idx = [&](int tile, int* dst, uint32_t& m) {
-      const bool live = tile < total_tiles;
-      const int mt = live ? tile % m_tiles : 0;
-      const int row = mt * 128 + pt;
-      m = 0xffffffffu;
-      if (a.tile_mask) m = live ? __ldg(a.tile_mask + mt) : 0u;
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        dst[k] = -1;
-        if (live && k < a.kvol && ((m >> k) & 1u) && row < m_rows) dst[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
-      }
-    };
-    load_idx(blockIdx.x, idx, mask);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      load_idx(tile + gridDim.x, nxt, mask_nxt);      // next tile's indices: 27 loads in flight during this tile
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        if (k < a.kvol && ((mask >> k) & 1u)) {
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const int src_row = (a.dbg & 1) ? -1 : idx[k];
-          const __nv_bfloat16* src = src_row >= 0 ? a.in + (size_t)src_row * a.in_stride : a.in;
-          const uint32_t nbytes = src_row >= 0 ? 16u : 0u;
-          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
-#pragma unroll
-          for (int c = 0; c < C::CH; ++c) cp_async16_ca(sa + c * C::A_LBO + pt * 16, src + c * 8, nbytes);
-          if (!C::WRES && pt == 0) {
-            const uint32_t fb = full_bar(s);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)C::B_MEMBER) : "memory");
-            bulk_g2s(sa + C::A_BYTES, a.w + (size_t)k * (size_t)(CIN * COUT), C::B_MEMBER, fb);
-          }
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
-          ++it;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 27; ++k) idx[k] = nxt[k];
-      mask = mask_nxt;
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp >= 4 && warp < 4 + C::NPW) {
+  if (warp >= 4 && warp < 4 + C::NPW) {
     // ------------------------------------------------------------------ producers
     const int pt = threadIdx.x - 128;
     int it = 0;
@@ -206,85 +206,163 @@ igemm_umma_kernel(const IgemmArgs a) {
         if (live && pt < 128 && k < a.kvol && ((mask >> k) & 1u) && row < m_rows) cur[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
       }
     };
+    PROF_DECL(p_total); PROF_DECL(p_empty); PROF_DECL(p_pub); PROF_DECL(p_issue); PROF_DECL(p_arr); PROF_DECL(p_fetch);
+    PROF_TBEGIN(p_total);
     load_idx(blockIdx.x);
     // copy mapping: the 128*CH 16-byte pieces of a stage are dealt out so that consecutive
     // lanes take consecutive pieces of the SAME row (coalesced: a warp instruction touches
-    // 32/CH rows x one contiguous row segment each instead of 32 different rows)
+    // 32/CH rows x one contiguous row segment each instead of 32 different rows; measured
+    // 2.4x the LDGSTS rate of the thread-per-row mapping for 64-byte rows, tools/micro/).
+    // Thread pt always copies chunk c = pt % CH of rows r0 + i * RSTEP.
     constexpr int CHS = C::CH == 2 ? 1 : (C::CH == 4 ? 2 : (C::CH == 8 ? 3 : 4));
+    constexpr int RSTEP = C::NPT / C::CH;
+    const int pc = pt & (C::CH - 1), r0 = pt >> CHS;
+    const uint32_t dst_off = (uint32_t)(pc * C::A_LBO + r0 * 16);
+    const char* src_c = reinterpret_cast<const char*>(a.in) + pc * 16;
+    const uint32_t row_bytes = (uint32_t)(a.in_stride * 2);
+    // idx_s[k][r0 * PPT + i] = neighbour index of row r0 + i * RSTEP: the PPT indices a thread
+    // needs for one slot are adjacent, one vector LDS fetches them
+    const uint32_t idx_s_addr = smem_u32(idx_s) + (uint32_t)(r0 * C::PPT) * 4u;
+    const int pub_pos = (pt % RSTEP) * C::PPT + pt / RSTEP;   // where row pt's index goes
+    int gi[G][C::PPT];   // neighbour indices of this thread's rows for the (up to G) offsets of the slot being filled
+    // shared-memory index reads are issued one slot AHEAD (right after the copies of the
+    // current slot): an LDS queues behind every LDGSTS already in the LSU pipe, and a
+    // load -> copy -> load -> copy chain exposed that queueing delay once per piece.
+    auto fetch_one = [&](int* g, int k) {
+      const uint32_t ad = idx_s_addr + (uint32_t)(k * 128 * 4);
+      if constexpr (C::PPT == 1) {
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(g[0]) : "r"(ad));
+      } else if constexpr (C::PPT == 2) {
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(g[0]), "=r"(g[1]) : "r"(ad));
+      } else {
+#pragma unroll
+        for (int i = 0; i < C::PPT; i += 4)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g[i]), "=r"(g[i + 1]), "=r"(g[i + 2]), "=r"(g[i + 3]) : "r"(ad + i * 4));
+      }
+    };
+    // indices of the next (up to G) active offsets, without consuming them
+    auto fetch_idx = [&](uint32_t rem) {
+      if (a.dbg & 16) return;
+#pragma unroll
+      for (int m = 0; m < G; ++m) {
+        if (rem) fetch_one(gi[m], __ffs((int)rem) - 1);
+        rem &= rem - 1;
+      }
+    };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile % m_tiles, nt = (tile % mn_tiles) / m_tiles, ks = tile / mn_tiles;
       uint32_t tmask = mask;
       if (SPARSE) {
+        if (pt == 0) PROF_TRACE(1);
+        PROF_BEGIN(p_pub);
         asm volatile("bar.sync 1, %0;" ::"n"(C::NPT) : "memory");   // previous tile's indices no longer read
         if (pt < 128) {
 #pragma unroll
-          for (int k = 0; k < 27; ++k) idx_s[k * 128 + pt] = cur[k];
+          for (int k = 0; k < 27; ++k) idx_s[k * 128 + pub_pos] = cur[k];
         }
         asm volatile("bar.sync 1, %0;" ::"n"(C::NPT) : "memory");
+        PROF_END(p_pub);
+        if (pt == 0) PROF_TRACE(2);
         load_idx(tile + gridDim.x);                       // next tile's indices, in flight during the fills
-      }
-      auto fill = [&](const Group<G>& g) {
-        const int s = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
-#pragma unroll
-        for (int i = 0; i < C::PPT; ++i) {
-          const int Q = i * C::NPT + pt;            // piece index inside the slot
-          const int m = Q / (128 * C::CH);            // group member (kernel offset)
-          if (m >= g.n || (a.dbg & 1)) continue;
-          const int q = Q % (128 * C::CH);
-          const int r = q >> CHS, c = q & (C::CH - 1);
-          int src_row;
-          if (SPARSE) src_row = idx_s[g.k[m] * 128 + r];
-          else src_row = (mt * 128 + r < m_rows) ? mt * 128 + r : -1;
-          const __nv_bfloat16* src = src_row >= 0 ? a.in + (size_t)src_row * a.in_stride + (size_t)g.k[m] * a.k_stride + c * 8 : a.in;
-          cp_async16_ca(sa + (m * C::CH + c) * C::A_LBO + r * 16, src, src_row >= 0 ? 16u : 0u);
-        }
-        if (!C::WRES && pt == 0) {
-          // the W_k tiles (packed global image == shared image) arrive by bulk copy (UBLKCP),
-          // tracked by the same barrier through its transaction count
-          const uint32_t fb = full_bar(s);
-          if (a.dbg & 2) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
-          } else {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(g.n * C::B_MEMBER)) : "memory");
-#pragma unroll
-            for (int m = 0; m < G; ++m)
-              if (m < g.n)
-                bulk_g2s(sa + C::A_BYTES + m * C::B_MEMBER, a.w + ((size_t)nt * a.kvol + g.k[m]) * (size_t)(CIN * COUT), C::B_MEMBER, fb);
-          }
-        }
-        // the hardware arrives on full[s] for this thread when its copies have landed
-        // (cutlass::arch::cpasync_barrier_arrive_noinc pattern): producers never wait on data
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
-        ++it;
-      };
-      if (SPARSE) {
-        uint64_t rem = (uint64_t)tmask & all_k;
+        uint32_t rem = tmask & (uint32_t)all_k;
+        fetch_idx(rem);
         while (rem) {
-          const Group<G> g = pop_group<G>(rem);
-          fill(g);
+          int kk[G], n = 0;
+#pragma unroll
+          for (int m = 0; m < G; ++m) {
+            kk[m] = 0;
+            if (rem) { kk[m] = __ffs((int)rem) - 1; rem &= rem - 1; n = m + 1; }
+          }
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          PROF_BEGIN(p_empty);
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          PROF_END(p_empty);
+          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
+          PROF_BEGIN(p_issue);
+          if (!(a.dbg & 1)) {
+#pragma unroll
+            for (int m = 0; m < G; ++m) {
+              if (m < n) {
+#pragma unroll
+                for (int i = 0; i < C::PPT; ++i) {
+                  const int src_row = gi[m][i];
+                  const char* src = src_c + (size_t)(uint32_t)max(src_row, 0) * row_bytes;
+                  cp_async16_ca(sa + (uint32_t)(m * C::A_MEMBER) + dst_off + (uint32_t)(i * RSTEP * 16), src, src_row >= 0 ? 16u : 0u);
+                }
+              }
+            }
+          }
+          PROF_END(p_issue);
+          PROF_BEGIN(p_arr);
+          if (!C::WRES && pt == 0) {
+            // the W_k tiles (packed global image == shared image) arrive by bulk copy (UBLKCP),
+            // tracked by the same barrier through its transaction count
+            const uint32_t fb = full_bar(s);
+            if (a.dbg & 2) {
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+            } else {
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(n * C::B_MEMBER)) : "memory");
+#pragma unroll
+              for (int m = 0; m < G; ++m)
+                if (m < n)
+                  bulk_g2s(sa + C::A_BYTES + m * C::B_MEMBER, a.w + ((size_t)nt * a.kvol + kk[m]) * (size_t)(CIN * COUT), C::B_MEMBER, fb);
+            }
+          }
+          // the hardware arrives on full[s] for this thread when its copies have landed
+          // (cutlass::arch::cpasync_barrier_arrive_noinc pattern): producers never wait on data
+          if (a.dbg & 128) { __syncwarp(); if (lane == 0) mbar_arrive(full_bar(s)); }
+          else if (a.dbg & 64) mbar_arrive(full_bar(s));
+          else asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+          PROF_END(p_arr);
+          PROF_BEGIN(p_fetch);
+          fetch_idx(rem);
+          PROF_END(p_fetch);
+          ++it;
         }
-      } else {               // dense linear: every K slice, in order (kvol may exceed 64)
-        Group<G> g;
-        g.n = 1;
+        if (pt == 0) PROF_TRACE(3);
+      } else {
+        // dense linear: every K slice of this split, in order (kvol may exceed 64); rows are
+        // the tile's own, no index traffic at all
         for (int k = ks * kper; k < min(a.kvol, (ks + 1) * kper); ++k) {
-          g.k[0] = k;
-          fill(g);
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < C::PPT; ++i) {
+            const int r = r0 + i * RSTEP;
+            const bool ok = mt * 128 + r < m_rows;
+            const __nv_bfloat16* src = ok ? a.in + (size_t)(mt * 128 + r) * a.in_stride + (size_t)k * a.k_stride + pc * 8 : a.in;
+            cp_async16_ca(sa + dst_off + (uint32_t)(i * RSTEP * 16), src, ok ? 16u : 0u);
+          }
+          if (pt == 0) {
+            const uint32_t fb = full_bar(s);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)C::B_MEMBER) : "memory");
+            bulk_g2s(sa + C::A_BYTES, a.w + ((size_t)nt * a.kvol + k) * (size_t)(CIN * COUT), C::B_MEMBER, fb);
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+          ++it;
         }
       }
     }
+    PROF_TEND(p_total);
+    if (pt == 0) { PROF_STORE(0, p_total); PROF_STORE(1, p_empty); PROF_STORE(2, p_pub); PROF_STORE(3, it); PROF_STORE(11, p_issue); PROF_STORE(12, p_arr); PROF_STORE(13, p_fetch); }
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == C::MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     int it = 0, tcount = 0;
+    PROF_DECL(m_total); PROF_DECL(m_full); PROF_DECL(m_tempty); PROF_DECL(m_issue);
+    PROF_TBEGIN(m_total);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile % m_tiles;
       const uint32_t mask = (SPARSE && a.tile_mask) ? __ldg(a.tile_mask + mt) : 0xffffffffu;
       const int buf = tcount & 1;
       const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
+      if (lane == 0) PROF_TRACE(4);
+      PROF_BEGIN(m_tempty);
       mbar_wait(tempty_bar(buf), tph ^ 1u);
+      PROF_END(m_tempty);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * COUT);
       uint32_t accumulate = 0;
@@ -301,40 +379,59 @@ igemm_umma_kernel(const IgemmArgs a) {
         }
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
+        PROF_BEGIN(m_full);
         mbar_wait(full_bar(s), ph);
+        PROF_END(m_full);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
+        PROF_BEGIN(m_issue);
+        {
+          // descriptors advance additively (start-address field += bytes >> 4): one uniform add per MMA
+          const uint32_t sa = stage_u32 + (uint32_t)s * C::STAGE_BYTES;
+          const uint32_t a_lo0 = ((sa >> 4) & 0x3fffu) | ((uint32_t)(C::A_LBO >> 4) << 16);
+          const uint32_t b_lo0 = (((sa + C::A_BYTES) >> 4) & 0x3fffu) | ((uint32_t)(C::B_LBO >> 4) << 16);
+          const uint32_t w_lo0 = ((wres_u32 >> 4) & 0x3fffu) | ((uint32_t)(C::B_LBO >> 4) << 16);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int m = 0; m < G; ++m) {
-            if (m < g.n) {
-              const uint32_t sb = C::WRES ? smem_u32(w_res) + (uint32_t)g.k[m] * C::B_MEMBER : sa + C::A_BYTES + m * C::B_MEMBER;
+            for (int m = 0; m < G; ++m) {
+              if (m < g.n) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)(m * (C::A_MEMBER >> 4));
+                const uint32_t b_lo = C::WRES ? w_lo0 + (uint32_t)g.k[m] * (uint32_t)(C::B_MEMBER >> 4) : b_lo0 + (uint32_t)(m * (C::B_MEMBER >> 4));
 #pragma unroll
-              for (int j = 0; j < CIN / 16; ++j) {
-                uint64_t ad = make_desc(sa + (m * C::CH + 2 * j) * C::A_LBO, C::A_LBO, 128);
-                uint64_t bd = make_desc(sb + j * 2 * C::B_LBO, C::B_LBO, 128);
-                if (!(a.dbg & 4)) tc_mma_bf16(tmem_d, ad, bd, C::IDESC, accumulate);
-                accumulate = 1;
+                for (int j = 0; j < CIN / 16; ++j) {
+                  const uint64_t ad = desc_pack(a_lo + (uint32_t)(j * ((2 * C::A_LBO) >> 4)), DESC_HI);
+                  const uint64_t bd = desc_pack(b_lo + (uint32_t)(j * ((2 * C::B_LBO) >> 4)), DESC_HI);
+                  if (!(a.dbg & 4)) tc_mma_bf16(tmem_d, ad, bd, C::IDESC, accumulate);
+                  accumulate = 1;
+                }
               }
             }
+            if (a.dbg & 32) mbar_arrive(empty_bar(s)); else tc_commit(empty_bar(s));
           }
-          tc_commit(empty_bar(s));
         }
+        PROF_END(m_issue);
         __syncwarp();
         accumulate = 1;
         ++it;
       }
-      if (lane == 0) tc_commit(tfull_bar(buf));
+      if (elect_one_sync()) tc_commit(tfull_bar(buf));
       __syncwarp();
+      if (lane == 0) PROF_TRACE(5);
     }
+    PROF_TEND(m_total);
+    if (lane == 0) { PROF_STORE(4, m_total); PROF_STORE(5, m_full); PROF_STORE(6, m_tempty); PROF_STORE(7, tcount); PROF_STORE(14, m_issue); }
   } else {
     // ------------------------------------------------------------------ epilogue
     int tcount = 0;
+    PROF_DECL(e_total); PROF_DECL(e_tfull);
+    PROF_TBEGIN(e_total);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile % m_tiles, nt = (tile % mn_tiles) / m_tiles;
       const int buf = tcount & 1;
       const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
+      PROF_BEGIN(e_tfull);
       mbar_wait(tfull_bar(buf), tph);
+      PROF_END(e_tfull);
+      if (threadIdx.x == 0) PROF_TRACE(6);
       tc_fence_after();
       const int row = mt * 128 + warp * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * COUT);
@@ -359,14 +456,23 @@ igemm_umma_kernel(const IgemmArgs a) {
         mbar_arrive(tempty_bar(buf));
         if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v, tile / mn_tiles);
       }
+      if (threadIdx.x == 0) PROF_TRACE(7);
     }
+    PROF_TEND(e_total);
+    if (threadIdx.x == 0) { PROF_STORE(8, e_total); PROF_STORE(9, e_tfull); PROF_STORE(10, gridDim.x); }
   }
   tc_fence_before();
   __syncthreads();
+  PROF_T(2);
   if (warp == C::MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
+
+#ifdef SRF_IGEMM_PROF
+static int g_prof_launch = 0;
+static int prof_next_launch() { return g_prof_launch++; }
+#endif
 
 template <int CIN, int COUT, bool SPARSE>
 static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
@@ -386,7 +492,15 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   if (grid > host_tiles) grid = host_tiles;
   if (grid < 1) grid = 1;
   SRF_COUNT(1);
+#ifdef SRF_IGEMM_PROF
+  static int launch_id = 0;   // shared by all instantiations through the accessor below
+  IgemmArgs ap = a;
+  ap.dbg |= (prof_next_launch() & 63) << 16;
+  (void)launch_id;
+  igemm_umma_kernel<CIN, COUT, SPARSE><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ap);
+#else
   igemm_umma_kernel<CIN, COUT, SPARSE><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+#endif
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("igemm<%d,%d> launch failed: %s", CIN, COUT, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
   return SRF_OK;
@@ -708,6 +822,30 @@ static int dispatch_igemm(int cin, int cout, const IgemmArgs& a, int host_tiles,
 }  // namespace srf
 
 using namespace srf;
+
+#ifdef SRF_IGEMM_PROF
+extern "C" int srf_prof_read(unsigned long long* host, int reset) {
+  cudaDeviceSynchronize();
+  if (host) cudaMemcpyFromSymbol(host, srf::g_prof, sizeof(srf::g_prof));
+  if (reset) { static unsigned long long z[1024 * 16]; cudaMemcpyToSymbol(srf::g_prof, z, sizeof(z)); }
+  return 0;
+}
+extern "C" int srf_prof_trace(unsigned long long* host, int launch) {   // host[256]; returns the number of events
+  cudaDeviceSynchronize();
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, srf::g_trace_n, 4, (size_t)(launch & 63) * 4);
+  cudaMemcpyFromSymbol(host, srf::g_trace, 256 * 8, (size_t)(launch & 63) * 256 * 8);
+  int z = 0;
+  cudaMemcpyToSymbol(srf::g_trace_n, &z, 4, (size_t)(launch & 63) * 4);
+  return n < 256 ? n : 256;
+}
+extern "C" int srf_prof_read_t(unsigned long long* host, int launch) {   // launch < 0: next launch id
+  if (launch < 0) return srf::g_prof_launch;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host, srf::g_prof_t, 1024 * 4 * 8, (size_t)(launch & 63) * 1024 * 4 * 8);
+  return 0;
+}
+#endif
 
 extern "C" {
 

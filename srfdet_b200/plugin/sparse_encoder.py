@@ -16,6 +16,7 @@ Differences in HOW (not WHAT):
     worst-case capacities (<= 8x growth per stride-2 stage, bounded by the grid).
 """
 import ctypes
+import os
 
 import torch
 from torch import nn

@@ -186,6 +186,7 @@ def test_encoder_full_size_properties():
     hn, an = h.cpu().numpy(), a.cpu().numpy()
     assert rel_err(hn, an) < 2e-2
     assert np.sqrt(((hn - an) ** 2).mean()) / np.sqrt((an ** 2).mean()) < 1e-2
+    assert torch.equal(enc(f, c, 1, precision='bf16'), h)      # BF16 mode is deterministic too
     assert a.shape == (1, 256, 184, 184)
     counts = [int(x) for x in enc.last_counts]
     assert counts[0] == f.shape[0] and all(x > 0 for x in counts)
