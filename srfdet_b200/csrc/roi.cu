@@ -298,22 +298,38 @@ __device__ __forceinline__ void sample_taps(int smp, const RoiGeom& g, int* off,
 constexpr int NTAP = NBIN * 16;   // taps per RoI: 49 bins x 4 samples x 4 corners
 
 // accumulate one bin from staged taps into acc[NP] (float4 = 4 channels per lane per pass)
+// The taps of a bin are loaded in batches of TB independent 16-byte loads per lane before any
+// FMA consumes them (a load -> FMA -> load chain kept one request in flight per warp and left the
+// kernel latency bound); weights of exactly 0 (out-of-range samples) are not loaded, as before.
+// The accumulation order is unchanged (tap 0..15).
 template <int NP>
 __device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_base, const int* __restrict__ s_off,
                                                   const float* __restrict__ s_wt, int bin, int C, int lane, float4* acc) {
+  constexpr int TB = NP == 1 ? 16 : 8;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const float w = s_wt[bin * 16 + q];
-    if (w == 0.f) continue;
-    const float4* src = reinterpret_cast<const float4*>(img_base + (size_t)s_off[bin * 16 + q] * C) + lane;
+  for (int q0 = 0; q0 < 16; q0 += TB) {
+    float w[TB];
+    float4 v[TB][NP];
 #pragma unroll
-    for (int pss = 0; pss < NP; ++pss) {
-      if ((pss * 32 + lane) * 4 < C) {
-        const float4 v = __ldg(src + pss * 32);
-        acc[pss].x = fmaf(w, v.x, acc[pss].x);
-        acc[pss].y = fmaf(w, v.y, acc[pss].y);
-        acc[pss].z = fmaf(w, v.z, acc[pss].z);
-        acc[pss].w = fmaf(w, v.w, acc[pss].w);
+    for (int q = 0; q < TB; ++q) {
+      w[q] = s_wt[bin * 16 + q0 + q];
+      const float4* src = reinterpret_cast<const float4*>(img_base + (size_t)s_off[bin * 16 + q0 + q] * C) + lane;
+#pragma unroll
+      for (int pss = 0; pss < NP; ++pss) {
+        v[q][pss] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w[q] != 0.f && (pss * 32 + lane) * 4 < C) v[q][pss] = __ldg(src + pss * 32);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < TB; ++q) {
+#pragma unroll
+      for (int pss = 0; pss < NP; ++pss) {
+        if (w[q] != 0.f) {
+          acc[pss].x = fmaf(w[q], v[q][pss].x, acc[pss].x);
+          acc[pss].y = fmaf(w[q], v[q][pss].y, acc[pss].y);
+          acc[pss].z = fmaf(w[q], v[q][pss].z, acc[pss].z);
+          acc[pss].w = fmaf(w[q], v[q][pss].w, acc[pss].w);
+        }
       }
     }
   }

@@ -182,6 +182,11 @@ class RegionFeaturePipeline:
                                                            channel_last=True)
                 cat = torch.cat((img_roi, pts_roi), dim=2).view(N_PROP * 49, 2 * self.C)
                 roi = _head._linear(cat, self.fuse[s], self.precision, self._fuse_cache[s], 'fuse').view(N_PROP, 49, self.C)
+            elif self.channels_last and self.precision == 'bf16':
+                # the interaction MMA consumes bf16 operands: the sampler rounds once, on store
+                roi = torch.empty((N_PROP, 49, self.C), dtype=torch.bfloat16, device=self.device)
+                points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
+                                                 channel_last=True, out=roi)
             else:
                 roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
                                                        channel_last=True)
