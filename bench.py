@@ -124,15 +124,43 @@ def conv_roofline(pipe, pts, pk, torch):
         row['tflops'] = row['flops'] / (row['ms'] * 1e-3) / 1e12
         row['gbs'] = row['bytes'] / (row['ms'] * 1e-3) / 1e9
     umma = [r for r in rows if r['kernel'] == 'igemm_umma']
-    top = max(umma, key=lambda r: r['ms']) if umma else max(rows, key=lambda r: r['ms'])
     tot_ms = sum(r['ms'] for r in umma)
     tot_fl = sum(r['flops'] for r in umma)
-    roof = dict(bound='tensor', kernel=f"igemm_umma_kernel<{top['cin']},{top['cout']}> (layer {top['layer']}, "
-                f"{'SubM' if top['subm'] else 'strided'} k{top['kvol']}, {top['n_out']} rows, {top['pairs']} pairs)",
-                achieved=round(top['tflops'], 2), peak=pk['tf_sust'], unit='TFLOP/s', frac=round(top['tflops'] / pk['tf_sust'], 4),
-                traffic=None, peak_source=f"{pk['src']} bf16 sustained", launch_ms=round(top['ms'], 4),
-                algorithmic_flops_per_launch=top['flops'], algorithmic_bytes_per_launch=top['bytes'],
-                hbm_frac_of_same_launch=round(top['gbs'] / pk['hbm'], 4),
+    # dominant kernel = the instantiation with the largest share of the step; its numbers are per-launch averages
+    groups = {}
+    for r in (umma or rows):
+        groups.setdefault((r['cin'], r['cout']), []).append(r)
+    key, grp = max(groups.items(), key=lambda kv: sum(r['ms'] for r in kv[1]))
+    n = len(grp)
+    ms = sum(r['ms'] for r in grp) / n
+    flops = sum(r['flops'] for r in grp) / n
+    byts = sum(r['bytes'] for r in grp) / n
+    tflops, gbs = flops / (ms * 1e-3) / 1e12, byts / (ms * 1e-3) / 1e9
+    # roofline side: arithmetic intensity against the ridge of the two measured peaks
+    ridge = pk['tf_sust'] * 1e12 / (pk['hbm'] * 1e9)
+    hbm_bound = flops / byts < ridge
+    name = f"igemm_umma_kernel<{key[0]},{key[1]}>"
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
+            t = json.load(f)['kernels'].get(name)
+        if t:
+            traffic = t['dram_read_bytes'] + t['dram_write_bytes']
+            traffic_src = 'profiles/r01_ncu_traffic.json (ncu --set full, dram read+write per launch, cold cache)'
+    except (OSError, ValueError, KeyError):
+        pass
+    roof = dict(bound='hbm' if hbm_bound else 'tensor',
+                kernel=f"{name} ({n} launches per frame: layers {[r['layer'] for r in grp]}, SubM k27, "
+                       f"{grp[0]['n_out']} rows, {grp[0]['pairs']} pairs)",
+                achieved=round(gbs if hbm_bound else tflops, 2), peak=pk['hbm'] if hbm_bound else pk['tf_sust'],
+                unit='GB/s' if hbm_bound else 'TFLOP/s',
+                frac=round(gbs / pk['hbm'] if hbm_bound else tflops / pk['tf_sust'], 4),
+                traffic=traffic, traffic_source=traffic_src,
+                peak_source=f"{pk['src']} {'HBM copy bandwidth' if hbm_bound else 'bf16 sustained'}", launch_ms=round(ms, 4),
+                algorithmic_flops_per_launch=flops, algorithmic_bytes_per_launch=byts,
+                arithmetic_intensity=round(flops / byts, 1), ridge=round(ridge, 1),
+                tensor_frac_of_same_launch=round(tflops / pk['tf_sust'], 4), hbm_frac_of_same_launch=round(gbs / pk['hbm'], 4),
+                share_of_step_ms=round(sum(r['ms'] for r in grp), 4),
                 all_umma_launches=dict(n=len(umma), ms=round(tot_ms, 4), tflops=round(tot_fl / (tot_ms * 1e-3) / 1e12, 2) if tot_ms else None))
     return roof, rows
 
