@@ -41,9 +41,11 @@ def build(force=False, verbose=False, defines=(), so=SO):
     tag = '_' + os.path.basename(so).replace('libsrfdet_b200_', '').replace('.so', '') if defines else ''
     for s in SOURCES:
         obj = os.path.join(CSRC, s.replace('.cu', tag + '.o'))
-        if defines and s != 'igemm_umma.cu' and os.path.exists(os.path.join(CSRC, s.replace('.cu', '.o'))):
-            objs.append(os.path.join(CSRC, s.replace('.cu', '.o')))      # variants only touch the igemm kernel
-            continue
+        if defines and os.path.exists(os.path.join(CSRC, s.replace('.cu', '.o'))):
+            text = open(os.path.join(CSRC, s)).read() + open(os.path.join(CSRC, 'igemm_common.cuh')).read() * (s == 'igemm_umma.cu')
+            if not any(d.split('=')[0] in text for d in defines):
+                objs.append(os.path.join(CSRC, s.replace('.cu', '.o')))      # this source does not see the variant's macros
+                continue
         cmd = ([_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else [])
                + ['-c', os.path.join(CSRC, s), '-o', obj])
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -295,6 +295,14 @@ __device__ __forceinline__ void sample_taps(int smp, const RoiGeom& g, int* off,
   off[3] = yh * W + xh; wt[3] = ly * lx * 0.25f;
 }
 
+// resident CTAs per SM the compiler must leave room for / taps per batch of independent loads (A/B knobs)
+#ifndef SRF_ROI_MINB
+#define SRF_ROI_MINB 2
+#endif
+#ifndef SRF_ROI_TB
+#define SRF_ROI_TB 16
+#endif
+
 constexpr int NTAP = NBIN * 16;   // taps per RoI: 49 bins x 4 samples x 4 corners
 
 // accumulate one bin from staged taps into acc[NP] (float4 = 4 channels per lane per pass)
@@ -305,7 +313,7 @@ constexpr int NTAP = NBIN * 16;   // taps per RoI: 49 bins x 4 samples x 4 corne
 template <int NP>
 __device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_base, const int* __restrict__ s_off,
                                                   const float* __restrict__ s_wt, int bin, int C, int lane, float4* acc) {
-  constexpr int TB = NP == 1 ? 16 : 8;
+  constexpr int TB = NP == 1 ? SRF_ROI_TB : 8;
 #pragma unroll
   for (int q0 = 0; q0 < 16; q0 += TB) {
     float w[TB];
@@ -357,7 +365,7 @@ __device__ __forceinline__ void store_bin_cl(const OutSpec& o, int k, int bin, i
 }
 
 template <int NP>
-__global__ void __launch_bounds__(256) bev_roi_cl_kernel(Pyr p, float* __restrict__ boxes, const float* __restrict__ rois_in,
+__global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) bev_roi_cl_kernel(Pyr p, float* __restrict__ boxes, const float* __restrict__ rois_in,
                                                         int n_prop, int box_dim, Range rg, int mutate, OutSpec out,
                                                         float* __restrict__ rois_out) {
   __shared__ int s_off[NTAP];
@@ -407,7 +415,7 @@ __global__ void __launch_bounds__(256) bev_roi_cl_kernel(Pyr p, float* __restric
 constexpr int IMG_MAX_CAM = 8;
 
 template <int NP>
-__global__ void __launch_bounds__(256) img_roi_cl_kernel(Pyr p, const float* __restrict__ boxes, int n_prop, int box_dim,
+__global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) img_roi_cl_kernel(Pyr p, const float* __restrict__ boxes, int n_prop, int box_dim,
                                                         const float* __restrict__ lidar2img, int n_cam, Range rg,
                                                         OutSpec out, float* __restrict__ rois_out) {
   extern __shared__ __align__(16) uint8_t sm_img[];
