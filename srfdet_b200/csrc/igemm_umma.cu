@@ -59,6 +59,16 @@ __device__ int g_trace_n[64];
 #define PROF_TRACE(code_)
 #endif
 
+// ring depth cap, and one-CTA-per-SM deep-ring layouts for narrow / 64-channel rows (A/B knobs)
+#ifndef SRF_IGEMM_MAXSTAGES
+#define SRF_IGEMM_MAXSTAGES 8
+#endif
+#ifndef SRF_IGEMM_BIG_NARROW
+#define SRF_IGEMM_BIG_NARROW 0
+#endif
+#ifndef SRF_IGEMM_BIG_64
+#define SRF_IGEMM_BIG_64 0
+#endif
 // gather warps per CTA for rows of <= 4 / 8 / 16 chunks (A/B knobs)
 #ifndef SRF_IGEMM_NPW_NARROW
 #define SRF_IGEMM_NPW_NARROW 4
@@ -97,9 +107,10 @@ struct Cfg {
   static constexpr int B_BYTES = WRES ? 0 : G * B_MEMBER;
   static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
-  static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024;
+  static constexpr bool BIG = SPARSE && ((CH <= 4 && SRF_IGEMM_BIG_NARROW) || (CH == 8 && SRF_IGEMM_BIG_64));   // one CTA per SM, deep ring
+  static constexpr int BUDGET = (BIG || STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int STAGES = STAGES_RAW > SRF_IGEMM_MAXSTAGES ? SRF_IGEMM_MAXSTAGES : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int SMEM_BYTES = W_BYTES + IDX_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
