@@ -69,6 +69,10 @@ __device__ int g_trace_n[64];
 #ifndef SRF_IGEMM_BIG_64
 #define SRF_IGEMM_BIG_64 0
 #endif
+// resident CTAs per SM aimed at for rows of <= 4 chunks (2 or 3; 3 = 74 KB of smem and <= 72 registers per thread)
+#ifndef SRF_IGEMM_CTAS_NARROW
+#define SRF_IGEMM_CTAS_NARROW 2
+#endif
 // gather warps per CTA for rows of <= 4 / 8 / 16 chunks (A/B knobs)
 #ifndef SRF_IGEMM_NPW_NARROW
 #define SRF_IGEMM_NPW_NARROW 4
@@ -86,7 +90,8 @@ struct Cfg {
   // For Cin = 16 one ring slot carries G = 4 kernel offsets (K = 64 per slot): the fixed
   // per-slot cost of the ring (~0.4 us per slot) is then paid once per 64 input channels.
   // (measured: 16-channel layers -15 %; at Cin = 32 the doubled slot leaves too few slots in 104 KB)
-  static constexpr int G = (SPARSE && CIN == 16) ? 4 : 1;
+  static constexpr bool TRI = SPARSE && CH <= 4 && SRF_IGEMM_CTAS_NARROW == 3;   // three CTAs per SM
+  static constexpr int G = (SPARSE && CIN == 16) ? (TRI ? 2 : 4) : 1;
   // producer warps: the sparse gather is bound by loads in flight: 16 gather warps for Cin=128
   // (one CTA per SM), 8 for Cin=64 (two CTAs per SM; one CTA with 16 warps and 8 slots measured
   // 25 % slower); the chunked epilogue keeps the register budget for that many warps
@@ -102,13 +107,13 @@ struct Cfg {
   static constexpr int B_LBO = COUT * 16;
   static constexpr int B_MEMBER = CH * B_LBO;
   // tiny weight sets stay resident in shared memory; otherwise W_k arrives by bulk copy
-  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= (CH <= 4 ? 56 : 16) * 1024);
+  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= (TRI ? 16 : (CH <= 4 ? 56 : 16)) * 1024);
   static constexpr int W_BYTES = WRES ? (27 * B_MEMBER + 127) / 128 * 128 : 0;
   static constexpr int B_BYTES = WRES ? 0 : G * B_MEMBER;
   static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
   static constexpr bool BIG = SPARSE && ((CH <= 4 && SRF_IGEMM_BIG_NARROW) || (CH == 8 && SRF_IGEMM_BIG_64));   // one CTA per SM, deep ring
-  static constexpr int BUDGET = (BIG || STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024;
+  static constexpr int BUDGET = TRI ? 73 * 1024 : ((BIG || STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024);
   static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > SRF_IGEMM_MAXSTAGES ? SRF_IGEMM_MAXSTAGES : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
@@ -141,7 +146,7 @@ __device__ __forceinline__ Group<G> pop_group(uint64_t& rem) {
 }
 
 template <int CIN, int COUT, bool SPARSE>
-__global__ void __launch_bounds__(Cfg<CIN, COUT, SPARSE>::THREADS, (Cfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1)
+__global__ void __launch_bounds__(Cfg<CIN, COUT, SPARSE>::THREADS, (Cfg<CIN, COUT, SPARSE>::TRI && COUT <= 64) ? 3 : ((Cfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1))
 igemm_umma_kernel(const IgemmArgs a) {
   using C = Cfg<CIN, COUT, SPARSE>;
   constexpr int S = C::STAGES;
@@ -498,7 +503,7 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   int per_sm = (227 * 1024) / (C::SMEM_BYTES + 1024);
   int by_tmem = 512 / C::TMEM_COLS;
   if (per_sm > by_tmem) per_sm = by_tmem;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > ((C::TRI && COUT <= 64) ? 3 : 2)) per_sm = (C::TRI && COUT <= 64) ? 3 : 2;
   if (per_sm < 1) per_sm = 1;
   int grid = sm_count() * per_sm;
   if (grid > host_tiles) grid = host_tiles;
