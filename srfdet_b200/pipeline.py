@@ -152,7 +152,7 @@ class RegionFeaturePipeline:
                     ev_params = self._aux.record_event()
                 if not torch.cuda.is_current_stream_capturing():
                     params.record_stream(main)
-            boxes = self.stage_boxes[s].clone()          # the sampler de-normalises centres in place
+            boxes = self.stage_boxes[s]                  # static inputs: sampled with mutate=False (no in-place de-normalisation)
             if self.fusion and self.channels_last:
                 # both samplers fill their half of the concatenated fusion input
                 # (cat(img, pts), srfdet_head.py:2257) directly, in the GEMM's dtype, concurrently.
@@ -170,7 +170,7 @@ class RegionFeaturePipeline:
                     if fork:
                         ev_img = self._aux2.record_event()
                 points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
-                                                 channel_last=True, out=cat, ch_offset=self.C)
+                                                 channel_last=True, out=cat, ch_offset=self.C, mutate=False)
                 if fork:
                     main.wait_event(ev_img)
                 roi = _head._linear(cat.view(N_PROP * 49, 2 * self.C), self.fuse[s], self.precision, self._fuse_cache[s],
@@ -179,17 +179,17 @@ class RegionFeaturePipeline:
                 img_roi = img_feats_sampling_bboxes_roi(self.img_feats, boxes, self.pooler_img, self.lidar2img, self.pc_range,
                                                         channel_last=True)
                 pts_roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
-                                                           channel_last=True)
+                                                           channel_last=True, mutate=False)
                 cat = torch.cat((img_roi, pts_roi), dim=2).view(N_PROP * 49, 2 * self.C)
                 roi = _head._linear(cat, self.fuse[s], self.precision, self._fuse_cache[s], 'fuse').view(N_PROP, 49, self.C)
             elif self.channels_last and self.precision == 'bf16':
                 # the interaction MMA consumes bf16 operands: the sampler rounds once, on store
                 roi = torch.empty((N_PROP, 49, self.C), dtype=torch.bfloat16, device=self.device)
                 points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
-                                                 channel_last=True, out=roi)
+                                                 channel_last=True, out=roi, mutate=False)
             else:
                 roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
-                                                       channel_last=True)
+                                                       channel_last=True, mutate=False)
             if params is not None:
                 main.wait_event(ev_params)
             prop = self.dynconvs[s].forward_kc(prop, roi, precision=self.precision, params=params)

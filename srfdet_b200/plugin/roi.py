@@ -113,10 +113,11 @@ def _roi_out(k, c, channel_last, device, out=None, ch_offset=0):
 
 
 def points_feats_sampling_bboxes_roi(points_feats, bboxes, pooler, pc_range, voxel_size, channel_last=False,
-                                     return_rois=False, out=None, ch_offset=0):
+                                     return_rois=False, out=None, ch_offset=0, mutate=True):
     """Fused srfdet_head.py:2568-2629.  bboxes (bs, n_p, >=8) normalised centres; the
-    centres are de-normalised IN PLACE like the reference (:2587).  -> (bs*n_p, C, 7, 7)
-    (or channel-last (bs*n_p, 49, C); `out`/`ch_offset`: write into a slice of a caller buffer)."""
+    centres are de-normalised IN PLACE like the reference (:2587) unless mutate=False.
+    -> (bs*n_p, C, 7, 7) (or channel-last (bs*n_p, 49, C); `out`/`ch_offset`: write into a slice
+    of a caller buffer)."""
     assert bboxes.is_contiguous() and bboxes.dtype == torch.float32
     bs, n_p, d = bboxes.shape
     p, keep = _pyramid(points_feats, pooler.featmap_strides, pooler.num_inputs)
@@ -124,7 +125,7 @@ def points_feats_sampling_bboxes_roi(points_feats, bboxes, pooler, pc_range, vox
     k = bs * n_p
     out, spec = _roi_out(k, c, channel_last, bboxes.device, out, ch_offset)
     rois = torch.empty((k, 5), dtype=torch.float32, device=bboxes.device) if return_rois else None
-    L.check(L.load().srf_bev_roi_features(ctypes.byref(p), L.ptr(bboxes), bs, n_p, d, L.f6(pc_range), L.f3(voxel_size), 1,
+    L.check(L.load().srf_bev_roi_features(ctypes.byref(p), L.ptr(bboxes), bs, n_p, d, L.f6(pc_range), L.f3(voxel_size), int(bool(mutate)),
                                           ctypes.byref(spec), L.ptr(rois), L.stream_ptr()), 'srf_bev_roi_features')
     return (out, rois) if return_rois else out
 

@@ -291,6 +291,14 @@ class SparseEncoderCustom(nn.Module):
                     geo.append((nbr, mask, lv_out, ready))
                     levels.append(lv_out)
                     cur = lv_out
+            # the zeroed dense BEV map the last conv scatters into (SparseConvTensor.dense()): cleared on
+            # the side stream as well, off the critical path
+            last_lv, last_conv = geo[-1][2], plan[-1][0]
+            dense = torch.zeros((batch_size, last_conv.out_channels * last_lv.dims[1], last_lv.dims[2], last_lv.dims[3]),
+                                dtype=torch.float32, device=dev)
+            dense_ready = aux.record_event() if aux is not main else None
+        if aux is not main and not capturing:
+            dense.record_stream(main)
         if aux is not main and not capturing:   # tensors born on the side stream are consumed on main
             for nbr, mask, lv_o, _ in geo:
                 for t in (nbr, mask, lv_o.index, lv_o.coors, lv_o.count):
@@ -320,8 +328,8 @@ class SparseEncoderCustom(nn.Module):
             for j in range(4):
                 a.out_dims[j] = lv_out.dims[j]
             if last:
-                dense = torch.zeros((batch_size, conv.out_channels * lv_out.dims[1], lv_out.dims[2], lv_out.dims[3]),
-                                    dtype=torch.float32, device=dev)
+                if dense_ready is not None:
+                    main.wait_event(dense_ready)
                 a.dense = L.ptr(dense)
                 a.out_coors = L.ptr(lv_out.coors)
                 a.out = None
