@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/srfdet_b200.h"
 
@@ -86,5 +87,39 @@ int scan_flags_launch(const uint32_t* in, uint32_t* out_excl, uint32_t* blocksum
                       int32_t* d_total, int popcount_mode, cudaStream_t st);
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __uint_as_float(hi16 << 16); }
+
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched through launch_pdl() may be scheduled while
+// its predecessor on the stream is still draining (its launch latency and prologue overlap
+// the predecessor's tail).  Such a kernel MUST execute pdl_wait() before it touches anything
+// the predecessor wrote; pdl_trigger() lets the successor start launching.  Both are no-ops
+// for plain launches.  SRFDET_B200_PDL=0 falls back to plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SRFDET_B200_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 }  // namespace srf

@@ -165,6 +165,7 @@ igemm_umma_kernel(const IgemmArgs a) {
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * S + 2 + b); };
 
   PROF_T(0);
+  pdl_trigger();   // the next kernel on the stream may start its own prologue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_rows = SPARSE ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
   const int m_tiles = (m_rows + 127) >> 7;
@@ -199,6 +200,9 @@ igemm_umma_kernel(const IgemmArgs a) {
   const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
   const uint32_t stage_u32 = smem_u32(stage_base), wres_u32 = smem_u32(w_res);
   PROF_T(1);
+  // everything above (barriers, TMEM, resident weights) is independent of the previous kernel;
+  // activations, residuals and every global write come after this point
+  pdl_wait();
 
   if (warp >= 4 && warp < 4 + C::NPW) {
     // ------------------------------------------------------------------ producers
@@ -509,16 +513,12 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   if (grid > host_tiles) grid = host_tiles;
   if (grid < 1) grid = 1;
   SRF_COUNT(1);
-#ifdef SRF_IGEMM_PROF
-  static int launch_id = 0;   // shared by all instantiations through the accessor below
   IgemmArgs ap = a;
+#ifdef SRF_IGEMM_PROF
   ap.dbg |= (prof_next_launch() & 63) << 16;
-  (void)launch_id;
-  igemm_umma_kernel<CIN, COUT, SPARSE><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ap);
-#else
-  igemm_umma_kernel<CIN, COUT, SPARSE><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
 #endif
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(igemm_umma_kernel<CIN, COUT, SPARSE>, dim3(grid), dim3(C::THREADS), (size_t)C::SMEM_BYTES, st, ap);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("igemm<%d,%d> launch failed: %s", CIN, COUT, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
   return SRF_OK;
 }
