@@ -46,6 +46,11 @@ def test_bev_roi_golden(golden_dir):
     boxes = cuda(z['boxes'].copy())
     cl = points_feats_sampling_bboxes_roi(feats, boxes, pooler, z['pc_range'].tolist(), z['voxel_size'].tolist(), channel_last=True)
     np.testing.assert_array_equal(cl.permute(0, 2, 1).reshape(out.shape).cpu().numpy(), out.cpu().numpy())
+    # mutate=False: same features, the caller's boxes stay normalised
+    boxes = cuda(z['boxes'].copy())
+    keep = points_feats_sampling_bboxes_roi(feats, boxes, pooler, z['pc_range'].tolist(), z['voxel_size'].tolist(), mutate=False)
+    np.testing.assert_array_equal(boxes.cpu().numpy(), z['boxes'])
+    np.testing.assert_array_equal(keep.cpu().numpy(), out.cpu().numpy())
 
 
 def test_img_roi_golden(golden_dir):
