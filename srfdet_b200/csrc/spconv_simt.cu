@@ -3,6 +3,8 @@
 //
 // The FP32 kernels are the parity mode (tolerance 1e-4 vs the fp32 reference): same
 // output-stationary rulebook as the tensor-core kernel, FFMA accumulation in fp32.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace srf {
@@ -400,7 +402,12 @@ int srf_pack_weight_bf16(const float* w, int32_t kvol, int32_t cin, int32_t cout
   return SRF_OK;
 }
 
-int srf_linear_tile_k(int32_t k) { return k > 128 ? 128 : k; }
+int srf_linear_tile_k(int32_t k) {
+  // K slice per ring slot of the dense tcgen05 GEMM (SRF_LINEAR_TILE_K: A/B knob, 64 or 128)
+  static int cap = 0;
+  if (!cap) { const char* e = getenv("SRF_LINEAR_TILE_K"); cap = e ? atoi(e) : 128; if (cap != 64 && cap != 128) cap = 128; }
+  return k > cap ? cap : k;
+}
 int srf_linear_tile_n(int32_t n) { return n > 128 ? 128 : n; }
 
 int srf_pack_linear_bf16(const float* w, int32_t n, int32_t k, void* packed, void* stream) {
