@@ -11,17 +11,25 @@
 // lives in TMEM (double buffered so the epilogue of tile i overlaps the main loop of tile
 // i+1) and is written exactly once with bias / residual / ReLU / LayerNorm fused.
 //
-// Warp roles (288 threads):
-//   warps 0-3  epilogue  : tcgen05.ld (warp w owns TMEM lanes 32w..32w+31 = rows), fused
-//                          epilogue, global stores
-//   warps 4-7  producers : one thread per tile row; cp.async 16-byte row chunks (zero-fill
-//                          for missing neighbours) + the W_k tile into a STAGES-deep ring
-//   warp  8    MMA       : one lane issues tcgen05.mma (M=128, N=COUT, K=16) per 16 input
-//                          channels, tcgen05.commit releases ring slots / publishes the
-//                          accumulator
-// TMA cannot express this gather (row indices are data dependent and -1 rows must read
-// zeros), hence cp.async into the canonical no-swizzle K-major core-matrix layout:
+// Warp roles (4 + NPW + 1 warps; NPW = 4 gather warps, 8 for 128 input channels):
+//   warps 0-3        epilogue  : tcgen05.ld (warp w owns TMEM lanes 32w..32w+31 = rows), fused
+//                                epilogue, global stores
+//   warps 4..4+NPW-1 producers : 16-byte cp.async row pieces, consecutive lanes on consecutive
+//                                pieces of one row (zero-fill for missing neighbours), + the W_k
+//                                tile by cp.async.bulk, into a STAGES-deep mbarrier ring; the
+//                                neighbour indices are prefetched one tile ahead (registers ->
+//                                shared memory) and read one ring slot ahead
+//   last warp        MMA       : one elected lane issues tcgen05.mma (M=128, N=COUT, K=16) per 16
+//                                input channels; tcgen05.commit releases ring slots / publishes
+//                                the accumulator
+// The measured reasons for each of these choices are in profiles/r01_notes.md.
+// The gather goes through cp.async (row indices are data dependent and -1 rows must read
+// zeros; the TMA gather4 variant below is correct but slower) into the canonical no-swizzle
+// K-major core-matrix layout:
 //   operand byte offset(row r, 16B chunk c) = c * LBO + r * 16     (SBO = 128)
+// Launched with programmatic stream serialization: the prologue (barriers, TMEM, resident
+// weights) overlaps the tail of the previous kernel, griddepcontrol.wait precedes the first
+// access to activations.
 #include "igemm_common.cuh"
 
 namespace srf {
@@ -92,9 +100,8 @@ struct Cfg {
   // (measured: 16-channel layers -15 %; at Cin = 32 the doubled slot leaves too few slots in 104 KB)
   static constexpr bool TRI = SPARSE && CH <= 4 && SRF_IGEMM_CTAS_NARROW == 3;   // three CTAs per SM
   static constexpr int G = (SPARSE && CIN == 16) ? (TRI ? 2 : 4) : 1;
-  // producer warps: the sparse gather is bound by loads in flight: 16 gather warps for Cin=128
-  // (one CTA per SM), 8 for Cin=64 (two CTAs per SM; one CTA with 16 warps and 8 slots measured
-  // 25 % slower); the chunked epilogue keeps the register budget for that many warps
+  // gather warps per CTA (measured, profiles/r01_notes.md): 4 for Cin <= 64 (two CTAs per SM),
+  // 8 for Cin = 128 (one CTA per SM); the chunked epilogue keeps the register budget low
   static constexpr int NPW = SPARSE ? (CH >= 16 ? SRF_IGEMM_NPW_128 : (CH >= 8 ? SRF_IGEMM_NPW_64 : SRF_IGEMM_NPW_NARROW)) : 4;
   static constexpr int NPT = NPW * 32;
   static constexpr int THREADS = 32 * (4 + NPW + 1);
@@ -528,8 +535,8 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
 // (cp.async.bulk.tensor.2d ... tile::gather4: four independent row coordinates per
 // instruction, out-of-range / negative rows are zero-filled by the hardware) straight into
 // the 128B/64B/32B-swizzled K-major layout tcgen05 reads, and the W_k tile arrives with one
-// cp.async.bulk.  No LSU instruction touches operand data: on B200 the LDGSTS path tops out
-// near 20-25 B/clk/SM (profiles/), which was the limiter of the cp.async variant above.
+// cp.async.bulk.  No LSU instruction touches operand data.  Opt-in (SRF_IGEMM_TMA=1), kept as the
+// measured negative result: ~45 clk per gather4 instruction makes it ~2x slower than cp.async.
 //   warps 0-3 epilogue | warps 4-7 neighbour-index prefetch (+ warp 4 issues all TMA) | warp 8 MMA
 // =====================================================================================
 template <int CIN, int COUT, bool SPARSE>
