@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);
 extern unsigned long long g_launches;  // kernels launched by this library (bench evidence)
 #define SRF_COUNT(n) (srf::g_launches += (n))
 int sm_count();
+int spconv16_warp_launch(const srf_conv_args* cv, cudaStream_t st);   // spconv_warp16.cu
 
 #define SRF_CHECK_ARG(cond, ...)          \
   do {                                    \

@@ -876,12 +876,21 @@ extern "C" {
 int srf_linear_tile_k(int32_t k);
 int srf_linear_tile_n(int32_t n);
 
+static bool use_warp16() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("SRF_CONV16_WARP"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
 int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
   SRF_CHECK_ARG(c && c->in && c->nbr && c->w && (c->out || c->dense), "srf_spconv_bf16: null arg");
   SRF_CHECK_ARG(c->in_dtype == SRF_BF16, "srf_spconv_bf16: input features must be bf16");
   SRF_CHECK_ARG(c->kvol >= 1 && c->kvol <= 27, "srf_spconv_bf16: kvol must be in [1,27]");
   SRF_CHECK_ARG(c->cap_out > 0 && c->cap_out % 128 == 0, "srf_spconv_bf16: cap_out must be a multiple of 128");
   SRF_CHECK_ARG(!c->dense || c->out_coors, "srf_spconv_bf16: dense output needs out_coors");
+  // 16 -> 16 channels (the sparsely connected finest level): warp-level MMA kernel, spconv_warp16.cu
+  if (c->cin == 16 && c->cout == 16 && !c->dense && c->out && c->out_dtype == SRF_BF16 && use_warp16())
+    return spconv16_warp_launch(c, (cudaStream_t)stream);
   IgemmArgs a = {};
   { const char* e = getenv("SRF_IGEMM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.in = (const __nv_bfloat16*)c->in;

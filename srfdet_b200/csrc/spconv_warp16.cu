@@ -1,0 +1,146 @@
+// 16 -> 16 channel sparse convolution on warp-level tensor-core MMAs (BF16 mode).
+//
+// The finest level of the encoder has few neighbours per voxel (3.7 of 27 on the nuScenes-shaped
+// bench cloud): a 128-row tcgen05 tile gathers 27 x 128 row slots of which 14 % exist, and the
+// kernel is bound by the rate of those (mostly zero-fill) copies.  Here a warp owns 32 consecutive
+// output rows (two m16n8k16 row groups), keeps the 32x16 fp32 accumulator in its mma.sync
+// fragments across the 27 offsets, and loads an input row only when the neighbour exists: the
+// four lanes of a fragment row read the row's 32 bytes as 4-byte pieces straight into the A
+// fragment (no shared-memory staging), predicated per lane, four offsets per batch.  Weights (27 x 16 x 16 bf16 = 13.8 KB, the packed UMMA order
+// [k][ci/8][co][ci%8] of srf_pack_weight_bf16) sit in shared memory; a B fragment is two
+// conflict-free 32-bit LDS.  Same numerics contract as the tcgen05 path: bf16 operands, fp32
+// accumulation, bias(BN) + residual + ReLU fused, bf16 output.
+#include "common.cuh"
+
+namespace srf {
+
+__device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct Warp16Args {
+  const uint32_t* in;        // (rows, 16) bf16 viewed as 8 words per row
+  const int32_t* nbr;        // (kvol, cap_out)
+  const int32_t* d_n_out;
+  const uint32_t* w;         // packed bf16 weights, 128 words per kernel offset
+  const float* bias;
+  const uint32_t* residual;  // (cap_out, 16) bf16 or null
+  uint32_t* out;             // (cap_out, 16) bf16
+  int kvol, cap_out, relu;
+};
+
+__global__ void __launch_bounds__(128) spconv16_warp_kernel(Warp16Args a) {
+  __shared__ uint32_t sW[27 * 128];
+  for (int e = threadIdx.x; e < a.kvol * 128; e += blockDim.x) sW[e] = __ldg(a.w + e);
+  __syncthreads();
+  const int n_out = a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_tiles = (n_out + 31) >> 5;
+  for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+    const int row = tile * 32 + lane;
+    int idx[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) idx[k] = (k < a.kvol && row < n_out) ? __ldg(a.nbr + (size_t)k * a.cap_out + row) : -1;
+    float acc[2][2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[h][nt][q] = 0.f;
+    // offsets in batches of KB: first every A fragment of the batch (predicated 4-byte loads, no
+    // branches, so up to KB * 8 independent requests per lane are in flight), then the MMAs
+    constexpr int KB = 4;
+#pragma unroll
+    for (int k0 = 0; k0 < 27; k0 += KB) {
+      uint32_t fa[KB][2][4];
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) {
+        const int k = k0 + kk;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int r0 = -1, r1 = -1;
+          if (k < 27) {
+            r0 = __shfl_sync(0xffffffffu, idx[k < 27 ? k : 0], 16 * h + g);
+            r1 = __shfl_sync(0xffffffffu, idx[k < 27 ? k : 0], 16 * h + g + 8);
+          }
+          fa[kk][h][0] = fa[kk][h][1] = fa[kk][h][2] = fa[kk][h][3] = 0u;
+          if (r0 >= 0) { fa[kk][h][0] = __ldg(a.in + (size_t)r0 * 8 + c); fa[kk][h][2] = __ldg(a.in + (size_t)r0 * 8 + 4 + c); }
+          if (r1 >= 0) { fa[kk][h][1] = __ldg(a.in + (size_t)r1 * 8 + c); fa[kk][h][3] = __ldg(a.in + (size_t)r1 * 8 + 4 + c); }
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) {
+        const int k = k0 + kk;
+        if (k >= 27) break;
+        // B fragments of W_k: word (chunk * 16 + co) * 4 + c holds W[ci = chunk*8 + 2c, 2c+1][co]
+        uint32_t b[2][2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          b[nt][0] = sW[k * 128 + (nt * 8 + g) * 4 + c];
+          b[nt][1] = sW[k * 128 + (16 + nt * 8 + g) * 4 + c];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mma_bf16_16816(acc[h][0], fa[kk][h][0], fa[kk][h][1], fa[kk][h][2], fa[kk][h][3], b[0][0], b[0][1]);
+          mma_bf16_16816(acc[h][1], fa[kk][h][0], fa[kk][h][1], fa[kk][h][2], fa[kk][h][3], b[1][0], b[1][1]);
+        }
+      }
+    }
+    // epilogue: fragment (row g / g+8 of group h, columns nt*8 + 2c, +1) -> one bf16x2 word each
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = nt * 8 + 2 * c;
+        const float bz0 = a.bias ? __ldg(a.bias + col) : 0.f, bz1 = a.bias ? __ldg(a.bias + col + 1) : 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int orow = tile * 32 + 16 * h + g + 8 * half;
+          if (orow >= n_out) continue;
+          float v0 = acc[h][nt][2 * half] + bz0, v1 = acc[h][nt][2 * half + 1] + bz1;
+          const size_t word = (size_t)orow * 8 + nt * 4 + c;
+          if (a.residual) {
+            const uint32_t rw = __ldg(a.residual + word);
+            const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw);
+            v0 += __low2float(rb);
+            v1 += __high2float(rb);
+          }
+          if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          const __nv_bfloat162 ob = __floats2bfloat162_rn(v0, v1);
+          a.out[word] = *reinterpret_cast<const uint32_t*>(&ob);
+        }
+      }
+    }
+  }
+}
+
+int spconv16_warp_launch(const srf_conv_args* cv, cudaStream_t st) {
+  Warp16Args a;
+  a.in = (const uint32_t*)cv->in;
+  a.nbr = cv->nbr;
+  a.d_n_out = cv->d_n_out;
+  a.w = (const uint32_t*)cv->w;
+  a.bias = cv->bias;
+  a.residual = (const uint32_t*)cv->residual;
+  a.out = (uint32_t*)cv->out;
+  a.kvol = cv->kvol;
+  a.cap_out = cv->cap_out;
+  a.relu = cv->relu;
+  int grid = (cv->cap_out / 32 + 3) / 4;            // 4 warps per CTA, one 32-row tile per warp
+  const int cap = sm_count() * 12;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  SRF_COUNT(1);
+  spconv16_warp_kernel<<<grid, 128, 0, st>>>(a);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+}  // namespace srf
