@@ -48,7 +48,11 @@ __global__ void __launch_bounds__(512, 1) bench(const uint8_t* table, uint32_t r
       int r, c;
       if (TPR) { r = (j / CH) * 32 + lane; c = j % CH; }
       else { r = j * RPI + lane / CH; c = lane % CH; }
-      const uint32_t row = hash32(it * 131u + r * 7919u + (blockIdx.x * 16 + warp) * 104729u) & row_mask;
+      uint32_t row = hash32(it * 131u + r * 7919u + (blockIdx.x * 16 + warp) * 104729u) & row_mask;
+      if (MISS == 4) {   // neighbour walk: consecutive rows, every row requested by three consecutive instructions (dx = -1, 0, +1)
+        const int grp = j / 3, dx = j % 3;
+        row = ((uint32_t)((blockIdx.x * 16 + warp) * 4099 + it * (U / 3) * RPI + grp * RPI + (TPR ? lane : lane / CH) + dx)) & row_mask;
+      }
       const uint8_t* src = table + (size_t)row * RB + c * 16;
       const bool missing = MISS && MISS != 3 && (hash32(row * 31u + it) % 10u) < 3u;
       uint32_t dst;
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(512, 1) bench(const uint8_t* table, uint32_t r
       else if (RB == 128) dst = base + r * 128 + ((c ^ (r & 7)) * 16);
       else if (RB == 64) dst = base + r * 64 + ((c ^ ((r >> 1) & 3)) * 16);
       else dst = base + r * 32 + ((c ^ ((r >> 2) & 1)) * 16);
-      if (MISS == 0) cp16<CA>(dst, src);
+      if (MISS == 0 || MISS == 4) cp16<CA>(dst, src);
       else if (MISS == 1) cp16z<CA>(dst, missing ? table : src, missing ? 0u : 16u);
       else if (MISS == 2) cp16<CA>(dst, missing ? table + c * 16 : src);
       else cp16z<CA>(dst, src, 16u + (row >> 31));
@@ -105,6 +109,14 @@ int main(int argc, char** argv) {
   cudaMalloc(&table, 512ull << 20);
   cudaMemset(table, 1, 512ull << 20);
   cudaMalloc(&clk, 148 * 8);
+  if (argc > 2) {   // neighbour-walk pattern vs random rows (L2-resident 16 MB table)
+    const size_t bytes = (size_t)16 << 20;
+    run<true, 64, false, false, 0>(bytes); run<true, 64, false, false, 4>(bytes);
+    run<true, 128, false, false, 0>(bytes); run<true, 128, false, false, 4>(bytes);
+    run<true, 256, false, false, 0>(bytes); run<true, 256, false, false, 4>(bytes);
+    run<false, 128, false, true, 0>(bytes); run<false, 128, false, true, 4>(bytes);
+    return 0;
+  }
   if (argc > 1) {   // missing-row handling
     for (size_t bytes : {(size_t)32 << 10, (size_t)16 << 20}) {
       run<true, 128, false, false, 0>(bytes); run<true, 128, false, false, 3>(bytes); run<true, 128, false, false, 1>(bytes); run<true, 128, false, false, 2>(bytes);
