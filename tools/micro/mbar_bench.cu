@@ -17,14 +17,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // V: 0 = every producer thread cp.async.mbarrier.arrive.noinc; 1 = every producer thread mbarrier.arrive;
 //    2 = one lane per producer warp arrives; 3 = 0 + one dummy 16-byte cp.async per thread before the arrive
-template <int V, int S>
+template <int V, int S, int IDLE = 0>
 __global__ void ring(int iters, int npw, const uint8_t* src, long long* clk) {
-  __shared__ __align__(8) uint64_t bars[2 * S];
+  __shared__ __align__(8) uint64_t bars[2 * S + 1];
   extern __shared__ __align__(128) uint8_t buf[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b0 = smem_u32(bars);
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(b0 + 8 * s, V == 2 ? npw : npw * 32); mbar_init(b0 + 8 * (S + s), 1); }
+    mbar_init(b0 + 8 * 2 * S, 1);   // parked warps wait here until the ring is done
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -48,18 +49,21 @@ __global__ void ring(int iters, int npw, const uint8_t* src, long long* clk) {
       if (lane == 0) mbar_arrive(b0 + 8 * (S + s));
       __syncwarp();
     }
+    if (IDLE && lane == 0) mbar_arrive(b0 + 8 * 2 * S);
+  } else if (IDLE && warp > npw) {
+    mbar_wait(b0 + 8 * 2 * S, 0);      // like the epilogue warps: blocked on one barrier for a whole tile
   }
   __syncthreads();
   if (threadIdx.x == 0) clk[blockIdx.x] = clock64() - t0;
 }
 
-template <int V, int S>
+template <int V, int S, int IDLE = 0>
 static void run(int npw, int ctas_per_sm, const uint8_t* src, long long* clk) {
   const int iters = 20000;
   const int smem = ctas_per_sm == 1 ? 120 * 1024 : 60 * 1024;
-  cudaFuncSetAttribute(ring<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(ring<V, S, IDLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int grid = 148 * ctas_per_sm;
-  for (int rep = 0; rep < 2; ++rep) ring<V, S><<<grid, (npw + 1) * 32, smem>>>(iters, npw, src, clk);
+  for (int rep = 0; rep < 2; ++rep) ring<V, S, IDLE><<<grid, (npw + 1 + IDLE) * 32, smem>>>(iters, npw, src, clk);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
   static long long h[296];
@@ -68,7 +72,7 @@ static void run(int npw, int ctas_per_sm, const uint8_t* src, long long* clk) {
   for (int i = 0; i < grid; ++i) avg += h[i];
   avg /= grid;
   const char* names[] = {"all threads cp.async.mbarrier.arrive.noinc", "all threads mbarrier.arrive", "one lane per warp mbarrier.arrive", "1 cp.async + noinc arrive per thread"};
-  printf("stages %d  producer warps %2d  CTAs/SM %d  %-44s : %7.1f clk per ring slot\n", S, npw, ctas_per_sm, names[V], avg / iters);
+  printf("stages %d  producer warps %2d  parked warps %d  CTAs/SM %d  %-44s : %7.1f clk per ring slot\n", S, npw, IDLE, ctas_per_sm, names[V], avg / iters);
 }
 
 int main() {
@@ -83,6 +87,10 @@ int main() {
       run<2, 4>(npw, c, src, clk);
       run<3, 4>(npw, c, src, clk);
     }
+  run<0, 4, 4>(4, 2, src, clk);
+  run<1, 4, 4>(4, 2, src, clk);
+  run<0, 4, 4>(4, 1, src, clk);
+  run<0, 4, 8>(4, 2, src, clk);
   run<0, 3>(8, 2, src, clk);
   run<0, 8>(8, 2, src, clk);
   run<2, 3>(8, 2, src, clk);
