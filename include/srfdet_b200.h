@@ -34,8 +34,19 @@ extern "C" {
 #define SRF_ERR_CUDA (-2)
 #define SRF_ERR_UNSUPPORTED (-3)
 
+/* Element encodings of activation / weight buffers.
+ *  SRF_F32, SRF_BF16, SRF_F16: plain rows of c elements.
+ *  SRF_BF16X2 / SRF_F16X2 ("split"): a row of c values is stored as 2c 16-bit elements
+ *  [hi(c) | lo(c)] with value = hi + lo (hi = round16(v), lo = round16(v - hi)).  The tensor-core
+ *  kernels multiply split operands with three MMAs (Ah.Wh + Al.Wh + Ah.Wl, fp32 accumulate),
+ *  which reproduces fp32 products to ~2^-16 (bf16) / 2^-21 (f16) relative: the tensor-core form
+ *  of the reference's FP32 mode (srfdet.py:204-206 force_fp32).  SRF_F16 is the reference's own
+ *  half precision (sparse_encoder_custom.py:109 auto_fp16); stores saturate at +-65504. */
 #define SRF_F32 0
 #define SRF_BF16 1
+#define SRF_F16 2
+#define SRF_BF16X2 3
+#define SRF_F16X2 4
 
 int srf_version(void);
 const char* srf_last_error(void);
@@ -161,22 +172,26 @@ int srf_rulebook_build(const void* in_index, const int32_t in_dims_host[4], cons
  * Replaces spconv SubMConv3d/SparseConv3d forward, BN1d, ReLU, SparseBasicBlock residual
  * and SparseConvTensor.dense() (sparse_encoder_custom.py:125-138).
  *   out[o] = act( sum_k W_k^T in[nbr[k][o]] + bias (+ residual[o]) )
- * f32 path : SIMT FFMA, exact fp32 ("FP32 mode", tol 1e-4).  w (kvol, cin, cout) f32.
- * bf16 path: tcgen05/TMEM implicit GEMM, bf16 operands, fp32 accumulate ("BF16 mode").
- *            w packed by srf_pack_weight_bf16.  cin, cout in {16,32,64,128}.
+ * srf_spconv_f32: SIMT FFMA, fp32 (cross-check mode; also the few-channel first layer of every
+ *            mode: in f32, out in any encoding).  w (kvol, cin, cout) f32.
+ * srf_spconv_tc : tcgen05/TMEM implicit GEMM, fp32 accumulate.  in_dtype SRF_BF16 | SRF_F16 (one MMA
+ *            per product) or SRF_BF16X2 | SRF_F16X2 (hi + lo operands, three MMAs per product: the
+ *            tensor-core form of the reference's FP32 mode).  out_dtype: the same encoding, or
+ *            SRF_F32.  w packed by srf_pack_weight_tc for the same encoding.  cin, cout in
+ *            {16,32,64,128}.  srf_spconv_bf16 / srf_pack_weight_bf16: the SRF_BF16 forms (round 1 names).
  * dense (nullable): write the result into a zeroed (B, cout*D, H, W) f32 map instead of
  * `out` (needs out_coors + out_dims_host).
  * ---------------------------------------------------------------------------------- */
 typedef struct srf_conv_args {
-  const void* in;          /* (in_rows, cin) f32 | bf16 */
-  int32_t in_dtype;        /* SRF_F32 | SRF_BF16 */
+  const void* in;          /* (in_rows, cin) in in_dtype (split encodings: 2*cin 16-bit elements per row) */
+  int32_t in_dtype;        /* SRF_* encoding */
   int32_t in_rows;         /* rows allocated behind `in` (TMA bounds; 0 = unknown) */
   int32_t cin, cout, kvol;
   const int32_t* nbr;      /* (kvol, cap_out) */
   const uint32_t* tile_mask;
   int32_t cap_out;
   const int32_t* d_n_out;
-  const void* w;           /* f32 (kvol,cin,cout) | packed bf16 */
+  const void* w;           /* f32 (kvol,cin,cout) | packed 16-bit */
   const float* bias;       /* (cout) folded BN */
   const void* residual;    /* (cap_out, cout) same dtype as out, nullable */
   int32_t relu;
@@ -187,11 +202,18 @@ typedef struct srf_conv_args {
   int32_t out_dims[4];
 } srf_conv_args;
 int srf_spconv_f32(const srf_conv_args* a_host, void* stream);
+int srf_spconv_tc(const srf_conv_args* a_host, void* stream);
 int srf_spconv_bf16(const srf_conv_args* a_host, void* stream);
-/* w_f32 (kvol, cin, cout) device -> packed bf16 (kvol*cin*cout elements) device */
+/* w_f32 (kvol, cin, cout) device -> packed 16-bit elements (kvol*cin*cout, twice that for the
+ * split encodings) in the order the kernel's shared-memory tiles use */
+int srf_pack_weight_tc(const float* w_f32, int32_t kvol, int32_t cin, int32_t cout, int32_t enc,
+                       void* w_packed, void* stream);
 int srf_pack_weight_bf16(const float* w_f32, int32_t kvol, int32_t cin, int32_t cout, void* w_packed,
                          void* stream);
-/* f32 <-> bf16 row conversion with optional channel zero-padding (cout_pad >= c) */
+/* f32 rows -> rows of c_pad (>= c, zero padded) elements in a 16-bit encoding (split rows are
+ * [hi(c_pad) | lo(c_pad)]).  srf_f32_to_bf16: the SRF_BF16 form. */
+int srf_convert_rows(const float* in, int64_t rows, int32_t c, int32_t c_pad, int32_t enc, void* out,
+                     void* stream);
 int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------- *
@@ -206,6 +228,16 @@ int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, voi
  * the slabs in order (deterministic) and applies bias/LN/ReLU.  The effective split count is
  * ceil(kvol / ceil(kvol / k_splits)) with kvol = k / min(k,128) (srf_linear_splits).
  * ---------------------------------------------------------------------------------- */
+/* srf_linear_tc: A (m,k) in a 16-bit encoding a_enc (plain or split), W packed by
+ * srf_pack_linear_tc for the same encoding, out in out_enc (SRF_F32 or a 16-bit form of A's
+ * element format), LayerNorm eps explicit.  K slices are min(k,128) wide (64 for split operands:
+ * srf_linear_tile_k_enc).  The *_bf16 / un-suffixed functions are the SRF_BF16, eps = 1e-5 forms. */
+int srf_linear_tile_k_enc(int32_t k, int32_t enc);
+int srf_linear_splits_enc(int32_t k, int32_t enc, int32_t k_splits);
+int srf_pack_linear_tc(const float* w_f32, int32_t n, int32_t k, int32_t enc, void* w_packed, void* stream);
+int srf_linear_tc(const void* a, int32_t a_enc, int32_t m, int32_t k, const void* w_packed, int32_t n,
+                  const float* bias, int32_t epi, const float* ln_w, const float* ln_b, float ln_eps,
+                  void* out, int32_t out_enc, int32_t k_splits, void* stream);
 int srf_linear_tile_k(int32_t k); /* host: K-slice width used by the packer (min(k,128)) */
 int srf_linear_tile_n(int32_t n); /* host: N tile width (min(n,128)) */
 int srf_linear_splits(int32_t k, int32_t k_splits); /* host: effective split count used for (k, k_splits) */
@@ -223,6 +255,10 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
 int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials,
                   const float* bias, const float* gamma, const float* beta, float eps, int32_t relu,
                   void* out, void* stream);
+/* same with separate encodings: in f32 | bf16 | f16, out any SRF_* encoding */
+int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, int32_t n_partials,
+                      const float* bias, const float* gamma, const float* beta, float eps, int32_t relu,
+                      void* out, int32_t out_enc, void* stream);
 
 /* ---------------------------------------------------------------------------------- *
  * Region features.
@@ -248,10 +284,11 @@ int srf_roi_extract(const srf_pyramid* p_host, const float* rois, int32_t k, flo
                     int32_t channel_last, void* stream);
 
 /* Destination of the fused samplers.  channel_last = 0: (k, C, 7, 7) f32 (reference layout).
- * channel_last = 1: rows (k*49 + bin) of row_stride channels (0 -> C), written at channel
- * offset ch_offset, dtype SRF_F32 | SRF_BF16 -- so the image and BEV samplers can fill the two
- * halves of the concatenated fusion input (srfdet_head.py:2257) directly, in the GEMM's dtype.
- * bf16 / strided forms need torch.channels_last feature maps. */
+ * channel_last = 1: rows (k*49 + bin) of row_stride elements (0 -> C, 2C for split encodings),
+ * written at channel offset ch_offset, dtype = any SRF_* encoding -- so the image and BEV samplers
+ * can fill the two halves of the concatenated fusion input (srfdet_head.py:2257) directly, in the
+ * GEMM's encoding.  Split encodings: the row is [hi(row_stride/2) | lo(row_stride/2)] and ch_offset
+ * applies inside each half.  16-bit / strided forms need torch.channels_last feature maps. */
 typedef struct srf_roi_out {
   void* ptr;
   int32_t channel_last;
@@ -279,7 +316,15 @@ int srf_img_roi_features(const srf_pyramid* p_host, const float* boxes, int32_t 
 /* DynamicConv interaction core (srfdet_head.py:2679-2686): per proposal
  *   f = relu(LN_d(feats(49,C) . P1(C,d))) ; g = relu(LN_C(f . P2(d,C)))
  * roi (K,49,C) f32|bf16, params (K, 2*C*d) f32|bf16 (P1 then P2, row-major),
- * out (K, 49*C) f32|bf16 (dtype flags).  C <= 256, d <= 64. */
+ * out (K, 49*C) f32|bf16 (dtype flags).  C <= 256, d <= 64.
+ * srf_dynconv_interact_tc: explicit LayerNorm eps and every encoding: a 16-bit out_enc selects the
+ * mma.sync kernel ((C,d) = (128,32) | (256,64)) in that element format; roi f32, that format, or
+ * (split out) the same split form; params f32 or (plain out) that format; split out rows are
+ * [hi(49*C) | lo(49*C)], i.e. the A operand of srf_linear_tc. */
+int srf_dynconv_interact_tc(const void* roi, int32_t roi_enc, const void* params, int32_t param_enc,
+                            int32_t k, int32_t c, int32_t d, const float* ln1_w, const float* ln1_b,
+                            float ln1_eps, const float* ln2_w, const float* ln2_b, float ln2_eps,
+                            void* out, int32_t out_enc, void* stream);
 int srf_dynconv_interact(const void* roi, int32_t roi_dtype, const void* params, int32_t param_dtype,
                          int32_t k, int32_t c, int32_t d, const float* ln1_w, const float* ln1_b,
                          const float* ln2_w, const float* ln2_b, void* out, int32_t out_dtype,

@@ -12,7 +12,37 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SRFDET_B200_LIB: development variants of the same library (e.g. the -DSRF_IGEMM_PROF build)
 SO_PATH = os.environ.get('SRFDET_B200_LIB') or os.path.join(_HERE, 'csrc', 'libsrfdet_b200.so')
 
-F32, BF16 = 0, 1
+F32, BF16, F16, BF16X2, F16X2 = 0, 1, 2, 3, 4      # include/srfdet_b200.h element encodings
+
+
+def enc_is_split(enc):
+    return enc in (BF16X2, F16X2)
+
+
+def enc_torch_dtype(enc):
+    """torch dtype of the buffer that holds encoding `enc` (split rows are 2c elements wide)."""
+    import torch
+    return {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16, BF16X2: torch.bfloat16, F16X2: torch.float16}[enc]
+
+
+def enc_width(enc, c):
+    return 2 * c if enc_is_split(enc) else c
+
+
+def enc_of_tensor(t, c):
+    """Encoding of a tensor whose logical row has c values (last dim c or 2c)."""
+    import torch
+    if t.dtype == torch.float32:
+        return F32
+    split = t.shape[-1] == 2 * c
+    return {torch.bfloat16: (BF16, BF16X2), torch.float16: (F16, F16X2)}[t.dtype][int(split)]
+
+
+def decode(t, c):
+    """fp32 view of an encoded tensor (tests / debugging)."""
+    if t.shape[-1] == 2 * c and t.dtype != __import__('torch').float32:
+        return t[..., :c].float() + t[..., c:].float()
+    return t.float()
 
 
 class SrfError(RuntimeError):
@@ -85,10 +115,22 @@ PROTOTYPES = {
                                      POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]),
     'srf_spconv_f32': (c_int32, [POINTER(ConvArgs), c_void_p]),
     'srf_spconv_bf16': (c_int32, [POINTER(ConvArgs), c_void_p]),
+    'srf_spconv_tc': (c_int32, [POINTER(ConvArgs), c_void_p]),
+    'srf_pack_weight_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_convert_rows': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'srf_pack_weight_bf16': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'srf_f32_to_bf16': (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     'srf_linear_tile_k': (c_int32, [c_int32]),
     'srf_linear_tile_n': (c_int32, [c_int32]),
+    'srf_linear_tile_k_enc': (c_int32, [c_int32, c_int32]),
+    'srf_linear_splits_enc': (c_int32, [c_int32, c_int32, c_int32]),
+    'srf_pack_linear_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_linear_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                c_void_p, c_float, c_void_p, c_int32, c_int32, c_void_p]),
+    'srf_layernorm_enc': (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32,
+                                    c_void_p, c_int32, c_void_p]),
+    'srf_dynconv_interact_tc': (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                          c_float, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     'srf_pack_linear_bf16': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     'srf_linear_bf16': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
                                   c_void_p, c_void_p, c_int32, c_int32, c_void_p]),

@@ -1,6 +1,7 @@
 // Shared helpers for the sm_100a kernels of libsrfdet_b200.so.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -14,7 +15,7 @@ void set_error(const char* fmt, ...);
 extern unsigned long long g_launches;  // kernels launched by this library (bench evidence)
 #define SRF_COUNT(n) (srf::g_launches += (n))
 int sm_count();
-int spconv16_warp_launch(const srf_conv_args* cv, cudaStream_t st);   // spconv_warp16.cu
+int spconv16_warp_launch(const srf_conv_args* cv, bool f16, cudaStream_t st);   // spconv_warp16.cu
 
 #define SRF_CHECK_ARG(cond, ...)          \
   do {                                    \
@@ -88,6 +89,40 @@ int scan_flags_launch(const uint32_t* in, uint32_t* out_excl, uint32_t* blocksum
                       int32_t* d_total, int popcount_mode, cudaStream_t st);
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __uint_as_float(hi16 << 16); }
+
+// ------------------------------------------------------------------------------------
+// 16-bit element encodings (include/srfdet_b200.h: SRF_BF16 / SRF_F16 and the split forms
+// SRF_BF16X2 / SRF_F16X2 = [hi | lo] rows with value = hi + lo).
+// ------------------------------------------------------------------------------------
+static inline __host__ __device__ bool enc_is_split(int e) { return e == SRF_BF16X2 || e == SRF_F16X2; }
+static inline __host__ __device__ bool enc_is_f16(int e) { return e == SRF_F16 || e == SRF_F16X2; }
+static inline __host__ __device__ bool enc_is_16(int e) { return e >= SRF_BF16 && e <= SRF_F16X2; }
+// bytes of one row of c values
+static inline __host__ __device__ int enc_row_bytes(int e, int c) { return e == SRF_F32 ? 4 * c : (enc_is_split(e) ? 4 * c : 2 * c); }
+
+// two fp32 values -> one 32-bit word of two 16-bit elements (low half = a); f16 saturates at +-65504
+__device__ __forceinline__ uint32_t pack16x2(bool f16, float a, float b) {
+  if (f16) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack16x2(bool f16, uint32_t w) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint16_t pack16(bool f16, float a) { return (uint16_t)(pack16x2(f16, a, 0.f) & 0xffffu); }
+__device__ __forceinline__ float unpack16(bool f16, uint16_t h) { return unpack16x2(f16, (uint32_t)h).x; }
+// split a pair: hi word and lo word (lo = round16(v - hi))
+__device__ __forceinline__ void split16x2(bool f16, float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack16x2(f16, a, b);
+  const float2 h = unpack16x2(f16, hi);
+  lo = pack16x2(f16, a - h.x, b - h.y);
+}
 
 
 // ---------------------------------------------------------------------------------------

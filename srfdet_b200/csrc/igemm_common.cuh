@@ -42,8 +42,9 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
+// kind::f16 covers bf16 and f16 operands (selected by the instruction descriptor)
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -98,9 +99,10 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
 __device__ __forceinline__ int k_first(int tile, int kvol) { return (int)(((unsigned)tile * 11u) % (unsigned)kvol); }
 
 struct IgemmArgs {
-  const __nv_bfloat16* in;
+  const uint16_t* in;   // 16-bit elements (bf16 or f16, see fmt); split rows are [hi | lo]
   long long in_stride;  // elements between A rows
   long long k_stride;   // element offset of the k-th slice inside a row (0 for sparse conv)
+  long long in_lo_off;  // split operands: elements from a row's hi part to its lo part
   const int32_t* nbr;   // (kvol, cap_out) or null (dense: identity rows)
   const uint32_t* tile_mask;
   const int32_t* d_n_out;
@@ -108,22 +110,87 @@ struct IgemmArgs {
   int m_rows;   // dense: number of rows
   int kvol;
   int n_tiles;
-  const __nv_bfloat16* w;  // packed [n_tile][k][CIN/8][COUT][8]
+  const uint16_t* w;  // packed [n_tile][k][q][hi|lo][KC/8][COUT][8]
   const float* bias;
-  const void* residual;
+  const void* residual;   // same encoding / stride as out
   int relu, ln;
   const float *ln_w, *ln_b;
+  float ln_eps;
   void* out;
-  int out_bf16;
-  long long out_stride;
+  int fmt;       // 16-bit operand format: 0 = bf16, 1 = f16
+  int out_enc;   // SRF_F32 | SRF_BF16 | SRF_F16 | SRF_BF16X2 | SRF_F16X2 (16-bit forms use fmt)
+  long long out_stride;   // elements of the out array between rows
+  long long out_lo_off;   // split output: elements from hi to lo part
   float* dense;
   const int4* out_coors;
   int D, H, W;
   int k_splits;  // dense linear only: K slices are dealt to k_splits CTAs per output tile, fp32 partials in k_splits slabs
-  int dbg;  // profiling only (SRF_IGEMM_DBG): 1 skip A copies, 2 skip B copies, 4 skip MMA issue, 8 skip epilogue math/stores
+  int dbg;       // -DSRF_IGEMM_PROF builds only: ablation switches / launch id
 };
 
-// bias / residual / LayerNorm / ReLU and the store of one output row held in registers
+// residual add of NC consecutive channels starting at column c (same encoding as the output)
+template <int NC>
+__device__ __forceinline__ void add_residual(const IgemmArgs& a, size_t row, int c, float* v) {
+  if (a.out_enc == SRF_F32) {
+    const float4* rp = (const float4*)((const float*)a.residual + row * a.out_stride + c);
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) {
+      const float4 u = __ldg(rp + i / 4);
+      v[i] += u.x; v[i + 1] += u.y; v[i + 2] += u.z; v[i + 3] += u.w;
+    }
+    return;
+  }
+  const bool f16 = a.fmt != 0;
+  const uint16_t* base = (const uint16_t*)a.residual + row * a.out_stride + c;
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+    if (part == 1 && !enc_is_split(a.out_enc)) break;
+    const uint4* rp = (const uint4*)(base + (part ? a.out_lo_off : 0));
+#pragma unroll
+    for (int i = 0; i < NC; i += 8) {
+      const uint4 u = __ldg(rp + i / 8);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack16x2(f16, w4[q]);
+        v[i + 2 * q] += f.x;
+        v[i + 2 * q + 1] += f.y;
+      }
+    }
+  }
+}
+
+// store of NC consecutive channels of one row at column c in the output's encoding
+template <int NC>
+__device__ __forceinline__ void store_cols(const IgemmArgs& a, size_t row, int c, const float* v) {
+  if (a.out_enc == SRF_F32) {
+    float4* op = (float4*)((float*)a.out + row * a.out_stride + c);
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) op[i / 4] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    return;
+  }
+  const bool f16 = a.fmt != 0;
+  uint16_t* base = (uint16_t*)a.out + row * a.out_stride + c;
+  if (!enc_is_split(a.out_enc)) {
+    uint4* op = (uint4*)base;
+#pragma unroll
+    for (int i = 0; i < NC; i += 8)
+      op[i / 8] = make_uint4(pack16x2(f16, v[i], v[i + 1]), pack16x2(f16, v[i + 2], v[i + 3]), pack16x2(f16, v[i + 4], v[i + 5]),
+                             pack16x2(f16, v[i + 6], v[i + 7]));
+    return;
+  }
+  uint4* oh = (uint4*)base;
+  uint4* ol = (uint4*)(base + a.out_lo_off);
+#pragma unroll
+  for (int i = 0; i < NC; i += 8) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split16x2(f16, v[i + 2 * q], v[i + 2 * q + 1], h[q], l[q]);
+    oh[i / 8] = make_uint4(h[0], h[1], h[2], h[3]);
+    ol[i / 8] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 // Sparse-conv epilogue of NC consecutive output channels [c0, c0+NC) of one row (the row's
 // accumulator is drained from TMEM in chunks to keep the epilogue's register footprint small,
 // which is what lets the kernel afford more gather warps): bias(BN) + residual + ReLU + store.
@@ -133,28 +200,7 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmArgs& a, int row, int 
 #pragma unroll
     for (int c = 0; c < NC; ++c) v[c] += __ldg(a.bias + c0 + c);
   }
-  if (a.residual) {
-    if (a.out_bf16) {
-      const uint4* rp = (const uint4*)((const __nv_bfloat16*)a.residual + (size_t)row * a.out_stride + c0);
-#pragma unroll
-      for (int c = 0; c < NC; c += 8) {
-        uint4 u = __ldg(rp + c / 8);
-        uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          v[c + 2 * q] += __uint_as_float(w4[q] << 16);
-          v[c + 2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
-        }
-      }
-    } else {
-      const float4* rp = (const float4*)((const float*)a.residual + (size_t)row * a.out_stride + c0);
-#pragma unroll
-      for (int c = 0; c < NC; c += 4) {
-        float4 u = __ldg(rp + c / 4);
-        v[c] += u.x; v[c + 1] += u.y; v[c + 2] += u.z; v[c + 3] += u.w;
-      }
-    }
-  }
+  if (a.residual) add_residual<NC>(a, (size_t)row, c0, v);
   if (a.relu) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) v[c] = fmaxf(v[c], 0.f);
@@ -165,25 +211,12 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmArgs& a, int row, int 
     float* dp = a.dense + ((size_t)q.x * COUT * a.D + q.y) * hw + (size_t)q.z * a.W + q.w + (size_t)c0 * a.D * hw;
 #pragma unroll
     for (int c = 0; c < NC; ++c) dp[(size_t)c * a.D * hw] = v[c];
-  } else if (a.out_bf16) {
-    uint4* op = (uint4*)((__nv_bfloat16*)a.out + (size_t)row * a.out_stride + c0);
-#pragma unroll
-    for (int c = 0; c < NC; c += 8) {
-      uint32_t w4[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(v[c + 2 * q], v[c + 2 * q + 1]);
-        w4[q] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      op[c / 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-    }
   } else {
-    float4* op = (float4*)((float*)a.out + (size_t)row * a.out_stride + c0);
-#pragma unroll
-    for (int c = 0; c < NC; c += 4) op[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    store_cols<NC>(a, (size_t)row, c0, v);
   }
 }
 
+// dense-linear epilogue of a whole COUT-wide row: bias / residual / LayerNorm / ReLU / store
 template <int COUT>
 __device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt, float* v, int ks = 0) {
   if (a.k_splits > 1) {   // partial sum of one K range -> its own (m, n) slab; summed in fixed order by srf_layernorm
@@ -192,72 +225,29 @@ __device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt
     for (int c = 0; c < COUT; c += 4) op[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
     return;
   }
-    const int col0 = nt * COUT;
-    if (a.bias) {
+  const int col0 = nt * COUT;
+  if (a.bias) {
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) v[c] += __ldg(a.bias + col0 + c);
-    }
-    if (a.residual) {
-      if (a.out_bf16) {
-        const uint4* rp = (const uint4*)((const __nv_bfloat16*)a.residual + (size_t)row * a.out_stride + col0);
+    for (int c = 0; c < COUT; ++c) v[c] += __ldg(a.bias + col0 + c);
+  }
+  if (a.residual) add_residual<COUT>(a, (size_t)row, col0, v);
+  if (a.ln) {
+    float mean = 0.f;
 #pragma unroll
-        for (int c = 0; c < COUT; c += 8) {
-          uint4 u = __ldg(rp + c / 8);
-          uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+    for (int c = 0; c < COUT; ++c) mean += v[c];
+    mean *= (1.f / COUT);
+    float var = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            v[c + 2 * q] += __uint_as_float(w4[q] << 16);
-            v[c + 2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
-          }
-        }
-      } else {
-        const float4* rp = (const float4*)((const float*)a.residual + (size_t)row * a.out_stride + col0);
+    for (int c = 0; c < COUT; ++c) { float d = v[c] - mean; var += d * d; }
+    const float rstd = rsqrtf(var * (1.f / COUT) + a.ln_eps);
 #pragma unroll
-        for (int c = 0; c < COUT; c += 4) {
-          float4 u = __ldg(rp + c / 4);
-          v[c] += u.x; v[c + 1] += u.y; v[c + 2] += u.z; v[c + 3] += u.w;
-        }
-      }
-    }
-    if (a.ln) {
-      float mean = 0.f;
+    for (int c = 0; c < COUT; ++c) v[c] = (v[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
+  }
+  if (a.relu) {
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) mean += v[c];
-      mean *= (1.f / COUT);
-      float var = 0.f;
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) { float d = v[c] - mean; var += d * d; }
-      const float rstd = rsqrtf(var * (1.f / COUT) + 1e-5f);
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) v[c] = (v[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
-    }
-    if (a.relu) {
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) v[c] = fmaxf(v[c], 0.f);
-    }
-    if (a.dense) {
-      const int4 q = __ldg(a.out_coors + row);
-      const size_t hw = (size_t)a.H * a.W;
-      float* dp = a.dense + ((size_t)q.x * COUT * a.D + q.y) * hw + (size_t)q.z * a.W + q.w;
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) dp[(size_t)c * a.D * hw] = v[c];
-    } else if (a.out_bf16) {
-      uint4* op = (uint4*)((__nv_bfloat16*)a.out + (size_t)row * a.out_stride + col0);
-#pragma unroll
-      for (int c = 0; c < COUT; c += 8) {
-        uint32_t w4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[c + 2 * q], v[c + 2 * q + 1]);
-          w4[q] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        op[c / 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-      }
-    } else {
-      float4* op = (float4*)((float*)a.out + (size_t)row * a.out_stride + col0);
-#pragma unroll
-      for (int c = 0; c < COUT; c += 4) op[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-    }
+    for (int c = 0; c < COUT; ++c) v[c] = fmaxf(v[c], 0.f);
+  }
+  store_cols<COUT>(a, (size_t)row, col0, v);
 }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

@@ -1,4 +1,4 @@
-// Implicit gather-GEMM on tcgen05 / TMEM (sm_100a): the BF16 mode of the sparse
+// Implicit gather-GEMM on tcgen05 / TMEM (sm_100a): the tensor-core modes of the sparse
 // convolution and of the dense projections of the region-fusion
 // head (rows a9, a10).
 //
@@ -7,11 +7,20 @@
 // sparse conv : idx_k(m) = nbr[k][m] (rulebook, -1 -> zero row), k-slice = whole row
 // dense linear: idx_k(m) = m, k-slice = columns [k*CIN, (k+1)*CIN)
 //
+// Operand precision (include/srfdet_b200.h):
+//   SRF_F16 / SRF_BF16   one tcgen05.mma per 16 input channels (kind::f16, fp32 accumulate)
+//   SRF_F16X2 / SRF_BF16X2 ("split", the tensor-core form of the reference's FP32 mode): every
+//     value is stored as hi + lo (two 16-bit elements), rows are [hi | lo], weights likewise, and
+//     each 16-channel step issues three MMAs  Al.Wh + Ah.Wl + Ah.Wh  into the same fp32
+//     accumulator: products are exact to ~2^-16 (bf16) / 2^-21 (f16) relative.
+// The operand format (bf16 / f16) is a run-time field of the instruction descriptor; the split
+// form is a template parameter because it changes the shared-memory geometry.
+//
 // Output-stationary: one CTA owns a 128-row output tile; the 128xCOUT fp32 accumulator
 // lives in TMEM (double buffered so the epilogue of tile i overlaps the main loop of tile
 // i+1) and is written exactly once with bias / residual / ReLU / LayerNorm fused.
 //
-// Warp roles (4 + NPW + 1 warps; NPW = 4 gather warps, 8 for 128 input channels):
+// Warp roles (4 + NPW + 1 warps; NPW = 4 gather warps, 8 when a slot row is 256 bytes):
 //   warps 0-3        epilogue  : tcgen05.ld (warp w owns TMEM lanes 32w..32w+31 = rows), fused
 //                                epilogue, global stores
 //   warps 4..4+NPW-1 producers : 16-byte cp.async row pieces, consecutive lanes on consecutive
@@ -22,10 +31,12 @@
 //   last warp        MMA       : one elected lane issues tcgen05.mma (M=128, N=COUT, K=16) per 16
 //                                input channels; tcgen05.commit releases ring slots / publishes
 //                                the accumulator
-// The measured reasons for each of these choices are in profiles/r01_notes.md.
+// A ring slot carries KC input channels of G kernel offsets (KC = CIN, or CIN/2 when a split row
+// would not fit: the offset is then fed as KSPL = 2 consecutive slots reusing the same indices).
+// The measured reasons for each of these choices are in profiles/r01_notes.md, r02_notes.md.
 // The gather goes through cp.async (row indices are data dependent and -1 rows must read
-// zeros; the TMA gather4 variant below is correct but slower) into the canonical no-swizzle
-// K-major core-matrix layout:
+// zeros; a TMA gather4 variant was correct but 2x slower, tools/variants/) into the canonical
+// no-swizzle K-major core-matrix layout:
 //   operand byte offset(row r, 16B chunk c) = c * LBO + r * 16     (SBO = 128)
 // Launched with programmatic stream serialization: the prologue (barriers, TMEM, resident
 // weights) overlaps the tail of the previous kernel, griddepcontrol.wait precedes the first
@@ -92,29 +103,46 @@ __device__ int g_trace_n[64];
 #define SRF_IGEMM_NPW_128 8
 #endif
 
-template <int CIN, int COUT, bool SPARSE>
+#ifdef SRF_IGEMM_PROF
+#define DBG(bit_) (a.dbg & (bit_))
+#else
+#define DBG(bit_) false
+#endif
+// input channels per ring slot of split operands with 64 / 128 input channels (A/B knobs)
+#ifndef SRF_SPLIT_KC64
+#define SRF_SPLIT_KC64 32
+#endif
+#ifndef SRF_SPLIT_KC128
+#define SRF_SPLIT_KC128 64
+#endif
+
+template <int CIN, int COUT, bool SPARSE, bool SPLIT>
 struct Cfg {
-  static constexpr int CH = CIN / 8;  // 16-byte chunks per A row
-  // For Cin = 16 one ring slot carries G = 4 kernel offsets (K = 64 per slot): the fixed
-  // per-slot cost of the ring (~0.4 us per slot) is then paid once per 64 input channels.
+  // input channels carried by one slot member; an offset takes KSPL consecutive slots
+  static constexpr int KC = !SPLIT ? CIN : (CIN == 64 ? (SPARSE ? SRF_SPLIT_KC64 : 64) : (CIN == 128 ? SRF_SPLIT_KC128 : CIN));
+  static constexpr int KSPL = CIN / KC;
+  static constexpr int NJ = KC / 16;                     // MMA K-steps per member (x3 when split)
+  static constexpr int CH = (SPLIT ? 2 : 1) * KC / 8;    // 16-byte chunks per A row per slot member (hi planes, then lo planes)
+  // For 16 input channels one ring slot carries G kernel offsets (128-byte slot rows): the fixed
+  // per-slot cost of the ring (~0.4 us per slot) is then paid once per 64 channels.
   // (measured: 16-channel layers -15 %; at Cin = 32 the doubled slot leaves too few slots in 104 KB)
   static constexpr bool TRI = SPARSE && CH <= 4 && SRF_IGEMM_CTAS_NARROW == 3;   // three CTAs per SM
-  static constexpr int G = (SPARSE && CIN == 16) ? (TRI ? 2 : 4) : 1;
-  // gather warps per CTA (measured, profiles/r01_notes.md): 4 for Cin <= 64 (two CTAs per SM),
-  // 8 for Cin = 128 (one CTA per SM); the chunked epilogue keeps the register budget low
+  static constexpr int G = (SPARSE && CIN == 16) ? ((TRI || SPLIT) ? 2 : 4) : 1;
+  // gather warps per CTA (measured, profiles/r01_notes.md): 4 for slot rows <= 128 B (two CTAs per SM),
+  // 8 for 256-byte rows (one CTA per SM); the chunked epilogue keeps the register budget low
   static constexpr int NPW = SPARSE ? (CH >= 16 ? SRF_IGEMM_NPW_128 : (CH >= 8 ? SRF_IGEMM_NPW_64 : SRF_IGEMM_NPW_NARROW)) : 4;
   static constexpr int NPT = NPW * 32;
   static constexpr int THREADS = 32 * (4 + NPW + 1);
   static constexpr int MMA_WARP = 4 + NPW;
-  static constexpr int PPT = CH * 128 / NPT;  // 16-byte pieces per producer thread per kernel offset
+  static constexpr int PPT = CH * 128 / NPT;  // 16-byte pieces per producer thread per slot member
   static constexpr int A_PAD = CH == 2 ? 64 : (CH == 4 ? 32 : 16);
   static constexpr int A_LBO = 128 * 16 + A_PAD;
   static constexpr int A_MEMBER = CH * A_LBO;
   static constexpr int A_BYTES = G * A_MEMBER;
   static constexpr int B_LBO = COUT * 16;
-  static constexpr int B_MEMBER = CH * B_LBO;
+  static constexpr int B_MEMBER = CH * B_LBO;            // [hi planes | lo planes] of KC x COUT
   // tiny weight sets stay resident in shared memory; otherwise W_k arrives by bulk copy
-  static constexpr bool WRES = SPARSE && (27 * B_MEMBER <= (TRI ? 16 : (CH <= 4 ? 56 : 16)) * 1024);
+  static constexpr bool WRES = SPARSE && KSPL == 1 && (27 * B_MEMBER <= (TRI ? 16 : (CH <= 4 ? (SPLIT ? 28 : 56) : 16)) * 1024);
   static constexpr int W_BYTES = WRES ? (27 * B_MEMBER + 127) / 128 * 128 : 0;
   static constexpr int B_BYTES = WRES ? 0 : G * B_MEMBER;
   static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
@@ -126,8 +154,9 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int SMEM_BYTES = W_BYTES + IDX_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
-  // kind::f16: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), K-major both, N>>3 @17, M>>4 @24
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr int MINB = (TRI && COUT <= 64) ? 3 : ((SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1);
+  // kind::f16: D fp32 (bit 4), A/B format at bits 7 / 10 (0 = f16, 1 = bf16: set at run time), K-major both, N>>3 @17, M>>4 @24
+  static constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
 };
 
 // next group of up to G active kernel offsets from the remaining-offset bit mask
@@ -152,12 +181,14 @@ __device__ __forceinline__ Group<G> pop_group(uint64_t& rem) {
   return g;
 }
 
-template <int CIN, int COUT, bool SPARSE>
-__global__ void __launch_bounds__(Cfg<CIN, COUT, SPARSE>::THREADS, (Cfg<CIN, COUT, SPARSE>::TRI && COUT <= 64) ? 3 : ((Cfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1))
+template <int CIN, int COUT, bool SPARSE, bool SPLIT>
+__global__ void __launch_bounds__(Cfg<CIN, COUT, SPARSE, SPLIT>::THREADS, Cfg<CIN, COUT, SPARSE, SPLIT>::MINB)
 igemm_umma_kernel(const IgemmArgs a) {
-  using C = Cfg<CIN, COUT, SPARSE>;
+  using C = Cfg<CIN, COUT, SPARSE, SPLIT>;
   constexpr int S = C::STAGES;
   constexpr int G = C::G;
+  constexpr int KSPL = C::KSPL;
+  static_assert(SPARSE || KSPL == 1, "dense K slices are never sub-split");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint8_t* w_res = smem;
@@ -183,7 +214,7 @@ igemm_umma_kernel(const IgemmArgs a) {
   const uint64_t all_k = a.kvol >= 64 ? ~0ull : ((1ull << a.kvol) - 1ull);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), ((SPARSE && (a.dbg & 128)) ? C::NPW : C::NPT) + (C::WRES ? 0 : 1)); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), ((SPARSE && DBG(128)) ? C::NPW : C::NPT) + (C::WRES ? 0 : 1)); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -192,7 +223,7 @@ igemm_umma_kernel(const IgemmArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (C::WRES) {
-    // resident weights: packed global image == shared image ([k][CIN/8][COUT][8] bf16)
+    // resident weights: packed global image == shared image ([k][hi|lo][KC/8][COUT][8])
     const uint4* wsrc = reinterpret_cast<const uint4*>(a.w);
     uint4* wdst = reinterpret_cast<uint4*>(w_res);
     const int n16 = a.kvol * (C::B_MEMBER / 16);
@@ -236,16 +267,19 @@ igemm_umma_kernel(const IgemmArgs a) {
     PROF_DECL(p_total); PROF_DECL(p_empty); PROF_DECL(p_pub); PROF_DECL(p_issue); PROF_DECL(p_arr); PROF_DECL(p_fetch);
     PROF_TBEGIN(p_total);
     load_idx(blockIdx.x);
-    // copy mapping: the 128*CH 16-byte pieces of a stage are dealt out so that consecutive
+    // copy mapping: the 128*CH 16-byte pieces of a slot member are dealt out so that consecutive
     // lanes take consecutive pieces of the SAME row (coalesced: a warp instruction touches
     // 32/CH rows x one contiguous row segment each instead of 32 different rows; measured
     // 2.4x the LDGSTS rate of the thread-per-row mapping for 64-byte rows, tools/micro/).
-    // Thread pt always copies chunk c = pt % CH of rows r0 + i * RSTEP.
+    // Thread pt always copies chunk c = pt % CH of rows r0 + i * RSTEP; chunks [0, CH/2) of a
+    // split row come from its hi part, the rest from its lo part.
     constexpr int CHS = C::CH == 2 ? 1 : (C::CH == 4 ? 2 : (C::CH == 8 ? 3 : 4));
+    static_assert(C::CH == 2 || C::CH == 4 || C::CH == 8 || C::CH == 16, "slot rows of 32..256 bytes");
     constexpr int RSTEP = C::NPT / C::CH;
     const int pc = pt & (C::CH - 1), r0 = pt >> CHS;
     const uint32_t dst_off = (uint32_t)(pc * C::A_LBO + r0 * 16);
-    const char* src_c = reinterpret_cast<const char*>(a.in) + pc * 16;
+    const long long pcol = (SPLIT && pc >= C::CH / 2) ? a.in_lo_off + (pc - C::CH / 2) * 8 : (long long)pc * 8;   // elements
+    const char* src_c = reinterpret_cast<const char*>(a.in + pcol);
     const uint32_t row_bytes = (uint32_t)(a.in_stride * 2);
     // idx_s[k][r0 * PPT + i] = neighbour index of row r0 + i * RSTEP: the PPT indices a thread
     // needs for one slot are adjacent, one vector LDS fetches them
@@ -269,7 +303,7 @@ igemm_umma_kernel(const IgemmArgs a) {
     };
     // indices of the next (up to G) active offsets, without consuming them
     auto fetch_idx = [&](uint32_t rem) {
-      if (a.dbg & 16) return;
+      if (DBG(16)) return;
 #pragma unroll
       for (int m = 0; m < G; ++m) {
         if (rem) fetch_one(gi[m], __ffs((int)rem) - 1);
@@ -300,53 +334,57 @@ igemm_umma_kernel(const IgemmArgs a) {
             kk[m] = 0;
             if (rem) { kk[m] = __ffs((int)rem) - 1; rem &= rem - 1; n = m + 1; }
           }
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
-          PROF_BEGIN(p_empty);
-          if (!(a.dbg & 512)) mbar_wait(empty_bar(s), ph ^ 1u);
-          PROF_END(p_empty);
-          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
-          PROF_BEGIN(p_issue);
-          if (!(a.dbg & 1)) {
 #pragma unroll
-            for (int m = 0; m < G; ++m) {
-              if (m < n) {
+          for (int q = 0; q < KSPL; ++q) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            PROF_BEGIN(p_empty);
+            if (!DBG(512)) mbar_wait(empty_bar(s), ph ^ 1u);
+            PROF_END(p_empty);
+            const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
+            PROF_BEGIN(p_issue);
+            if (!DBG(1)) {
 #pragma unroll
-                for (int i = 0; i < C::PPT; ++i) {
-                  const int src_row = gi[m][i];
-                  const char* src = src_c + (size_t)(uint32_t)max(src_row, 0) * row_bytes;
-                  cp_async16_ca(sa + (uint32_t)(m * C::A_MEMBER) + dst_off + (uint32_t)(i * RSTEP * 16), src, src_row >= 0 ? 16u : 0u);
+              for (int m = 0; m < G; ++m) {
+                if (m < n) {
+#pragma unroll
+                  for (int i = 0; i < C::PPT; ++i) {
+                    const int src_row = gi[m][i];
+                    const char* src = src_c + (size_t)(uint32_t)max(src_row, 0) * row_bytes + q * (C::KC * 2);
+                    cp_async16_ca(sa + (uint32_t)(m * C::A_MEMBER) + dst_off + (uint32_t)(i * RSTEP * 16), src, src_row >= 0 ? 16u : 0u);
+                  }
                 }
               }
             }
-          }
-          PROF_END(p_issue);
-          PROF_BEGIN(p_arr);
-          if (!C::WRES && pt == 0) {
-            // the W_k tiles (packed global image == shared image) arrive by bulk copy (UBLKCP),
-            // tracked by the same barrier through its transaction count
-            const uint32_t fb = full_bar(s);
-            if (a.dbg & 2) {
-              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
-            } else {
-              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(n * C::B_MEMBER)) : "memory");
+            PROF_END(p_issue);
+            PROF_BEGIN(p_arr);
+            if (!C::WRES && pt == 0) {
+              // the W_k tiles (packed global image == shared image) arrive by bulk copy (UBLKCP),
+              // tracked by the same barrier through its transaction count
+              const uint32_t fb = full_bar(s);
+              if (DBG(2)) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+              } else {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(n * C::B_MEMBER)) : "memory");
 #pragma unroll
-              for (int m = 0; m < G; ++m)
-                if (m < n)
-                  bulk_g2s(sa + C::A_BYTES + m * C::B_MEMBER, a.w + ((size_t)nt * a.kvol + kk[m]) * (size_t)(CIN * COUT), C::B_MEMBER, fb);
+                for (int m = 0; m < G; ++m)
+                  if (m < n)
+                    bulk_g2s(sa + C::A_BYTES + m * C::B_MEMBER,
+                             a.w + (((size_t)nt * a.kvol + kk[m]) * KSPL + q) * (size_t)(C::B_MEMBER / 2), C::B_MEMBER, fb);
+              }
             }
+            // the hardware arrives on full[s] for this thread when its copies have landed
+            // (cutlass::arch::cpasync_barrier_arrive_noinc pattern): producers never wait on data
+            if (DBG(512)) {}
+            else if (DBG(128)) { __syncwarp(); if (lane == 0) mbar_arrive(full_bar(s)); }
+            else if (DBG(64)) mbar_arrive(full_bar(s));
+            else asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+            PROF_END(p_arr);
+            ++it;
           }
-          // the hardware arrives on full[s] for this thread when its copies have landed
-          // (cutlass::arch::cpasync_barrier_arrive_noinc pattern): producers never wait on data
-          if (a.dbg & 512) {}
-          else if (a.dbg & 128) { __syncwarp(); if (lane == 0) mbar_arrive(full_bar(s)); }
-          else if (a.dbg & 64) mbar_arrive(full_bar(s));
-          else asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
-          PROF_END(p_arr);
           PROF_BEGIN(p_fetch);
           fetch_idx(rem);
           PROF_END(p_fetch);
-          ++it;
         }
         if (pt == 0) PROF_TRACE(3);
       } else {
@@ -361,13 +399,13 @@ igemm_umma_kernel(const IgemmArgs a) {
           for (int i = 0; i < C::PPT; ++i) {
             const int r = r0 + i * RSTEP;
             const bool ok = mt * 128 + r < m_rows;
-            const __nv_bfloat16* src = ok ? a.in + (size_t)(mt * 128 + r) * a.in_stride + (size_t)k * a.k_stride + pc * 8 : a.in;
+            const uint16_t* src = ok ? a.in + (size_t)(mt * 128 + r) * a.in_stride + (size_t)k * a.k_stride + pcol : a.in;
             cp_async16_ca(sa + dst_off + (uint32_t)(i * RSTEP * 16), src, ok ? 16u : 0u);
           }
           if (pt == 0) {
             const uint32_t fb = full_bar(s);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)C::B_MEMBER) : "memory");
-            bulk_g2s(sa + C::A_BYTES, a.w + ((size_t)nt * a.kvol + k) * (size_t)(CIN * COUT), C::B_MEMBER, fb);
+            bulk_g2s(sa + C::A_BYTES, a.w + ((size_t)nt * a.kvol + k) * (size_t)(C::B_MEMBER / 2), C::B_MEMBER, fb);
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
           ++it;
@@ -380,6 +418,7 @@ igemm_umma_kernel(const IgemmArgs a) {
   } else if (warp == C::MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     int it = 0, tcount = 0;
+    const uint32_t idesc = C::IDESC0 | (a.fmt ? 0u : ((1u << 7) | (1u << 10)));
     PROF_DECL(m_total); PROF_DECL(m_full); PROF_DECL(m_tempty); PROF_DECL(m_issue);
     PROF_TBEGIN(m_total);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -405,41 +444,55 @@ igemm_umma_kernel(const IgemmArgs a) {
           g.n = 1;
           g.k[0] = kd++;
         }
-        const int s = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
-        PROF_BEGIN(m_full);
-        if (!(a.dbg & 512)) mbar_wait(full_bar(s), ph);
-        PROF_END(m_full);
-        tc_fence_after();
-        PROF_BEGIN(m_issue);
-        {
-          // descriptors advance additively (start-address field += bytes >> 4): one uniform add per MMA
-          const uint32_t sa = stage_u32 + (uint32_t)s * C::STAGE_BYTES;
-          const uint32_t a_lo0 = ((sa >> 4) & 0x3fffu) | ((uint32_t)(C::A_LBO >> 4) << 16);
-          const uint32_t b_lo0 = (((sa + C::A_BYTES) >> 4) & 0x3fffu) | ((uint32_t)(C::B_LBO >> 4) << 16);
-          const uint32_t w_lo0 = ((wres_u32 >> 4) & 0x3fffu) | ((uint32_t)(C::B_LBO >> 4) << 16);
-          if (elect_one_sync()) {
 #pragma unroll
-            for (int m = 0; m < G; ++m) {
-              if (m < g.n) {
-                const uint32_t a_lo = a_lo0 + (uint32_t)(m * (C::A_MEMBER >> 4));
-                const uint32_t b_lo = C::WRES ? w_lo0 + (uint32_t)g.k[m] * (uint32_t)(C::B_MEMBER >> 4) : b_lo0 + (uint32_t)(m * (C::B_MEMBER >> 4));
+        for (int q = 0; q < KSPL; ++q) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          PROF_BEGIN(m_full);
+          if (!DBG(512)) mbar_wait(full_bar(s), ph);
+          PROF_END(m_full);
+          tc_fence_after();
+          PROF_BEGIN(m_issue);
+          {
+            // descriptors advance additively (start-address field += bytes >> 4): one uniform add per MMA
+            const uint32_t sa = stage_u32 + (uint32_t)s * C::STAGE_BYTES;
+            const uint32_t a_lo0 = ((sa >> 4) & 0x3fffu) | ((uint32_t)(C::A_LBO >> 4) << 16);
+            const uint32_t b_lo0 = (((sa + C::A_BYTES) >> 4) & 0x3fffu) | ((uint32_t)(C::B_LBO >> 4) << 16);
+            const uint32_t w_lo0 = ((wres_u32 >> 4) & 0x3fffu) | ((uint32_t)(C::B_LBO >> 4) << 16);
+            if (elect_one_sync()) {
 #pragma unroll
-                for (int j = 0; j < CIN / 16; ++j) {
-                  const uint64_t ad = desc_pack(a_lo + (uint32_t)(j * ((2 * C::A_LBO) >> 4)), DESC_HI);
-                  const uint64_t bd = desc_pack(b_lo + (uint32_t)(j * ((2 * C::B_LBO) >> 4)), DESC_HI);
-                  if (!(a.dbg & 4)) tc_mma_bf16(tmem_d, ad, bd, C::IDESC, accumulate);
-                  accumulate = 1;
+              for (int m = 0; m < G; ++m) {
+                if (m < g.n) {
+                  const uint32_t a_lo = a_lo0 + (uint32_t)(m * (C::A_MEMBER >> 4));
+                  const uint32_t b_lo = C::WRES ? w_lo0 + (uint32_t)g.k[m] * (uint32_t)(C::B_MEMBER >> 4) : b_lo0 + (uint32_t)(m * (C::B_MEMBER >> 4));
+#pragma unroll
+                  for (int j = 0; j < C::NJ; ++j) {
+                    const uint64_t ah = desc_pack(a_lo + (uint32_t)(j * ((2 * C::A_LBO) >> 4)), DESC_HI);
+                    const uint64_t bh = desc_pack(b_lo + (uint32_t)(j * ((2 * C::B_LBO) >> 4)), DESC_HI);
+                    if (SPLIT) {
+                      // hi/lo planes: [0, NJ) hi, [NJ, 2 NJ) lo.  Small cross terms first, then the main product.
+                      const uint64_t al = desc_pack(a_lo + (uint32_t)((C::NJ + j) * ((2 * C::A_LBO) >> 4)), DESC_HI);
+                      const uint64_t bl = desc_pack(b_lo + (uint32_t)((C::NJ + j) * ((2 * C::B_LBO) >> 4)), DESC_HI);
+                      if (!DBG(4)) {
+                        tc_mma_f16(tmem_d, al, bh, idesc, accumulate);
+                        tc_mma_f16(tmem_d, ah, bl, idesc, 1u);
+                        tc_mma_f16(tmem_d, ah, bh, idesc, 1u);
+                      }
+                    } else {
+                      if (!DBG(4)) tc_mma_f16(tmem_d, ah, bh, idesc, accumulate);
+                    }
+                    accumulate = 1;
+                  }
                 }
               }
+              if (DBG(512)) {} else if (DBG(32)) mbar_arrive(empty_bar(s)); else tc_commit(empty_bar(s));
             }
-            if (a.dbg & 512) {} else if (a.dbg & 32) mbar_arrive(empty_bar(s)); else tc_commit(empty_bar(s));
           }
+          PROF_END(m_issue);
+          __syncwarp();
+          accumulate = 1;
+          ++it;
         }
-        PROF_END(m_issue);
-        __syncwarp();
-        accumulate = 1;
-        ++it;
       }
       if (elect_one_sync()) tc_commit(tfull_bar(buf));
       __syncwarp();
@@ -471,7 +524,7 @@ igemm_umma_kernel(const IgemmArgs a) {
           float v[NC];
 #pragma unroll
           for (int cc = 0; cc < NC; cc += 16) tc_ld16(taddr + c0 + cc, v + cc);
-          if (row < m_rows && !(a.dbg & 8)) epilogue_chunk<COUT, NC>(a, row, c0, v);
+          if (row < m_rows && !DBG(8)) epilogue_chunk<COUT, NC>(a, row, c0, v);
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
@@ -482,7 +535,7 @@ igemm_umma_kernel(const IgemmArgs a) {
         // accumulator is in registers: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
-        if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v, tile / mn_tiles);
+        if (row < m_rows && !DBG(8)) epilogue_row<COUT>(a, row, nt, v, tile / mn_tiles);
       }
       if (threadIdx.x == 0) PROF_TRACE(7);
     }
@@ -500,21 +553,22 @@ igemm_umma_kernel(const IgemmArgs a) {
 #ifdef SRF_IGEMM_PROF
 static int g_prof_launch = 0;
 static int prof_next_launch() { return g_prof_launch++; }
+static int prof_dbg_env() { const char* e = getenv("SRF_IGEMM_DBG"); return e ? atoi(e) : 0; }
 #endif
 
-template <int CIN, int COUT, bool SPARSE>
+template <int CIN, int COUT, bool SPARSE, bool SPLIT>
 static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
-  using C = Cfg<CIN, COUT, SPARSE>;
+  using C = Cfg<CIN, COUT, SPARSE, SPLIT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_umma_kernel<CIN, COUT, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm_umma_kernel<CIN, COUT, SPARSE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("igemm<%d,%d>: cannot set %d B dynamic smem: %s", CIN, COUT, C::SMEM_BYTES, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
     configured = true;
   }
   int per_sm = (227 * 1024) / (C::SMEM_BYTES + 1024);
   int by_tmem = 512 / C::TMEM_COLS;
   if (per_sm > by_tmem) per_sm = by_tmem;
-  if (per_sm > ((C::TRI && COUT <= 64) ? 3 : 2)) per_sm = (C::TRI && COUT <= 64) ? 3 : 2;
+  if (per_sm > C::MINB) per_sm = C::MINB;
   if (per_sm < 1) per_sm = 1;
   int grid = sm_count() * per_sm;
   if (grid > host_tiles) grid = host_tiles;
@@ -522,324 +576,38 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   SRF_COUNT(1);
   IgemmArgs ap = a;
 #ifdef SRF_IGEMM_PROF
-  ap.dbg |= (prof_next_launch() & 63) << 16;
+  ap.dbg = prof_dbg_env() | ((prof_next_launch() & 63) << 16);
 #endif
-  cudaError_t e = launch_pdl(igemm_umma_kernel<CIN, COUT, SPARSE>, dim3(grid), dim3(C::THREADS), (size_t)C::SMEM_BYTES, st, ap);
+  cudaError_t e = launch_pdl(igemm_umma_kernel<CIN, COUT, SPARSE, SPLIT>, dim3(grid), dim3(C::THREADS), (size_t)C::SMEM_BYTES, st, ap);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("igemm<%d,%d> launch failed: %s", CIN, COUT, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
   return SRF_OK;
 }
 
-// =====================================================================================
-// TMA variant: the A operand is gathered by the TMA unit itself
-// (cp.async.bulk.tensor.2d ... tile::gather4: four independent row coordinates per
-// instruction, out-of-range / negative rows are zero-filled by the hardware) straight into
-// the 128B/64B/32B-swizzled K-major layout tcgen05 reads, and the W_k tile arrives with one
-// cp.async.bulk.  No LSU instruction touches operand data.  Opt-in (SRF_IGEMM_TMA=1), kept as the
-// measured negative result: ~45 clk per gather4 instruction makes it ~2x slower than cp.async.
-//   warps 0-3 epilogue | warps 4-7 neighbour-index prefetch (+ warp 4 issues all TMA) | warp 8 MMA
-// =====================================================================================
-template <int CIN, int COUT, bool SPARSE>
-struct TCfg {
-  static constexpr int KP = CIN >= 64 ? 64 : CIN;   // elements per swizzled panel row
-  static constexpr int ROWB = KP * 2;               // 128 / 64 / 32 bytes
-  static constexpr int NP = CIN / KP;               // K panels per stage
-  static constexpr int PANEL_BYTES = 128 * ROWB;
-  static constexpr int A_BYTES = NP * PANEL_BYTES;
-  static constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);  // UMMA::LayoutType
-  static constexpr int SBO = 8 * ROWB;
-  static constexpr int CH = CIN / 8;
-  static constexpr int B_LBO = COUT * 16;
-  static constexpr int B_BYTES = CH * B_LBO;
-  static constexpr bool WRES = SPARSE && (27 * B_BYTES <= 56 * 1024);
-  static constexpr int W_BYTES = WRES ? (27 * B_BYTES + 1023) / 1024 * 1024 : 0;
-  static constexpr int IDX_BYTES = SPARSE ? 14 * 1024 : 0;
-  static constexpr int STAGE_BYTES = (A_BYTES + (WRES ? 0 : B_BYTES) + 1023) / 1024 * 1024;
-  static constexpr int BUDGET = (STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 200 * 1024 : 104 * 1024;
-  static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 12 ? 12 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = W_BYTES + IDX_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-  static constexpr uint32_t TX_BYTES = A_BYTES + (WRES ? 0 : B_BYTES);
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
-};
+// NOTE: two other producers were built and measured slower on B200 (profiles/r01_notes.md): the TMA
+// tile::gather4 form (~45 clk per 4-row instruction, ~2x slower; archived in tools/variants/) and a
+// register-staged LDG -> STS form (1.5x slower).  Neither is part of the build.
 
-// K-major swizzled operand descriptor: LBO is ignored (encoded 1), SBO = 8 rows
-__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t sbo, uint32_t layout) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) |
-         (1ull << 46) | ((uint64_t)layout << 61);
-}
-
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int col, int4 rows) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(col), "r"(rows.x), "r"(rows.y), "r"(rows.z), "r"(rows.w)
-      : "memory");
-}
-
-template <int CIN, int COUT, bool SPARSE>
-__global__ void __launch_bounds__(288, (TCfg<CIN, COUT, SPARSE>::SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1)
-igemm_tma_kernel(const __grid_constant__ CUtensorMap tmapA, const IgemmArgs a) {
-  using C = TCfg<CIN, COUT, SPARSE>;
-  constexpr int S = C::STAGES;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_res = smem;
-  int32_t* idx_s = reinterpret_cast<int32_t*>(smem + C::W_BYTES);   // [27][128]
-  uint8_t* stage_base = smem + C::W_BYTES + C::IDX_BYTES;
-  uint64_t* bars = (uint64_t*)(stage_base + S * C::STAGE_BYTES);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
-  const uint32_t bar0 = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * S + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * S + 2 + b); };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_rows = SPARSE ? (a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out) : a.m_rows;
-  const int m_tiles = (m_rows + 127) >> 7;
-  const int total_tiles = m_tiles * a.n_tiles;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
-  }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (C::WRES) {
-    const uint4* wsrc = reinterpret_cast<const uint4*>(a.w);
-    uint4* wdst = reinterpret_cast<uint4*>(w_res);
-    const int n16 = a.kvol * (C::B_BYTES / 16);
-    for (int j = threadIdx.x; j < n16; j += blockDim.x) wdst[j] = __ldg(wsrc + j);
-    fence_proxy_async();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------ index prefetch + TMA issue
-    const int pt = threadIdx.x - 128;
-    int it = 0;
-    int cur[27];
-    uint32_t mask = 0xffffffffu;
-    auto load_idx = [&](int tile) {
-      mask = 0xffffffffu;
-      if (!SPARSE) return;
-      const bool live = tile < total_tiles;
-      const int mt = live ? tile % m_tiles : 0;
-      const int row = mt * 128 + pt;
-      if (a.tile_mask) mask = live ? __ldg(a.tile_mask + mt) : 0u;
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        cur[k] = -1;
-        if (live && k < a.kvol && ((mask >> k) & 1u) && row < m_rows) cur[k] = __ldg(a.nbr + (size_t)k * a.cap_out + row);
-      }
-    };
-    load_idx(blockIdx.x);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
-      const uint32_t tmask = mask;
-      if (SPARSE) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // warp 4 has issued every stage of the previous tile
-#pragma unroll
-        for (int k = 0; k < 27; ++k) idx_s[k * 128 + pt] = cur[k];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        load_idx(tile + gridDim.x);
-      }
-      if (warp == 4) {
-        int k = k_first(tile, a.kvol);
-        for (int j = 0; j < a.kvol; ++j, k = (k + 1 == a.kvol) ? 0 : k + 1) {
-          if (SPARSE && !((tmask >> k) & 1u)) continue;
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
-          if (lane == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(s)), "r"(C::TX_BYTES) : "memory");
-            if (!C::WRES) bulk_g2s(sa + C::A_BYTES, a.w + ((size_t)nt * a.kvol + k) * (size_t)(CIN * COUT), C::B_BYTES, full_bar(s));
-          }
-          __syncwarp();
-          int4 r4;
-          if (SPARSE) {
-            r4 = *reinterpret_cast<const int4*>(idx_s + k * 128 + 4 * lane);
-          } else {
-            const int r0 = mt * 128 + 4 * lane;
-            r4 = make_int4(r0, r0 + 1, r0 + 2, r0 + 3);
-          }
-          const int col0 = (int)((long long)k * a.k_stride);
-#pragma unroll
-          for (int p = 0; p < C::NP; ++p)
-            tma_gather4(sa + p * C::PANEL_BYTES + lane * 4 * C::ROWB, &tmapA, full_bar(s), col0 + p * C::KP, r4);
-          ++it;
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
-    int it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile % m_tiles;
-      const uint32_t mask = (SPARSE && a.tile_mask) ? __ldg(a.tile_mask + mt) : 0xffffffffu;
-      const int buf = tcount & 1;
-      const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
-      mbar_wait(tempty_bar(buf), tph ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * COUT);
-      uint32_t accumulate = 0;
-      int k = k_first(tile, a.kvol);
-      for (int j = 0; j < a.kvol; ++j, k = (k + 1 == a.kvol) ? 0 : k + 1) {
-        if (SPARSE && !((mask >> k) & 1u)) continue;
-        const int s = it % S;
-        const uint32_t ph = (uint32_t)(it / S) & 1u;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(stage_base + s * C::STAGE_BYTES);
-          const uint32_t sb = C::WRES ? smem_u32(w_res) + (uint32_t)k * C::B_BYTES : sa + C::A_BYTES;
-#pragma unroll
-          for (int j = 0; j < CIN / 16; ++j) {
-            const int p = (j * 16) / C::KP, off = ((j * 16) % C::KP) * 2;
-            uint64_t ad = make_desc_sw(sa + p * C::PANEL_BYTES + off, C::SBO, C::LAYOUT);
-            uint64_t bd = make_desc(sb + j * 2 * C::B_LBO, C::B_LBO, 128);
-            if (!(a.dbg & 4)) tc_mma_bf16(tmem_d, ad, bd, C::IDESC, accumulate);
-            accumulate = 1;
-          }
-          tc_commit(empty_bar(s));
-        }
-        __syncwarp();
-        accumulate = 1;
-        ++it;
-      }
-      if (lane == 0) tc_commit(tfull_bar(buf));
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue
-    int tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
-      const int buf = tcount & 1;
-      const uint32_t tph = (uint32_t)(tcount >> 1) & 1u;
-      mbar_wait(tfull_bar(buf), tph);
-      tc_fence_after();
-      const int row = mt * 128 + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * COUT);
-      float v[COUT];
-#pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 16) tc_ld16(taddr + c0, v + c0);
-      tc_fence_before();
-      mbar_arrive(tempty_bar(buf));
-      if (row < m_rows && !(a.dbg & 8)) epilogue_row<COUT>(a, row, nt, v);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
-  }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// 2-D bf16 row-major (rows, cols) tensor, box = {box_cols, 1}: the gather4 form (each of the
-// four row coordinates of an instruction fetches one box)
-static int make_gather_tmap(CUtensorMap* m, const void* base, long long rows, long long cols, long long row_stride_elems,
-                            int box_cols) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return SRF_ERR_CUDA; }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)row_stride_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, 1};
-  cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld stride=%lld box=%d", (int)r, rows, cols, row_stride_elems, box_cols); return SRF_ERR_CUDA; }
-  return SRF_OK;
-}
-
-template <int CIN, int COUT, bool SPARSE>
-static int launch_igemm_tma(const IgemmArgs& a, int host_tiles, long long in_rows, long long in_cols, cudaStream_t st) {
-  using C = TCfg<CIN, COUT, SPARSE>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tma_kernel<CIN, COUT, SPARSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("igemm_tma<%d,%d>: cannot set %d B dynamic smem: %s", CIN, COUT, C::SMEM_BYTES, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
-    configured = true;
-  }
-  alignas(64) CUtensorMap tmap;
-  int rc = make_gather_tmap(&tmap, a.in, in_rows, in_cols, a.in_stride, C::KP);
-  if (rc) return rc;
-  int per_sm = (227 * 1024) / (C::SMEM_BYTES + 1024);
-  int by_tmem = 512 / C::TMEM_COLS;
-  if (per_sm > by_tmem) per_sm = by_tmem;
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  int grid = sm_count() * per_sm;
-  if (grid > host_tiles) grid = host_tiles;
-  if (grid < 1) grid = 1;
-  SRF_COUNT(1);
-  igemm_tma_kernel<CIN, COUT, SPARSE><<<grid, 288, C::SMEM_BYTES, st>>>(tmap, a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error("igemm_tma<%d,%d> launch failed: %s", CIN, COUT, cudaGetErrorString(e)); return SRF_ERR_CUDA; }
-  return SRF_OK;
-}
-
-template <bool SPARSE>
-static int dispatch_igemm_tma(int cin, int cout, const IgemmArgs& a, int host_tiles, long long in_rows, long long in_cols, cudaStream_t st) {
-#define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm_tma<ci, co, SPARSE>(a, host_tiles, in_rows, in_cols, st);
+// channel pairs of the encoders of the four configs plus the head's tiles
+template <bool SPLIT>
+static int dispatch_sparse(int cin, int cout, const IgemmArgs& a, int host_tiles, cudaStream_t st) {
+#define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm<ci, co, true, SPLIT>(a, host_tiles, st);
   SRF_CASE(16, 16) SRF_CASE(16, 32) SRF_CASE(32, 32) SRF_CASE(32, 64) SRF_CASE(64, 64) SRF_CASE(64, 128)
-  SRF_CASE(128, 128) SRF_CASE(16, 128) SRF_CASE(32, 128) SRF_CASE(64, 32) SRF_CASE(128, 64) SRF_CASE(128, 32)
-  SRF_CASE(64, 16) SRF_CASE(32, 16) SRF_CASE(16, 64) SRF_CASE(128, 16)
+  SRF_CASE(128, 128) SRF_CASE(128, 64) SRF_CASE(64, 32) SRF_CASE(32, 16)
 #undef SRF_CASE
-  set_error("igemm_tma: unsupported channel pair cin=%d cout=%d (each must be 16/32/64/128)", cin, cout);
+  set_error("sparse igemm: unsupported channel pair cin=%d cout=%d", cin, cout);
   return SRF_ERR_UNSUPPORTED;
 }
 
-// The TMA-gather variant is correct but measured SLOWER on B200 (gather4 issues at ~45 clk per
-// instruction = <= 11 B/clk/SM for 128-byte rows; profiles/r01_notes.md), so the cp.async
-// gather + bulk-copied weights variant is the default.  SRF_IGEMM_TMA=1 selects the TMA one.
-static bool use_ldgsts() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SRF_IGEMM_TMA");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-// NOTE: a register-staged variant (LDG.128 -> registers -> STS.128 + fence.proxy.async, 4 barrier
-// arrivals per slot) was built and measured 1.5x SLOWER than the cp.async ring on B200
-// (profiles/r01_notes.md), so it is not part of the build.
-
-template <bool SPARSE>
-static int dispatch_igemm(int cin, int cout, const IgemmArgs& a, int host_tiles, cudaStream_t st) {
-#define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm<ci, co, SPARSE>(a, host_tiles, st);
-  SRF_CASE(16, 16) SRF_CASE(16, 32) SRF_CASE(32, 32) SRF_CASE(32, 64) SRF_CASE(64, 64) SRF_CASE(64, 128)
-  SRF_CASE(128, 128) SRF_CASE(16, 128) SRF_CASE(32, 128) SRF_CASE(64, 32) SRF_CASE(128, 64) SRF_CASE(128, 32)
-  SRF_CASE(64, 16) SRF_CASE(32, 16) SRF_CASE(16, 64) SRF_CASE(128, 16)
+template <bool SPLIT>
+static int dispatch_dense(int tk, int tn, const IgemmArgs& a, int host_tiles, cudaStream_t st) {
+  // (split operands use K slices of at most 64 channels: srf_linear_tile_k_enc)
+#define SRF_CASE(ci, co) if constexpr (!(SPLIT && ci > 64)) { if (tk == ci && tn == co) return launch_igemm<ci, co, false, SPLIT>(a, host_tiles, st); }
+  SRF_CASE(128, 128) SRF_CASE(64, 128) SRF_CASE(32, 128) SRF_CASE(16, 128)
+  SRF_CASE(128, 64) SRF_CASE(64, 64) SRF_CASE(32, 64) SRF_CASE(128, 32) SRF_CASE(64, 32) SRF_CASE(32, 32)
+  SRF_CASE(128, 16) SRF_CASE(64, 16) SRF_CASE(16, 16)
 #undef SRF_CASE
-  set_error("igemm: unsupported channel pair cin=%d cout=%d (each must be 16/32/64/128)", cin, cout);
+  set_error("dense igemm: unsupported tile k=%d n=%d", tk, tn);
   return SRF_ERR_UNSUPPORTED;
 }
 
@@ -873,28 +641,28 @@ extern "C" int srf_prof_read_t(unsigned long long* host, int launch) {   // laun
 
 extern "C" {
 
-int srf_linear_tile_k(int32_t k);
-int srf_linear_tile_n(int32_t n);
-
 static bool use_warp16() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("SRF_CONV16_WARP"); on = (e && e[0] == '0') ? 0 : 1; }
   return on != 0;
 }
 
-int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
-  SRF_CHECK_ARG(c && c->in && c->nbr && c->w && (c->out || c->dense), "srf_spconv_bf16: null arg");
-  SRF_CHECK_ARG(c->in_dtype == SRF_BF16, "srf_spconv_bf16: input features must be bf16");
-  SRF_CHECK_ARG(c->kvol >= 1 && c->kvol <= 27, "srf_spconv_bf16: kvol must be in [1,27]");
-  SRF_CHECK_ARG(c->cap_out > 0 && c->cap_out % 128 == 0, "srf_spconv_bf16: cap_out must be a multiple of 128");
-  SRF_CHECK_ARG(!c->dense || c->out_coors, "srf_spconv_bf16: dense output needs out_coors");
+int srf_spconv_tc(const srf_conv_args* c, void* stream) {
+  SRF_CHECK_ARG(c && c->in && c->nbr && c->w && (c->out || c->dense), "srf_spconv_tc: null arg");
+  SRF_CHECK_ARG(enc_is_16(c->in_dtype), "srf_spconv_tc: input features must be bf16 / f16 / split");
+  SRF_CHECK_ARG(c->kvol >= 1 && c->kvol <= 27, "srf_spconv_tc: kvol must be in [1,27]");
+  SRF_CHECK_ARG(c->cap_out > 0 && c->cap_out % 128 == 0, "srf_spconv_tc: cap_out must be a multiple of 128");
+  SRF_CHECK_ARG(!c->dense || c->out_coors, "srf_spconv_tc: dense output needs out_coors");
+  SRF_CHECK_ARG(c->dense || c->out_dtype == SRF_F32 || (enc_is_16(c->out_dtype) && enc_is_f16(c->out_dtype) == enc_is_f16(c->in_dtype)),
+                "srf_spconv_tc: a 16-bit output must use the input's element format");
+  const bool split = enc_is_split(c->in_dtype);
   // 16 -> 16 channels (the sparsely connected finest level): warp-level MMA kernel, spconv_warp16.cu
-  if (c->cin == 16 && c->cout == 16 && !c->dense && c->out && c->out_dtype == SRF_BF16 && use_warp16())
-    return spconv16_warp_launch(c, (cudaStream_t)stream);
+  if (!split && c->cin == 16 && c->cout == 16 && c->kvol == 27 && !c->dense && c->out && c->out_dtype == c->in_dtype && use_warp16())
+    return spconv16_warp_launch(c, enc_is_f16(c->in_dtype), (cudaStream_t)stream);
   IgemmArgs a = {};
-  { const char* e = getenv("SRF_IGEMM_DBG"); a.dbg = e ? atoi(e) : 0; }
-  a.in = (const __nv_bfloat16*)c->in;
-  a.in_stride = c->cin;
+  a.in = (const uint16_t*)c->in;
+  a.in_stride = split ? 2 * c->cin : c->cin;
+  a.in_lo_off = c->cin;
   a.k_stride = 0;
   a.nbr = c->nbr;
   a.tile_mask = c->tile_mask;
@@ -902,66 +670,96 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) {
   a.cap_out = c->cap_out;
   a.kvol = c->kvol;
   a.n_tiles = 1;
-  a.w = (const __nv_bfloat16*)c->w;
+  a.w = (const uint16_t*)c->w;
   a.bias = c->bias;
   a.residual = c->residual;
   a.relu = c->relu;
   a.out = c->out;
-  a.out_bf16 = c->out_dtype == SRF_BF16;
-  a.out_stride = c->cout;
+  a.fmt = enc_is_f16(c->in_dtype) ? 1 : 0;
+  a.out_enc = c->dense ? SRF_F32 : c->out_dtype;
+  a.out_stride = enc_is_split(a.out_enc) ? 2 * c->cout : c->cout;
+  a.out_lo_off = c->cout;
   a.dense = c->dense;
   a.out_coors = (const int4*)c->out_coors;
   a.D = c->out_dims[1];
   a.H = c->out_dims[2];
   a.W = c->out_dims[3];
-  if (!use_ldgsts()) {
-    const long long in_rows = c->in_rows > 0 ? c->in_rows : (1ll << 30);
-    return dispatch_igemm_tma<true>(c->cin, c->cout, a, c->cap_out / 128, in_rows, c->cin, (cudaStream_t)stream);
-  }
-  return dispatch_igemm<true>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream);
+  return split ? dispatch_sparse<true>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream)
+               : dispatch_sparse<false>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream);
 }
 
-int srf_linear_splits(int32_t k, int32_t k_splits) {
-  const int kvol = k / srf_linear_tile_k(k);
+int srf_spconv_bf16(const srf_conv_args* c, void* stream) { return srf_spconv_tc(c, stream); }
+
+// K chunk per ring slot of the sparse kernel (the packer lays the weights out per chunk)
+int srf_pack_weight_kc(int32_t cin, int32_t enc) {
+  if (!enc_is_split(enc)) return cin;
+  return cin == 64 ? SRF_SPLIT_KC64 : (cin == 128 ? SRF_SPLIT_KC128 : cin);
+}
+
+int srf_linear_tile_k_enc(int32_t k, int32_t enc) {
+  // K slice per ring slot of the dense tcgen05 GEMM: 128 channels (64 for split operands, whose
+  // slot rows carry hi and lo)
+  const int cap = enc_is_split(enc) ? 64 : 128;
+  return k > cap ? cap : k;
+}
+int srf_linear_tile_k(int32_t k) { return srf_linear_tile_k_enc(k, SRF_BF16); }
+int srf_linear_tile_n(int32_t n) { return n > 128 ? 128 : n; }
+
+int srf_linear_splits_enc(int32_t k, int32_t enc, int32_t k_splits) {
+  const int kvol = k / srf_linear_tile_k_enc(k, enc);
   if (k_splits <= 1 || kvol <= 1) return 1;
   const int kper = (kvol + k_splits - 1) / k_splits;
   return (kvol + kper - 1) / kper;
 }
+int srf_linear_splits(int32_t k, int32_t k_splits) { return srf_linear_splits_enc(k, SRF_BF16, k_splits); }
 
-int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
-                    int32_t epi, const float* ln_w, const float* ln_b, void* out, int32_t out_dtype, int32_t k_splits,
-                    void* stream) {
-  SRF_CHECK_ARG(a_bf16 && w_packed && out && m >= 0 && k > 0 && n > 0, "srf_linear_bf16: bad args");
+int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
+                  int32_t epi, const float* ln_w, const float* ln_b, float ln_eps, void* out, int32_t out_enc, int32_t k_splits,
+                  void* stream) {
+  SRF_CHECK_ARG(a_in && w_packed && out && m >= 0 && k > 0 && n > 0, "srf_linear_tc: bad args");
+  SRF_CHECK_ARG(enc_is_16(a_enc), "srf_linear_tc: A must be bf16 / f16 / split");
+  SRF_CHECK_ARG(out_enc == SRF_F32 || (enc_is_16(out_enc) && enc_is_f16(out_enc) == enc_is_f16(a_enc)),
+                "srf_linear_tc: a 16-bit output must use A's element format");
   if (m == 0) return SRF_OK;
-  int tk = srf_linear_tile_k(k), tn = srf_linear_tile_n(n);
-  SRF_CHECK_ARG(k % tk == 0 && n % tn == 0, "srf_linear_bf16: n=%d k=%d not tileable", n, k);
-  SRF_CHECK_ARG(!(epi & 2) || (n == tn && ln_w && ln_b), "srf_linear_bf16: fused LayerNorm needs n <= 128 and ln weights");
+  const bool split = enc_is_split(a_enc);
+  int tk = srf_linear_tile_k_enc(k, a_enc), tn = srf_linear_tile_n(n);
+  SRF_CHECK_ARG(k % tk == 0 && n % tn == 0, "srf_linear_tc: n=%d k=%d not tileable", n, k);
+  SRF_CHECK_ARG(!(epi & 2) || (n == tn && ln_w && ln_b), "srf_linear_tc: fused LayerNorm needs n <= 128 and ln weights");
   IgemmArgs a = {};
-  { const char* e = getenv("SRF_IGEMM_DBG"); a.dbg = e ? atoi(e) : 0; }
-  a.in = (const __nv_bfloat16*)a_bf16;
-  a.in_stride = k;
+  a.in = (const uint16_t*)a_in;
+  a.in_stride = split ? 2 * k : k;
+  a.in_lo_off = k;
   a.k_stride = tk;
   a.m_rows = m;
   a.cap_out = m;
   a.kvol = k / tk;
   a.n_tiles = n / tn;
-  a.w = (const __nv_bfloat16*)w_packed;
+  a.w = (const uint16_t*)w_packed;
   a.bias = bias;
   a.relu = epi & 1;
   a.ln = (epi & 2) ? 1 : 0;
   a.ln_w = ln_w;
   a.ln_b = ln_b;
+  a.ln_eps = ln_eps;
   a.out = out;
-  a.out_bf16 = out_dtype == SRF_BF16;
-  a.out_stride = n;
+  a.fmt = enc_is_f16(a_enc) ? 1 : 0;
+  a.out_enc = out_enc;
+  a.out_stride = enc_is_split(out_enc) ? 2 * n : n;
+  a.out_lo_off = n;
   a.k_splits = 1;
-  if (k_splits > 1 && use_ldgsts()) {
-    SRF_CHECK_ARG(epi == 0 && !bias && out_dtype == SRF_F32, "srf_linear_bf16: split-K needs epi=0, no bias and an f32 output of k_splits slabs");
+  if (k_splits > 1) {
+    SRF_CHECK_ARG(epi == 0 && !bias && out_enc == SRF_F32, "srf_linear_tc: split-K needs epi=0, no bias and an f32 output of k_splits slabs");
     const int kper = (a.kvol + k_splits - 1) / k_splits;
     a.k_splits = (a.kvol + kper - 1) / kper;   // every split owns at least one K slice
   }
-  if (!use_ldgsts()) return dispatch_igemm_tma<false>(tk, tn, a, cdiv(m, 128) * (n / tn), m, k, (cudaStream_t)stream);
-  return dispatch_igemm<false>(tk, tn, a, cdiv(m, 128) * (n / tn) * a.k_splits, (cudaStream_t)stream);
+  const int tiles = cdiv(m, 128) * (n / tn) * a.k_splits;
+  return split ? dispatch_dense<true>(tk, tn, a, tiles, (cudaStream_t)stream) : dispatch_dense<false>(tk, tn, a, tiles, (cudaStream_t)stream);
+}
+
+int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
+                    int32_t epi, const float* ln_w, const float* ln_b, void* out, int32_t out_dtype, int32_t k_splits,
+                    void* stream) {
+  return srf_linear_tc(a_bf16, SRF_BF16, m, k, w_packed, n, bias, epi, ln_w, ln_b, 1e-5f, out, out_dtype, k_splits, stream);
 }
 
 }  // extern "C"

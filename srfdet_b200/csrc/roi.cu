@@ -25,7 +25,8 @@ struct Pyr {
 struct OutSpec {
   void* ptr;
   int channel_last;  // (k,49,C') rows instead of (k,C,7,7)
-  int bf16;          // bf16 output (channel_last only)
+  int enc;           // SRF_F32 or a 16-bit encoding (channel_last only); split rows are [hi | lo] halves of row_stride
+  int lo_off;        // split encodings: elements from the hi half to the lo half (row_stride / 2)
   int row_stride;    // C' = channels of a destination row (>= C): lets two samplers fill one concatenated buffer
   int ch_offset;     // first destination channel
 };
@@ -351,9 +352,13 @@ __device__ __forceinline__ void store_bin_cl(const OutSpec& o, int k, int bin, i
     if (c >= C) continue;
     if (o.channel_last) {
       const size_t e = ((size_t)k * NBIN + bin) * o.row_stride + o.ch_offset + c;
-      if (o.bf16) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[pss].x, acc[pss].y), h1 = __floats2bfloat162_rn(acc[pss].z, acc[pss].w);
-        *reinterpret_cast<uint2*>((__nv_bfloat16*)o.ptr + e) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      if (o.enc != SRF_F32) {
+        const bool f16 = enc_is_f16(o.enc);
+        uint32_t h0, h1, l0, l1;
+        split16x2(f16, acc[pss].x, acc[pss].y, h0, l0);
+        split16x2(f16, acc[pss].z, acc[pss].w, h1, l1);
+        *reinterpret_cast<uint2*>((uint16_t*)o.ptr + e) = make_uint2(h0, h1);
+        if (enc_is_split(o.enc)) *reinterpret_cast<uint2*>((uint16_t*)o.ptr + e + o.lo_off) = make_uint2(l0, l1);
       } else {
         *reinterpret_cast<float4*>((float*)o.ptr + e) = acc[pss];
       }
@@ -511,15 +516,18 @@ static int make_out(OutSpec* o, const srf_roi_out* u, int channels, bool cl_maps
   if (!u || !u->ptr) { set_error("%s: null output", who); return SRF_ERR_ARG; }
   o->ptr = u->ptr;
   o->channel_last = u->channel_last;
-  o->bf16 = u->dtype == SRF_BF16;
-  o->row_stride = u->row_stride > 0 ? u->row_stride : channels;
+  o->enc = u->dtype;
+  const int parts = enc_is_split(o->enc) ? 2 : 1;
+  o->row_stride = u->row_stride > 0 ? u->row_stride : parts * channels;
+  o->lo_off = o->row_stride / 2;
   o->ch_offset = u->ch_offset;
-  const bool plain = !o->bf16 && o->row_stride == channels && o->ch_offset == 0;
+  if (o->enc != SRF_F32 && !enc_is_16(o->enc)) { set_error("%s: bad output dtype", who); return SRF_ERR_ARG; }
+  const bool plain = o->enc == SRF_F32 && o->row_stride == channels && o->ch_offset == 0;
   if (!plain && !(cl_maps && o->channel_last)) {
-    set_error("%s: bf16 / strided output needs channel_last output and channels_last feature maps", who);
+    set_error("%s: 16-bit / strided output needs channel_last output and channels_last feature maps", who);
     return SRF_ERR_UNSUPPORTED;
   }
-  if (o->row_stride < o->ch_offset + channels || (o->row_stride % 4) || (o->ch_offset % 4)) {
+  if (o->row_stride / parts < o->ch_offset + channels || (o->row_stride % (4 * parts)) || (o->ch_offset % 4)) {
     set_error("%s: bad output row stride / channel offset", who);
     return SRF_ERR_ARG;
   }
@@ -534,7 +542,7 @@ int srf_roi_extract(const srf_pyramid* p, const float* rois, int32_t k, float* o
   SRF_COUNT(1);
   if (d.channels_last) {
     Range rg = {};
-    OutSpec o{out, channel_last, 0, d.channels, 0};
+    OutSpec o{out, channel_last, SRF_F32, 0, d.channels, 0};
     if (d.channels <= 128) bev_roi_cl_kernel<1><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, o, nullptr);
     else bev_roi_cl_kernel<2><<<k, 256, 0, (cudaStream_t)stream>>>(d, nullptr, rois, 1, 0, rg, 0, o, nullptr);
     SRF_LAUNCH_CHECK();

@@ -9,6 +9,24 @@
 
 namespace srf {
 
+// one value of a row-major (rows, c) buffer in encoding `enc` (split rows are [hi(c) | lo(c)])
+__device__ __forceinline__ float ld_enc(const void* p, int enc, size_t row, int c, int col) {
+  if (enc == SRF_F32) return __ldg((const float*)p + row * c + col);
+  const bool f16 = enc_is_f16(enc);
+  const uint16_t* q = (const uint16_t*)p;
+  if (!enc_is_split(enc)) return unpack16(f16, q[row * c + col]);
+  return unpack16(f16, q[row * 2 * c + col]) + unpack16(f16, q[row * 2 * c + c + col]);
+}
+__device__ __forceinline__ void st_enc(void* p, int enc, size_t row, int c, int col, float v) {
+  if (enc == SRF_F32) { ((float*)p)[row * c + col] = v; return; }
+  const bool f16 = enc_is_f16(enc);
+  uint16_t* q = (uint16_t*)p;
+  if (!enc_is_split(enc)) { q[row * c + col] = pack16(f16, v); return; }
+  const uint16_t h = pack16(f16, v);
+  q[row * 2 * c + col] = h;
+  q[row * 2 * c + c + col] = pack16(f16, v - unpack16(f16, h));
+}
+
 template <typename T>
 __device__ __forceinline__ float ld_as_float(const T* p);
 template <>
@@ -29,7 +47,7 @@ struct ConvDev {
   void* out;
   float* dense;
   const int4* out_coors;
-  int cin, kvol, cap_out, relu, out_bf16;
+  int cin, kvol, cap_out, relu, out_enc;
   int D, H, W;
 };
 
@@ -84,19 +102,14 @@ __global__ void __launch_bounds__(128) spconv_f32_kernel(ConvDev a) {
       int row = row0 + rg * RPT + r;
       if (row >= n_out) continue;
       float v = acc[r] + b;
-      if (a.residual) {
-        v += a.out_bf16 ? __bfloat162float(((const __nv_bfloat16*)a.residual)[(size_t)row * COUT + co])
-                        : ((const float*)a.residual)[(size_t)row * COUT + co];
-      }
+      if (a.residual) v += ld_enc(a.residual, a.out_enc, (size_t)row, COUT, co);
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.dense) {
         int4 q = __ldg(a.out_coors + row);
         size_t hw = (size_t)a.H * a.W;
         a.dense[((size_t)q.x * COUT * a.D + (size_t)co * a.D + q.y) * hw + (size_t)q.z * a.W + q.w] = v;
-      } else if (a.out_bf16) {
-        ((__nv_bfloat16*)a.out)[(size_t)row * COUT + co] = __float2bfloat16(v);
       } else {
-        ((float*)a.out)[(size_t)row * COUT + co] = v;
+        st_enc(a.out, a.out_enc, (size_t)row, COUT, co, v);
       }
     }
   }
@@ -139,62 +152,81 @@ __global__ void __launch_bounds__(128) spconv_smallcin_kernel(ConvDev a) {
 #pragma unroll
       for (int c = 0; c < COUT; ++c) acc[c] = fmaxf(acc[c], 0.f);
     }
-    if (a.out_bf16) {
-      uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)a.out + (size_t)row * COUT);
-#pragma unroll
-      for (int c = 0; c < COUT; c += 8) {
-        uint32_t w4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(acc[c + 2 * q], acc[c + 2 * q + 1]);
-          w4[q] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        op[c / 8] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-      }
-    } else {
+    if (a.out_enc == SRF_F32) {
       float4* op = reinterpret_cast<float4*>((float*)a.out + (size_t)row * COUT);
 #pragma unroll
       for (int c = 0; c < COUT; c += 4) op[c / 4] = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+    } else {
+      const bool f16 = enc_is_f16(a.out_enc), split = enc_is_split(a.out_enc);
+      uint16_t* orow = (uint16_t*)a.out + (size_t)row * COUT * (split ? 2 : 1);
+#pragma unroll
+      for (int c = 0; c < COUT; c += 8) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split16x2(f16, acc[c + 2 * q], acc[c + 2 * q + 1], h[q], l[q]);
+        *reinterpret_cast<uint4*>(orow + c) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (split) *reinterpret_cast<uint4*>(orow + COUT + c) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
     }
   }
 }
 
-// (kvol, cin, cout) f32 -> bf16 in UMMA "core matrix" order:
-//   [k][ci/8][co][ci%8]   (one 16-byte K-chunk per output channel row)
-__global__ void pack_weight_kernel(const float* __restrict__ w, int kvol, int cin, int cout,
-                                   __nv_bfloat16* __restrict__ out) {
+// (kvol, cin, cout) f32 -> 16-bit elements in UMMA "core matrix" order, per kernel offset k and
+// K chunk q of kc input channels:   [k][q][part][kc/8][co][ci%8]   (one 16-byte K-chunk per output
+// channel row; part = hi only, or hi then lo for the split encodings)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int kvol, int cin, int cout, int kc, int enc,
+                                   uint16_t* __restrict__ out) {
+  const bool f16 = enc_is_f16(enc);
+  const int parts = enc_is_split(enc) ? 2 : 1;
   int64_t total = (int64_t)kvol * cin * cout;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int co = (int)(e % cout);
     int64_t t = e / cout;
     int ci = (int)(t % cin);
     int k = (int)(t / cin);
-    int64_t dst = (((int64_t)k * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8);
-    out[dst] = __float2bfloat16(w[e]);
+    const int q = ci / kc, cl = ci % kc;
+    const int64_t member = ((int64_t)k * (cin / kc) + q) * parts;           // in units of kc*cout elements
+    const int64_t inner = ((int64_t)(cl / 8) * cout + co) * 8 + (cl % 8);
+    const float v = w[e];
+    const uint16_t h = pack16(f16, v);
+    out[member * kc * cout + inner] = h;
+    if (parts == 2) out[(member + 1) * kc * cout + inner] = pack16(f16, v - unpack16(f16, h));
   }
 }
 
-// nn.Linear weight (n, k) f32 -> bf16 tiles [n/tn][k/tk][tk/8][tn][8]
-__global__ void pack_linear_kernel(const float* __restrict__ w, int n, int k, int tn, int tk,
-                                   __nv_bfloat16* __restrict__ out) {
+// nn.Linear weight (n, k) f32 -> 16-bit tiles [n/tn][k/tk][part][tk/8][tn][8]
+__global__ void pack_linear_kernel(const float* __restrict__ w, int n, int k, int tn, int tk, int enc,
+                                   uint16_t* __restrict__ out) {
+  const bool f16 = enc_is_f16(enc);
+  const int parts = enc_is_split(enc) ? 2 : 1;
   int64_t total = (int64_t)n * k;
   int nkc = k / tk;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int kk = (int)(e % k);
     int nn = (int)(e / k);
     int nt = nn / tn, nl = nn % tn, kc = kk / tk, ci = kk % tk;
-    int64_t dst = ((((int64_t)nt * nkc + kc) * (tk / 8) + ci / 8) * tn + nl) * 8 + (ci % 8);
-    out[dst] = __float2bfloat16(w[e]);
+    const int64_t member = ((int64_t)nt * nkc + kc) * parts;
+    const int64_t inner = ((int64_t)(ci / 8) * tn + nl) * 8 + (ci % 8);
+    const float v = w[e];
+    const uint16_t h = pack16(f16, v);
+    out[member * tk * tn + inner] = h;
+    if (parts == 2) out[(member + 1) * tk * tn + inner] = pack16(f16, v - unpack16(f16, h));
   }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, int64_t rows, int c, int c_pad,
-                                   __nv_bfloat16* __restrict__ out) {
+// (rows, c) f32 -> rows of c_pad 16-bit elements (zero padded), split rows [hi(c_pad) | lo(c_pad)]
+__global__ void convert_rows_kernel(const float* __restrict__ in, int64_t rows, int c, int c_pad, int enc,
+                                    uint16_t* __restrict__ out) {
+  const bool f16 = enc_is_f16(enc), split = enc_is_split(enc);
   int64_t total = rows * c_pad;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int j = (int)(e % c_pad);
     int64_t r = e / c_pad;
-    out[e] = __float2bfloat16(j < c ? in[r * c + j] : 0.f);
+    const float v = j < c ? in[r * c + j] : 0.f;
+    const uint16_t h = pack16(f16, v);
+    if (!split) { out[e] = h; continue; }
+    out[r * 2 * c_pad + j] = h;
+    out[r * 2 * c_pad + c_pad + j] = pack16(f16, v - unpack16(f16, h));
   }
 }
 
@@ -257,14 +289,12 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 // row-wise LayerNorm (+ReLU) of (sum of split-K slabs + bias), one warp per row; f32 or bf16.
 // The row is read once into registers (n <= 32*LN_MAXPL), then reduced with shuffles.
 constexpr int LN_MAXPL = 16;   // values per lane -> n <= 512
-template <typename T>
-__global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, int n, int n_partials,
+__global__ void layernorm_rows_kernel(const void* __restrict__ in, int in_enc, int64_t rows, int n, int n_partials,
                                       const float* __restrict__ bias, const float* __restrict__ g,
-                                      const float* __restrict__ b, float eps, int relu, T* __restrict__ out) {
+                                      const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc) {
   int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const T* x = in + row * n;
   float v[LN_MAXPL];
   float s = 0.f;
 #pragma unroll
@@ -272,8 +302,8 @@ __global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, in
     const int j = lane + 32 * i;
     v[i] = 0.f;
     if (j < n) {
-      float t = (float)x[j];
-      for (int p = 1; p < n_partials; ++p) t += (float)x[(size_t)p * rows * n + j];   // slab order: deterministic
+      float t = ld_enc(in, in_enc, (size_t)row, n, j);
+      for (int p = 1; p < n_partials; ++p) t += ld_enc(in, in_enc, (size_t)(p * rows + row), n, j);   // slab order: deterministic
       v[i] = t + (bias ? bias[j] : 0.f);
       s += v[i];
     }
@@ -292,24 +322,22 @@ __global__ void layernorm_rows_kernel(const T* __restrict__ in, int64_t rows, in
     if (j < n) {
       float y = (v[i] - mean) * rstd * g[j] + b[j];
       if (relu) y = fmaxf(y, 0.f);
-      out[row * n + j] = (T)y;
+      st_enc(out, out_enc, (size_t)row, n, j, y);
     }
   }
 }
 
 // One block per row, one thread per column (n <= 1024): used when split-K slabs have to be
 // summed -- 4-32 warps per row instead of one keeps enough loads in flight.
-template <typename T>
-__global__ void layernorm_cols_kernel(const T* __restrict__ in, int64_t rows, int n, int n_partials,
+__global__ void layernorm_cols_kernel(const void* __restrict__ in, int in_enc, int64_t rows, int n, int n_partials,
                                       const float* __restrict__ bias, const float* __restrict__ g,
-                                      const float* __restrict__ b, float eps, int relu, T* __restrict__ out) {
+                                      const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc) {
   __shared__ float red[2][32];
   const int64_t row = blockIdx.x;
   const int j = threadIdx.x, lane = j & 31, w = j >> 5, nw = (blockDim.x + 31) >> 5;
   float v = 0.f;
   if (j < n) {
-    const T* x = in + row * n + j;
-    for (int p = 0; p < n_partials; ++p) v += (float)x[(size_t)p * rows * n];   // slab order: deterministic
+    for (int p = 0; p < n_partials; ++p) v += ld_enc(in, in_enc, (size_t)(p * rows + row), n, j);   // slab order: deterministic
     v += bias ? bias[j] : 0.f;
   }
   float s = j < n ? v : 0.f;
@@ -330,7 +358,7 @@ __global__ void layernorm_cols_kernel(const T* __restrict__ in, int64_t rows, in
   if (j < n) {
     float y = d * rstd * g[j] + b[j];
     if (relu) y = fmaxf(y, 0.f);
-    out[row * n + j] = (T)y;
+    st_enc(out, out_enc, (size_t)row, n, j, y);
   }
 }
 
@@ -369,7 +397,7 @@ int srf_spconv_f32(const srf_conv_args* a, void* stream) {
   d.in = a->in; d.nbr = a->nbr; d.tile_mask = a->tile_mask; d.d_n_out = a->d_n_out;
   d.w = (const float*)a->w; d.bias = a->bias; d.residual = a->residual; d.out = a->out; d.dense = a->dense;
   d.out_coors = (const int4*)a->out_coors; d.cin = a->cin; d.kvol = a->kvol; d.cap_out = a->cap_out;
-  d.relu = a->relu; d.out_bf16 = a->out_dtype == SRF_BF16;
+  d.relu = a->relu; d.out_enc = a->dense ? SRF_F32 : a->out_dtype;
   d.D = a->out_dims[1]; d.H = a->out_dims[2]; d.W = a->out_dims[3];
   int ntiles = a->cap_out / SIMT_TILE;
   int grid = sm_count() * 8;
@@ -393,41 +421,46 @@ int srf_spconv_f32(const srf_conv_args* a, void* stream) {
   return SRF_OK;
 }
 
-int srf_pack_weight_bf16(const float* w, int32_t kvol, int32_t cin, int32_t cout, void* packed, void* stream) {
-  SRF_CHECK_ARG(w && packed && kvol > 0 && cin % 8 == 0 && cout % 8 == 0, "srf_pack_weight_bf16: bad args");
+int srf_pack_weight_kc(int32_t cin, int32_t enc);   // igemm_umma.cu: K chunk per ring slot for (cin, enc)
+int srf_linear_tile_k_enc(int32_t k, int32_t enc);
+int srf_linear_tile_n(int32_t n);
+
+int srf_pack_weight_tc(const float* w, int32_t kvol, int32_t cin, int32_t cout, int32_t enc, void* packed, void* stream) {
+  SRF_CHECK_ARG(w && packed && kvol > 0 && cin % 8 == 0 && cout % 8 == 0 && enc_is_16(enc), "srf_pack_weight_tc: bad args");
   int64_t total = (int64_t)kvol * cin * cout;
   SRF_COUNT(1);
-  pack_weight_kernel<<<lgrid2(total, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cout, (__nv_bfloat16*)packed);
+  pack_weight_kernel<<<lgrid2(total, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cout, srf_pack_weight_kc(cin, enc), enc, (uint16_t*)packed);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }
-
-int srf_linear_tile_k(int32_t k) {
-  // K slice per ring slot of the dense tcgen05 GEMM (SRF_LINEAR_TILE_K: A/B knob, 64 or 128)
-  static int cap = 0;
-  if (!cap) { const char* e = getenv("SRF_LINEAR_TILE_K"); cap = e ? atoi(e) : 128; if (cap != 64 && cap != 128) cap = 128; }
-  return k > cap ? cap : k;
+int srf_pack_weight_bf16(const float* w, int32_t kvol, int32_t cin, int32_t cout, void* packed, void* stream) {
+  return srf_pack_weight_tc(w, kvol, cin, cout, SRF_BF16, packed, stream);
 }
-int srf_linear_tile_n(int32_t n) { return n > 128 ? 128 : n; }
 
-int srf_pack_linear_bf16(const float* w, int32_t n, int32_t k, void* packed, void* stream) {
-  SRF_CHECK_ARG(w && packed, "srf_pack_linear_bf16: null arg");
-  int tk = srf_linear_tile_k(k), tn = srf_linear_tile_n(n);
+int srf_pack_linear_tc(const float* w, int32_t n, int32_t k, int32_t enc, void* packed, void* stream) {
+  SRF_CHECK_ARG(w && packed && enc_is_16(enc), "srf_pack_linear_tc: bad args");
+  int tk = srf_linear_tile_k_enc(k, enc), tn = srf_linear_tile_n(n);
   SRF_CHECK_ARG(k % tk == 0 && n % tn == 0 && tk % 16 == 0 && tn % 16 == 0,
-                "srf_pack_linear_bf16: n=%d k=%d not tileable (multiples of 16; of 128 above 128)", n, k);
+                "srf_pack_linear_tc: n=%d k=%d not tileable (multiples of 16; of the tile size above it)", n, k);
   SRF_COUNT(1);
-  pack_linear_kernel<<<lgrid2((int64_t)n * k, 256), 256, 0, (cudaStream_t)stream>>>(w, n, k, tn, tk, (__nv_bfloat16*)packed);
+  pack_linear_kernel<<<lgrid2((int64_t)n * k, 256), 256, 0, (cudaStream_t)stream>>>(w, n, k, tn, tk, enc, (uint16_t*)packed);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }
+int srf_pack_linear_bf16(const float* w, int32_t n, int32_t k, void* packed, void* stream) {
+  return srf_pack_linear_tc(w, n, k, SRF_BF16, packed, stream);
+}
 
-int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, void* out, void* stream) {
-  SRF_CHECK_ARG(in && out && rows >= 0 && c > 0 && c_pad >= c, "srf_f32_to_bf16: bad args");
+int srf_convert_rows(const float* in, int64_t rows, int32_t c, int32_t c_pad, int32_t enc, void* out, void* stream) {
+  SRF_CHECK_ARG(in && out && rows >= 0 && c > 0 && c_pad >= c && enc_is_16(enc), "srf_convert_rows: bad args");
   if (rows == 0) return SRF_OK;
   SRF_COUNT(1);
-  f32_to_bf16_kernel<<<lgrid2(rows * c_pad, 256), 256, 0, (cudaStream_t)stream>>>(in, rows, c, c_pad, (__nv_bfloat16*)out);
+  convert_rows_kernel<<<lgrid2(rows * c_pad, 256), 256, 0, (cudaStream_t)stream>>>(in, rows, c, c_pad, enc, (uint16_t*)out);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
+}
+int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, void* out, void* stream) {
+  return srf_convert_rows(in, rows, c, c_pad, SRF_BF16, out, stream);
 }
 
 int srf_gather_rows(const float* in, const int32_t* perm, const int32_t* d_n, int32_t cap, int32_t c, float* out,
@@ -451,30 +484,30 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
   return SRF_OK;
 }
 
-int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
-                  const float* gamma, const float* beta, float eps, int32_t relu, void* out, void* stream) {
+int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
+                      const float* gamma, const float* beta, float eps, int32_t relu, void* out, int32_t out_enc, void* stream) {
   if (n_partials < 1) n_partials = 1;
   SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
+  SRF_CHECK_ARG(in_enc == SRF_F32 || in_enc == SRF_BF16 || in_enc == SRF_F16, "srf_layernorm: input must be f32 / bf16 / f16");
   SRF_CHECK_ARG(n <= 32 * LN_MAXPL || (n_partials > 1 && n <= 1024), "srf_layernorm: n must be <= %d", 32 * LN_MAXPL);
   if (rows == 0) return SRF_OK;
   SRF_COUNT(1);
   if (n_partials > 1 && n <= 1024) {
     const int threads = (n + 31) / 32 * 32;
-    if (dtype == SRF_BF16)
-      layernorm_cols_kernel<__nv_bfloat16><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (__nv_bfloat16*)out);
-    else
-      layernorm_cols_kernel<float><<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (float*)out);
+    layernorm_cols_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, gamma, beta, eps, relu, out, out_enc);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }
   int wpb = 4;
   int grid = (int)((rows + wpb - 1) / wpb);
-  if (dtype == SRF_BF16)
-    layernorm_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (__nv_bfloat16*)out);
-  else
-    layernorm_rows_kernel<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const float*)in, rows, n, n_partials, bias, gamma, beta, eps, relu, (float*)out);
+  layernorm_rows_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, gamma, beta, eps, relu, out, out_enc);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
+}
+
+int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
+                  const float* gamma, const float* beta, float eps, int32_t relu, void* out, void* stream) {
+  return srf_layernorm_enc(in, dtype, rows, n, n_partials, bias, gamma, beta, eps, relu, out, dtype, stream);
 }
 
 }  // extern "C"

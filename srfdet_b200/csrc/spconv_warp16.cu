@@ -1,4 +1,4 @@
-// 16 -> 16 channel sparse convolution on warp-level tensor-core MMAs (BF16 mode).
+// 16 -> 16 channel sparse convolution on warp-level tensor-core MMAs (16-bit modes: bf16 or f16).
 //
 // The finest level of the encoder has few neighbours per voxel (3.7 of 27 on the nuScenes-shaped
 // bench cloud): a 128-row tcgen05 tile gathers 27 x 128 row slots of which 14 % exist, and the
@@ -14,12 +14,19 @@
 
 namespace srf {
 
-__device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                               uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  if (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 struct Warp16Args {
@@ -33,6 +40,7 @@ struct Warp16Args {
   int kvol, cap_out, relu;
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(128) spconv16_warp_kernel(Warp16Args a) {
   __shared__ uint32_t sW[27 * 128];
   for (int e = threadIdx.x; e < a.kvol * 128; e += blockDim.x) sW[e] = __ldg(a.w + e);
@@ -88,8 +96,8 @@ __global__ void __launch_bounds__(128) spconv16_warp_kernel(Warp16Args a) {
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mma_bf16_16816(acc[h][0], fa[kk][h][0], fa[kk][h][1], fa[kk][h][2], fa[kk][h][3], b[0][0], b[0][1]);
-          mma_bf16_16816(acc[h][1], fa[kk][h][0], fa[kk][h][1], fa[kk][h][2], fa[kk][h][3], b[1][0], b[1][1]);
+          mma_16816<F16>(acc[h][0], fa[kk][h][0], fa[kk][h][1], fa[kk][h][2], fa[kk][h][3], b[0][0], b[0][1]);
+          mma_16816<F16>(acc[h][1], fa[kk][h][0], fa[kk][h][1], fa[kk][h][2], fa[kk][h][3], b[1][0], b[1][1]);
         }
       }
     }
@@ -107,21 +115,19 @@ __global__ void __launch_bounds__(128) spconv16_warp_kernel(Warp16Args a) {
           float v0 = acc[h][nt][2 * half] + bz0, v1 = acc[h][nt][2 * half + 1] + bz1;
           const size_t word = (size_t)orow * 8 + nt * 4 + c;
           if (a.residual) {
-            const uint32_t rw = __ldg(a.residual + word);
-            const __nv_bfloat162 rb = *reinterpret_cast<const __nv_bfloat162*>(&rw);
-            v0 += __low2float(rb);
-            v1 += __high2float(rb);
+            const float2 rf = unpack16x2(F16, __ldg(a.residual + word));
+            v0 += rf.x;
+            v1 += rf.y;
           }
           if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-          const __nv_bfloat162 ob = __floats2bfloat162_rn(v0, v1);
-          a.out[word] = *reinterpret_cast<const uint32_t*>(&ob);
+          a.out[word] = pack16x2(F16, v0, v1);
         }
       }
     }
   }
 }
 
-int spconv16_warp_launch(const srf_conv_args* cv, cudaStream_t st) {
+int spconv16_warp_launch(const srf_conv_args* cv, bool f16, cudaStream_t st) {
   Warp16Args a;
   a.in = (const uint32_t*)cv->in;
   a.nbr = cv->nbr;
@@ -138,7 +144,8 @@ int spconv16_warp_launch(const srf_conv_args* cv, cudaStream_t st) {
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   SRF_COUNT(1);
-  spconv16_warp_kernel<<<grid, 128, 0, st>>>(a);
+  if (f16) spconv16_warp_kernel<true><<<grid, 128, 0, st>>>(a);
+  else spconv16_warp_kernel<false><<<grid, 128, 0, st>>>(a);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }

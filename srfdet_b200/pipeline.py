@@ -24,6 +24,7 @@ from .plugin import (DynamicConv, SingleRoIExtractor, SRFDetPointPath, img_feats
                      points_feats_sampling_bboxes_roi)
 from .plugin import head as _head
 from .plugin import registry
+from . import _lib as _L
 
 MODEL_CFG = {
     # configs/nus/srfdet_voxel_nusc_L.py:34-50 (+ LC variant :40-84 for the image branch)
@@ -153,12 +154,13 @@ class RegionFeaturePipeline:
                 if not torch.cuda.is_current_stream_capturing():
                     params.record_stream(main)
             boxes = self.stage_boxes[s]                  # static inputs: sampled with mutate=False (no in-place de-normalisation)
+            enc = registry.act_enc(self.precision)
             if self.fusion and self.channels_last:
                 # both samplers fill their half of the concatenated fusion input
                 # (cat(img, pts), srfdet_head.py:2257) directly, in the GEMM's dtype, concurrently.
                 # The image sampler reads the still-normalised stage boxes, the BEV one its clone.
-                cat = torch.empty((N_PROP, 49, 2 * self.C), device=self.device,
-                                  dtype=torch.bfloat16 if self.precision == 'bf16' else torch.float32)
+                cenc = _L.F32 if enc is None else enc
+                cat = torch.empty((N_PROP, 49, _L.enc_width(cenc, 2 * self.C)), device=self.device, dtype=_L.enc_torch_dtype(cenc))
                 fork = main is not None and self.overlap_stage
                 if fork:
                     if self._aux2 is None:
@@ -166,27 +168,27 @@ class RegionFeaturePipeline:
                     self._aux2.wait_event(main.record_event())
                 with (torch.cuda.stream(self._aux2) if fork else contextlib.nullcontext()):
                     img_feats_sampling_bboxes_roi(self.img_feats, self.stage_boxes[s], self.pooler_img, self.lidar2img,
-                                                  self.pc_range, channel_last=True, out=cat, ch_offset=0)
+                                                  self.pc_range, channel_last=True, out=cat, ch_offset=0, out_enc=cenc)
                     if fork:
                         ev_img = self._aux2.record_event()
                 points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
-                                                 channel_last=True, out=cat, ch_offset=self.C, mutate=False)
+                                                 channel_last=True, out=cat, ch_offset=self.C, mutate=False, out_enc=cenc)
                 if fork:
                     main.wait_event(ev_img)
-                roi = _head._linear(cat.view(N_PROP * 49, 2 * self.C), self.fuse[s], self.precision, self._fuse_cache[s],
-                                    'fuse').view(N_PROP, 49, self.C)
+                roi = _head._linear(cat.view(N_PROP * 49, -1), self.fuse[s], self.precision, self._fuse_cache[s],
+                                    'fuse').view(N_PROP, 49, -1)
             elif self.fusion:
                 img_roi = img_feats_sampling_bboxes_roi(self.img_feats, boxes, self.pooler_img, self.lidar2img, self.pc_range,
                                                         channel_last=True)
                 pts_roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
                                                            channel_last=True, mutate=False)
                 cat = torch.cat((img_roi, pts_roi), dim=2).view(N_PROP * 49, 2 * self.C)
-                roi = _head._linear(cat, self.fuse[s], self.precision, self._fuse_cache[s], 'fuse').view(N_PROP, 49, self.C)
-            elif self.channels_last and self.precision == 'bf16':
-                # the interaction MMA consumes bf16 operands: the sampler rounds once, on store
-                roi = torch.empty((N_PROP, 49, self.C), dtype=torch.bfloat16, device=self.device)
+                roi = _head._linear(cat, self.fuse[s], self.precision, self._fuse_cache[s], 'fuse').view(N_PROP, 49, -1)
+            elif self.channels_last and enc is not None:
+                # the interaction MMA consumes 16-bit (or hi + lo) operands: the sampler encodes once, on store
+                roi = torch.empty((N_PROP, 49, _L.enc_width(enc, self.C)), dtype=_L.enc_torch_dtype(enc), device=self.device)
                 points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
-                                                 channel_last=True, out=roi, mutate=False)
+                                                 channel_last=True, out=roi, mutate=False, out_enc=enc)
             else:
                 roi = points_feats_sampling_bboxes_roi(self.bev_feats, boxes, self.pooler, self.pc_range, self.voxel_size,
                                                        channel_last=True, mutate=False)

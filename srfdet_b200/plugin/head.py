@@ -22,59 +22,106 @@ from .roi import img_feats_sampling_bboxes_roi, maps_channels_last, points_feats
 _DEFAULT_SCALE_CLAMP = math.log(100000.0 / 16)
 
 
-def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_bf16=None):
-    """x (M,K) f32|bf16 -> (M,N).  fp32: SIMT FFMA.  bf16: tcgen05 GEMM (weights packed once)."""
-    lib = L.load()
+def _f(t):
+    return t.detach().float().contiguous()
+
+
+def _cached(cache, key, src, make):
+    """Packed / folded form of `src` tensors, rebuilt when any of them was replaced or written
+    in place (load_state_dict at any level of the module tree, optimizer step, manual edit)."""
+    ver = tuple((t.data_ptr(), t._version) for t in src)
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, make())
+        cache[key] = hit
+    return hit[1]
+
+
+def _encode_out(x, enc):
+    return x if enc == L.F32 else encode_rows(x, enc)
+
+
+def encode_rows(x, enc):
+    """(M,K) fp32 -> (M, K | 2K) tensor in the 16-bit encoding `enc` (srf_convert_rows)."""
     m, k = x.shape
-    n = lin.out_features
+    out = torch.empty((m, L.enc_width(enc, k)), dtype=L.enc_torch_dtype(enc), device=x.device)
+    L.check(L.load().srf_convert_rows(L.ptr(_f(x)), m, k, k, enc, L.ptr(out), L.stream_ptr()), 'srf_convert_rows')
+    return out
+
+
+def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None):
+    """nn.Linear (+LayerNorm +ReLU) on the library's GEMMs.
+
+    x: (M,K) fp32, or an (M, K|2K) tensor already in the activation encoding of `precision`.
+    'fp32_simt': FFMA kernel, fp32 in/out.  Tensor-core modes: tcgen05 GEMM on operands in the
+    mode's encoding (weights packed once, re-packed when they change); the result is written in
+    `out_enc` (default: the mode's activation encoding; L.F32 for an fp32 result)."""
+    lib = L.load()
+    m = x.shape[0]
+    k, n = lin.in_features, lin.out_features
     dev = x.device
     st = L.stream_ptr()
-    bias = lin.bias.detach().float().contiguous() if lin.bias is not None else None
-    if precision == 'fp32':
-        x = x.float().contiguous()
-        w = lin.weight.detach().float().contiguous()
+    bias = _f(lin.bias) if lin.bias is not None else None
+    enc = registry.act_enc(precision)
+    if enc is not None:
+        # shapes the tcgen05 tiles cannot cover (not multiples of 16, or of the tile above it) take the FFMA kernel
+        tk = lib.srf_linear_tile_k_enc(k, enc)
+        if k % 16 or n % 16 or k % tk or (n > 128 and n % 128) or (ln is not None and n > 1024):
+            out = _linear(L.decode(x, k) if x.dtype != torch.float32 else x, lin, 'fp32_simt', cache, key, relu, ln)
+            return _encode_out(out, enc if out_enc is None else out_enc)
+    if enc is None:
+        x = _f(x)
+        w = _f(lin.weight)
         out = torch.empty((m, n), dtype=torch.float32, device=dev)
         fuse_relu = relu and ln is None
         L.check(lib.srf_linear_f32(L.ptr(x), m, k, L.ptr(w), n, L.ptr(bias), int(fuse_relu), L.ptr(out), st), 'srf_linear_f32')
         if ln is not None:
-            L.check(lib.srf_layernorm(L.ptr(out), L.F32, m, n, 1, None, L.ptr(ln.weight.detach().float().contiguous()),
-                                      L.ptr(ln.bias.detach().float().contiguous()), ln.eps, int(relu), L.ptr(out), st),
-                    'srf_layernorm')
+            L.check(lib.srf_layernorm(L.ptr(out), L.F32, m, n, 1, None, L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)), ln.eps,
+                                      int(relu), L.ptr(out), st), 'srf_layernorm')
         return out
-    if x.dtype != torch.bfloat16:
-        xb = torch.empty((m, k), dtype=torch.bfloat16, device=dev)
-        L.check(lib.srf_f32_to_bf16(L.ptr(x.float().contiguous()), m, k, k, L.ptr(xb), st), 'srf_f32_to_bf16')
-        x = xb
-    if key not in cache:
-        wp = torch.empty((n * k,), dtype=torch.bfloat16, device=dev)
-        L.check(lib.srf_pack_linear_bf16(L.ptr(lin.weight.detach().float().contiguous()), n, k, L.ptr(wp), st),
-                'srf_pack_linear_bf16')
-        cache[key] = wp
-    out_bf16 = True if out_bf16 is None else out_bf16
+    if x.dtype == torch.float32:
+        x = encode_rows(x, enc)
+    assert x.dtype == L.enc_torch_dtype(enc) and x.shape[1] == L.enc_width(enc, k), 'operand is not in the mode\'s encoding'
+    x = x.contiguous()
+
+    def pack():
+        wp = torch.empty((L.enc_width(enc, n * k),), dtype=L.enc_torch_dtype(enc), device=dev)
+        L.check(lib.srf_pack_linear_tc(L.ptr(_f(lin.weight)), n, k, enc, L.ptr(wp), st), 'srf_pack_linear_tc')
+        return wp
+    wp = _cached(cache, (key, enc), (lin.weight,), pack)
+    out_enc = enc if out_enc is None else out_enc
+    eps = float(ln.eps) if ln is not None else 1e-5
+
+    def alloc(e):
+        return torch.empty((m, L.enc_width(e, n)), dtype=L.enc_torch_dtype(e), device=dev)
     # few output tiles but a long reduction (DynamicConv.out_layer: 900 x 6272 -> 128): split K
-    # over CTAs, fp32 partials meet in a zeroed buffer, bias + LayerNorm + ReLU in one pass after
+    # over CTAs, fp32 partials in per-split slabs, bias + LayerNorm + ReLU in one pass after
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
-    kvol = k // min(k, 128)
+    kvol = k // lib.srf_linear_tile_k_enc(k, enc)
     if ln is not None and tiles * 4 <= 148 and kvol >= 8:
-        splits = lib.srf_linear_splits(k, min(kvol, max(1, 148 // tiles)))
+        splits = lib.srf_linear_splits_enc(k, enc, min(kvol, max(1, 148 // tiles)))
         part = torch.empty((splits, m, n), dtype=torch.float32, device=dev)
-        L.check(lib.srf_linear_bf16(L.ptr(x.contiguous()), m, k, L.ptr(cache[key]), n, None, 0, None, None, L.ptr(part), L.F32,
-                                    splits, st), 'srf_linear_bf16')
-        acc = torch.empty((m, n), dtype=torch.float32, device=dev)
-        L.check(lib.srf_layernorm(L.ptr(part), L.F32, m, n, splits, L.ptr(bias), L.ptr(ln.weight.detach().float().contiguous()),
-                                  L.ptr(ln.bias.detach().float().contiguous()), ln.eps, int(relu), L.ptr(acc), st), 'srf_layernorm')
-        return acc.to(torch.bfloat16) if out_bf16 else acc
-    out = torch.empty((m, n), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, None, 0, None, None, eps, L.ptr(part), L.F32, splits, st),
+                'srf_linear_tc')
+        out = alloc(out_enc)
+        L.check(lib.srf_layernorm_enc(L.ptr(part), L.F32, m, n, splits, L.ptr(bias), L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)),
+                                      eps, int(relu), L.ptr(out), out_enc, st), 'srf_layernorm')
+        return out
     fuse_ln = ln is not None and n <= 128
     epi = (1 if relu and (ln is None or fuse_ln) else 0) | (2 if fuse_ln else 0)
-    lnw = ln.weight.detach().float().contiguous() if fuse_ln else None
-    lnb = ln.bias.detach().float().contiguous() if fuse_ln else None
-    L.check(lib.srf_linear_bf16(L.ptr(x.contiguous()), m, k, L.ptr(cache[key]), n, L.ptr(bias), epi, L.ptr(lnw), L.ptr(lnb),
-                                L.ptr(out), L.BF16 if out_bf16 else L.F32, 1, st), 'srf_linear_bf16')
+    lnw = _f(ln.weight) if fuse_ln else None
+    lnb = _f(ln.bias) if fuse_ln else None
     if ln is not None and not fuse_ln:
-        L.check(lib.srf_layernorm(L.ptr(out), L.BF16 if out_bf16 else L.F32, m, n, 1, None,
-                                  L.ptr(ln.weight.detach().float().contiguous()), L.ptr(ln.bias.detach().float().contiguous()),
-                                  ln.eps, int(relu), L.ptr(out), st), 'srf_layernorm')
+        tmp = alloc(L.F32)
+        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), 0, None, None, eps, L.ptr(tmp), L.F32, 1, st),
+                'srf_linear_tc')
+        out = alloc(out_enc)
+        L.check(lib.srf_layernorm_enc(L.ptr(tmp), L.F32, m, n, 1, None, L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)), eps, int(relu),
+                                      L.ptr(out), out_enc, st), 'srf_layernorm')
+        return out
+    out = alloc(out_enc)
+    L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), epi, L.ptr(lnw), L.ptr(lnb), eps, L.ptr(out), out_enc,
+                              1, st), 'srf_linear_tc')
     return out
 
 
@@ -94,35 +141,38 @@ class DynamicConv(nn.Module):
         self.norm3 = nn.LayerNorm(feat_channels)
         self._cache = {}
 
-    def load_state_dict(self, *a, **k):
-        self._cache = {}
-        return super().load_state_dict(*a, **k)
-
     def make_params(self, prop_feats, precision=None):
         """dynamic_layer(prop_feats): (K,C) -> (K, 2*C*d).  Depends only on the proposal features,
-        so callers may run it concurrently with the RoI sampling of the same stage."""
+        so callers may run it concurrently with the RoI sampling of the same stage.  The split
+        ('fp32') mode keeps the generated parameters in fp32 (the interaction kernel splits them)."""
         precision = precision or registry.get_precision()
-        return _linear(prop_feats, self.dynamic_layer, precision, self._cache, ('dyn', str(prop_feats.device)))
+        enc = registry.act_enc(precision)
+        out_enc = L.F32 if (enc is None or L.enc_is_split(enc)) else enc
+        return _linear(prop_feats, self.dynamic_layer, precision, self._cache, ('dyn', str(prop_feats.device)), out_enc=out_enc)
 
     def forward_kc(self, prop_feats, roi_feats, precision=None, params=None):
-        """prop_feats (K,C); roi_feats (K,49,C) f32|bf16 (channel-last RoI features) -> (K,C) f32."""
+        """prop_feats (K,C) f32; roi_feats (K,49,C) f32 or (K,49,C|2C) in the mode's encoding
+        (channel-last RoI features) -> (K,C) f32."""
         precision = precision or registry.get_precision()
         lib = L.load()
         k, c = prop_feats.shape
         d = self.dynamic_dim
         dev = prop_feats.device
-        bf = precision == 'bf16'
+        enc = registry.act_enc(precision)
         if params is None:
             params = self.make_params(prop_feats, precision)
         roi_feats = roi_feats.contiguous()
-        inter = torch.empty((k, 49 * c), dtype=torch.bfloat16 if bf else torch.float32, device=dev)
-        f = lambda t: L.ptr(t.detach().float().contiguous())
-        L.check(lib.srf_dynconv_interact(L.ptr(roi_feats), L.BF16 if roi_feats.dtype == torch.bfloat16 else L.F32,
-                                         L.ptr(params), L.BF16 if bf else L.F32, k, c, d, f(self.norm1.weight),
-                                         f(self.norm1.bias), f(self.norm2.weight), f(self.norm2.bias), L.ptr(inter),
-                                         L.BF16 if bf else L.F32, L.stream_ptr()), 'srf_dynconv_interact')
-        out = _linear(inter, self.out_layer, precision, self._cache, ('out', str(dev)), relu=True, ln=self.norm3,
-                      out_bf16=False)
+        if enc is not None and (c, d) not in ((128, 32), (256, 64)):
+            # dims without a tensor-core interaction kernel: FFMA kernel on fp32 buffers
+            roi_feats, params, enc = L.decode(roi_feats, c).contiguous(), L.decode(params, 2 * c * d).contiguous(), None
+        out_enc = L.F32 if enc is None else enc
+        inter = torch.empty((k, L.enc_width(out_enc, 49 * c)), dtype=L.enc_torch_dtype(out_enc), device=dev)
+        L.check(lib.srf_dynconv_interact_tc(L.ptr(roi_feats), L.enc_of_tensor(roi_feats, c), L.ptr(params),
+                                            L.enc_of_tensor(params, 2 * c * d), k, c, d, L.ptr(_f(self.norm1.weight)),
+                                            L.ptr(_f(self.norm1.bias)), self.norm1.eps, L.ptr(_f(self.norm2.weight)),
+                                            L.ptr(_f(self.norm2.bias)), self.norm2.eps, L.ptr(inter), out_enc, L.stream_ptr()),
+                'srf_dynconv_interact')
+        out = _linear(inter, self.out_layer, precision, self._cache, ('out', str(dev)), relu=True, ln=self.norm3, out_enc=L.F32)
         return out.float()
 
     def forward(self, prop_feats, roi_feats):
@@ -248,10 +298,6 @@ class SingleSRFDetHead(_SingleHeadBase):
             self.output_fused_proj = nn.Linear(2 * feat_channels, feat_channels)
         self._cache = {}
 
-    def load_state_dict(self, *a, **k):
-        self._cache = {}
-        return super().load_state_dict(*a, **k)
-
     def region_features(self, img_feats, point_feats, bboxes, pooler, pooler_img, lidar2img, precision=None):
         """Fused RoI features (bs*n_p, 49, C) channel-last: image RoIs (camera sum), BEV RoIs,
         concat + Linear(2C->C) (srfdet_head.py:2236-2264)."""
@@ -262,13 +308,14 @@ class SingleSRFDetHead(_SingleHeadBase):
                 and maps_channels_last(point_feats, pooler.num_inputs)):
             # both samplers write their half of cat(img, pts) (srfdet_head.py:2257) in the GEMM's dtype
             k, c = bboxes.shape[0] * bboxes.shape[1], point_feats[0].shape[1]
-            cat = torch.empty((k, 49, 2 * c), device=bboxes.device,
-                              dtype=torch.bfloat16 if precision == 'bf16' else torch.float32)
+            enc = registry.act_enc(precision)
+            enc = L.F32 if enc is None else enc
+            cat = torch.empty((k, 49, L.enc_width(enc, 2 * c)), device=bboxes.device, dtype=L.enc_torch_dtype(enc))
             img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler_img, lidar2img, self.pc_range_lidar,
-                                          channel_last=True, out=cat, ch_offset=0)
+                                          channel_last=True, out=cat, ch_offset=0, out_enc=enc)
             points_feats_sampling_bboxes_roi(point_feats, bboxes, pooler, self.pc_range_lidar, self.voxel_size_lidar,
-                                             channel_last=True, out=cat, ch_offset=c)
-            fused = _linear(cat.view(k * 49, 2 * c), self.output_fused_proj, precision, self._cache, ('fuse', str(cat.device)))
+                                             channel_last=True, out=cat, ch_offset=c, out_enc=enc)
+            fused = _linear(cat.view(k * 49, -1), self.output_fused_proj, precision, self._cache, ('fuse', str(cat.device)))
             return fused.view(k, 49, -1)
         if img_feats is not None:
             img_roi = img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler_img, lidar2img, self.pc_range_lidar,
@@ -296,5 +343,5 @@ class SingleSRFDetHead(_SingleHeadBase):
                                         device=bboxes.device)
         roi = self.region_features(img_feats, point_feats, bboxes, pooler, pooler_img, lidar2img, precision)
         if prop_feats is None:
-            prop_feats = roi.float().mean(1).view(bs, n_p, -1)
+            prop_feats = L.decode(roi, self.feat_channels).mean(1).view(bs, n_p, -1)
         return self._stage_tail(roi, bboxes, prop_feats, bs, n_p, precision)

@@ -4,18 +4,42 @@ same registry names without mmcv (plugin mechanism: tools/test.py:136-157,
 mmdet3d_plugin/__init__.py:1-15)."""
 import os
 
-PRECISION = os.environ.get('SRFDET_B200_PRECISION', 'bf16')
+# Precision modes of the feature path (integer outputs -- coordinates, voxel order, rulebooks --
+# are bit-exact in every mode):
+#   'fp16'      f16 operands / activations, fp32 accumulate on tcgen05 (the reference's own half
+#               precision: sparse_encoder_custom.py:109 auto_fp16).  Tolerance 1e-2 (measured ~3e-3).
+#   'fp32'      the reference's precision (srfdet.py:204-206 force_fp32) on tensor cores: every
+#               operand is a hi + lo pair of 16-bit values, three MMAs per product (tolerance 1e-4).
+#   'bf16'      bf16 operands / activations.  Cheapest range-safe mode; 2e-2 at the full 300k-point frame.
+#   'fp32_simt' fp32 FFMA kernels (bit-level cross-check of the tensor-core modes; slow).
+PRECISIONS = ('fp16', 'fp32', 'bf16', 'fp32_simt')
+PRECISION = os.environ.get('SRFDET_B200_PRECISION', 'fp16')
+# element format of the split ('fp32') mode: 'bf16' (hi + lo = 16 significand bits, fp32 range)
+# or 'f16' (22 bits, range +-65504)
+SPLIT_FORMAT = os.environ.get('SRFDET_B200_SPLIT', 'bf16')
 
 
 def set_precision(p):
-    """'bf16' (tcgen05 tensor-core path, tol 1e-2) or 'fp32' (SIMT exact path, tol 1e-4)."""
     global PRECISION
-    assert p in ('bf16', 'fp32')
+    assert p in PRECISIONS, p
     PRECISION = p
 
 
 def get_precision():
     return PRECISION
+
+
+def act_enc(precision):
+    """Activation encoding (include/srfdet_b200.h SRF_*) of a precision mode; None for 'fp32_simt'."""
+    from .. import _lib as L
+    assert precision in PRECISIONS, precision
+    if precision == 'fp16':
+        return L.F16
+    if precision == 'bf16':
+        return L.BF16
+    if precision == 'fp32':
+        return L.F16X2 if SPLIT_FORMAT == 'f16' else L.BF16X2
+    return None
 
 
 class Registry:

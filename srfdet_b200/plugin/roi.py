@@ -99,21 +99,24 @@ class SingleRoIExtractor(nn.Module):
         return out
 
 
-def _roi_out(k, c, channel_last, device, out=None, ch_offset=0):
+def _roi_out(k, c, channel_last, device, out=None, ch_offset=0, out_enc=None):
     """Destination spec: a fresh (k,C,7,7) / (k,49,C) fp32 tensor, or a caller-provided
-    channel-last (k,49,C') fp32|bf16 buffer filled at channel offset `ch_offset`."""
+    channel-last (k,49,C') buffer in encoding `out_enc` (fp32, bf16, f16, or a split form whose rows
+    are [hi(C'/2) | lo(C'/2)]) filled at channel offset `ch_offset`."""
     if out is None:
         out = torch.empty((k, 49, c) if channel_last else (k, c, 7, 7), dtype=torch.float32, device=device)
         spec = L.RoiOut(out.data_ptr(), int(channel_last), L.F32, c, 0)
     else:
         assert out.is_contiguous() and out.dim() == 3 and out.shape[0] == k and out.shape[1] == 49
-        assert out.dtype in (torch.float32, torch.bfloat16)
-        spec = L.RoiOut(out.data_ptr(), 1, L.BF16 if out.dtype == torch.bfloat16 else L.F32, out.shape[2], int(ch_offset))
+        if out_enc is None:
+            out_enc = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}[out.dtype]
+        assert out.dtype == L.enc_torch_dtype(out_enc)
+        spec = L.RoiOut(out.data_ptr(), 1, out_enc, out.shape[2], int(ch_offset))
     return out, spec
 
 
 def points_feats_sampling_bboxes_roi(points_feats, bboxes, pooler, pc_range, voxel_size, channel_last=False,
-                                     return_rois=False, out=None, ch_offset=0, mutate=True):
+                                     return_rois=False, out=None, ch_offset=0, mutate=True, out_enc=None):
     """Fused srfdet_head.py:2568-2629.  bboxes (bs, n_p, >=8) normalised centres; the
     centres are de-normalised IN PLACE like the reference (:2587) unless mutate=False.
     -> (bs*n_p, C, 7, 7) (or channel-last (bs*n_p, 49, C); `out`/`ch_offset`: write into a slice
@@ -123,7 +126,7 @@ def points_feats_sampling_bboxes_roi(points_feats, bboxes, pooler, pc_range, vox
     p, keep = _pyramid(points_feats, pooler.featmap_strides, pooler.num_inputs)
     c = p.channels
     k = bs * n_p
-    out, spec = _roi_out(k, c, channel_last, bboxes.device, out, ch_offset)
+    out, spec = _roi_out(k, c, channel_last, bboxes.device, out, ch_offset, out_enc)
     rois = torch.empty((k, 5), dtype=torch.float32, device=bboxes.device) if return_rois else None
     L.check(L.load().srf_bev_roi_features(ctypes.byref(p), L.ptr(bboxes), bs, n_p, d, L.f6(pc_range), L.f3(voxel_size), int(bool(mutate)),
                                           ctypes.byref(spec), L.ptr(rois), L.stream_ptr()), 'srf_bev_roi_features')
@@ -131,7 +134,7 @@ def points_feats_sampling_bboxes_roi(points_feats, bboxes, pooler, pc_range, vox
 
 
 def img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler, lidar2img, pc_range, channel_last=False,
-                                  return_rois=False, out=None, ch_offset=0):
+                                  return_rois=False, out=None, ch_offset=0, out_enc=None):
     """Fused srfdet_head.py:2424-2565 (B = 1 semantics).  img_feats: list of
     (1, n_cam, C, H, W); bboxes (1, n_p, >=8) (not mutated); lidar2img (n_cam,4,4) tensor."""
     assert bboxes.shape[0] == 1 and img_feats[0].shape[0] == 1, 'image branch is built for batch size 1 (as the reference is)'
@@ -142,7 +145,7 @@ def img_feats_sampling_bboxes_roi(img_feats, bboxes, pooler, lidar2img, pc_range
     n_cam = flat[0].shape[0]
     l2i = lidar2img.reshape(n_cam, 4, 4).contiguous().float()
     c = p.channels
-    out, spec = _roi_out(n_p, c, channel_last, b.device, out, ch_offset)
+    out, spec = _roi_out(n_p, c, channel_last, b.device, out, ch_offset, out_enc)
     rois = torch.empty((n_cam * n_p, 5), dtype=torch.float32, device=b.device) if return_rois else None
     L.check(L.load().srf_img_roi_features(ctypes.byref(p), L.ptr(b), n_p, d, L.ptr(l2i), n_cam, L.f6(pc_range),
                                           ctypes.byref(spec), L.ptr(rois), L.stream_ptr()), 'srf_img_roi_features')

@@ -81,6 +81,10 @@ class SparseBasicBlock(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
 
+# (cin, cout) pairs instantiated by the tcgen05 sparse kernel (csrc/igemm_umma.cu dispatch_sparse)
+_TC_PAIRS = {(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128), (128, 64), (64, 32), (32, 16)}
+
+
 class _Level:
     __slots__ = ('dims', 'ncells', 'cap', 'index', 'coors', 'count', 'nbr', 'mask', 'ready')
 
@@ -153,31 +157,35 @@ class SparseEncoderCustom(nn.Module):
         plan.append((self.conv_out[0], self.conv_out[1], False, False))
         return plan
 
-    def load_state_dict(self, *a, **k):
-        self._packed = {}
-        return super().load_state_dict(*a, **k)
+    def _weights_version(self):
+        """Changes whenever a conv weight or a BatchNorm tensor is replaced or modified in place
+        (load_state_dict at any level of the module tree, optimizer steps, manual edits)."""
+        return tuple((t.data_ptr(), t._version) for conv, bn, _, _ in self.layer_plan()
+                     for t in (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var))
 
     def _pack(self, device, precision):
         key = (str(device), precision)
-        if key in self._packed:
-            return self._packed[key]
+        ver = self._weights_version()
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
         lib = L.load()
+        enc = registry.act_enc(precision)
         packed = []
         for li, (conv, bn, _, _) in enumerate(self.layer_plan()):
             w = conv.kio().to(device)
             s = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).to(device)
             bias = (bn.bias.detach().float().to(device) - bn.running_mean.detach().float().to(device) * s).contiguous()
             w = (w * s.view(1, 1, -1)).contiguous()
-            # layer 0 reads the raw fp32 voxel features (few channels): SIMT path, bf16 output
-            use_umma = precision == 'bf16' and li > 0 and conv.in_channels in (16, 32, 64, 128) \
-                and conv.out_channels in (16, 32, 64, 128)
+            # layer 0 reads the raw fp32 voxel features (few channels): SIMT kernel, encoded output
+            use_umma = enc is not None and li > 0 and (conv.in_channels, conv.out_channels) in _TC_PAIRS
             if use_umma:
-                wp = torch.empty(w.numel(), dtype=torch.bfloat16, device=device)
-                L.check(lib.srf_pack_weight_bf16(L.ptr(w), w.shape[0], w.shape[1], w.shape[2], L.ptr(wp),
-                                                 L.stream_ptr()), 'srf_pack_weight_bf16')
+                wp = torch.empty(L.enc_width(enc, w.numel()), dtype=L.enc_torch_dtype(enc), device=device)
+                L.check(lib.srf_pack_weight_tc(L.ptr(w), w.shape[0], w.shape[1], w.shape[2], enc, L.ptr(wp),
+                                               L.stream_ptr()), 'srf_pack_weight_tc')
                 w = wp
             packed.append(dict(w=w, bias=bias, umma=use_umma))
-        self._packed[key] = packed
+        self._packed[key] = (ver, packed)
         return packed
 
     def _side_stream(self, dev):
@@ -243,8 +251,9 @@ class SparseEncoderCustom(nn.Module):
         L.check(lib.srf_gather_rows(L.ptr(feats_in), L.ptr(perm), L.ptr(lv.count), lv.cap, self.in_channels, L.ptr(x), st),
                 'srf_gather_rows')
         x_dtype = L.F32
-        act_dtype = L.BF16 if precision == 'bf16' else L.F32
-        act_torch = torch.bfloat16 if precision == 'bf16' else torch.float32
+        enc = registry.act_enc(precision)
+        act_dtype = L.F32 if enc is None else enc
+        act_torch = L.enc_torch_dtype(act_dtype)
         levels = [lv]
         identity = None
         dense = None
@@ -335,21 +344,22 @@ class SparseEncoderCustom(nn.Module):
                 a.out = None
                 y = None
             else:
-                y = torch.empty((lv_out.cap, conv.out_channels), dtype=act_torch, device=dev)
+                y = torch.empty((lv_out.cap, L.enc_width(act_dtype, conv.out_channels)), dtype=act_torch, device=dev)
                 a.out = L.ptr(y)
             if self.profile is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
             if pk['umma']:
-                assert x_dtype == L.BF16
-                L.check(lib.srf_spconv_bf16(ctypes.byref(a), st), 'srf_spconv_bf16')
+                assert x_dtype == act_dtype
+                L.check(lib.srf_spconv_tc(ctypes.byref(a), st), 'srf_spconv_tc')
             else:
                 L.check(lib.srf_spconv_f32(ctypes.byref(a), st), 'srf_spconv_f32')
             if self.profile is not None:
                 ev1.record()
                 self.profile.append(dict(layer=li, subm=conv.subm, cin=conv.in_channels, cout=conv.out_channels, kvol=a.kvol,
                                          umma=pk['umma'], nbr=nbr, n_in=lv.count, n_out=lv_out.count, start=ev0, end=ev1,
-                                         in_bytes=2 if x_dtype == L.BF16 else 4, out_bytes=4 if last else (2 if act_dtype == L.BF16 else 4)))
+                                         in_bytes=2 if x_dtype in (L.BF16, L.F16) else 4,
+                                         out_bytes=4 if last else (2 if act_dtype in (L.BF16, L.F16) else 4)))
             x, x_dtype, lv = y, act_dtype, lv_out
         self.last_counts = [l.count for l in levels]
         if return_levels:

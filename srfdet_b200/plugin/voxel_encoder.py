@@ -94,21 +94,20 @@ class DynamicVFECustom(nn.Module):
                                                nn.Linear(d, d, bias=False), nn.BatchNorm1d(d), nn.Tanh())
         self._packed = None
 
-    def _invalidate(self, *a, **k):
-        self._packed = None
-
-    def load_state_dict(self, *a, **k):
-        self._packed = None
-        return super().load_state_dict(*a, **k)
+    def _weights_version(self):
+        """(data_ptr, version) of every parameter / buffer: changes on load_state_dict at any level
+        of the module tree and on in-place updates."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _pack(self, device):
-        if self._packed is not None and self._packed['dev'] == device:
+        ver = self._weights_version()
+        if self._packed is not None and self._packed['dev'] == device and self._packed['ver'] == ver:
             return self._packed
         enc = self.cen2point_pos_enc
         w0, b0 = fold_bn(enc[0].weight, enc[1])
         w1, b1 = fold_bn(enc[3].weight, enc[4])
         v0w, v0b = fold_bn(self.vfe_layers[0].linear.weight, self.vfe_layers[0].norm)
-        t = dict(dev=device, w0=w0, b0=b0, w1=w1, b1=b1, v0w=v0w, v0b=v0b, v1w=None, v1b=None)
+        t = dict(dev=device, ver=ver, w0=w0, b0=b0, w1=w1, b1=b1, v0w=v0w, v0b=v0b, v1w=None, v1b=None)
         if self.num_vfe == 2:
             t['v1w'], t['v1b'] = fold_bn(self.vfe_layers[1].linear.weight, self.vfe_layers[1].norm)
         for k, v in list(t.items()):

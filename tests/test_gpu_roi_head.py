@@ -118,11 +118,15 @@ def test_channels_last_maps_match_nchw(C):
         assert rel_err(r1.cpu().numpy(), r0.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-def test_samplers_fill_concatenated_buffer(dtype):
+@pytest.mark.parametrize('enc_name', ['f32', 'bf16', 'f16', 'bf16x2', 'f16x2'])
+def test_samplers_fill_concatenated_buffer(enc_name):
     """out= / ch_offset=: image and BEV samplers write the two halves of cat(img, pts)
-    (srfdet_head.py:2257) into one channel-last buffer, fp32 exact / bf16 rounded."""
+    (srfdet_head.py:2257) into one channel-last buffer: fp32 exact, 16-bit rounded, or hi + lo split
+    rows [hi(2C) | lo(2C)] whose sum reproduces the fp32 value to the format's 2x precision."""
+    from srfdet_b200 import _lib as L
     from srfdet_b200.plugin import img_feats_sampling_bboxes_roi, points_feats_sampling_bboxes_roi
+    enc = {'f32': L.F32, 'bf16': L.BF16, 'f16': L.F16, 'bf16x2': L.BF16X2, 'f16x2': L.F16X2}[enc_name]
+    dtype = L.enc_torch_dtype(enc)
     C = 128
     cl = lambda t: t.contiguous(memory_format=torch.channels_last)
     feats = [cl(cuda(f)) for f in synth.feature_pyramid(7, C, (184, 184), 4, lead=(1,))]
@@ -133,14 +137,19 @@ def test_samplers_fill_concatenated_buffer(dtype):
     img = img_feats_sampling_bboxes_roi(ifeats, cuda(boxes.copy()), pooli, l2i, PC, channel_last=True)
     pts = points_feats_sampling_bboxes_roi(feats, cuda(boxes.copy()), pool, PC, VS, channel_last=True)
     ref = torch.cat((img, pts), dim=2)
-    cat = torch.full((300, 49, 2 * C), float('nan'), dtype=dtype, device='cuda')
-    r = img_feats_sampling_bboxes_roi(ifeats, cuda(boxes.copy()), pooli, l2i, PC, channel_last=True, out=cat, ch_offset=0)
+    cat = torch.full((300, 49, L.enc_width(enc, 2 * C)), float('nan'), dtype=dtype, device='cuda')
+    r = img_feats_sampling_bboxes_roi(ifeats, cuda(boxes.copy()), pooli, l2i, PC, channel_last=True, out=cat, ch_offset=0, out_enc=enc)
     assert r.data_ptr() == cat.data_ptr()
-    points_feats_sampling_bboxes_roi(feats, cuda(boxes.copy()), pool, PC, VS, channel_last=True, out=cat, ch_offset=C)
-    if dtype == torch.float32:
+    points_feats_sampling_bboxes_roi(feats, cuda(boxes.copy()), pool, PC, VS, channel_last=True, out=cat, ch_offset=C, out_enc=enc)
+    if enc == L.F32:
         assert torch.equal(cat, ref)
+    elif not L.enc_is_split(enc):
+        assert torch.equal(cat, ref.to(dtype))
     else:
-        assert torch.equal(cat, ref.to(torch.bfloat16))
+        hi, lo = cat[..., :2 * C], cat[..., 2 * C:]
+        assert torch.equal(hi, ref.to(dtype))
+        assert torch.equal(lo, (ref - hi.float()).to(dtype))
+        assert rel_err(L.decode(cat, 2 * C).cpu().numpy(), ref.cpu().numpy()) < (2e-5 if enc == L.BF16X2 else 1e-6)
     # NCHW maps cannot take the strided form: loud error, no silent fallback
     with pytest.raises(RuntimeError):
         points_feats_sampling_bboxes_roi([f.contiguous() for f in feats], cuda(boxes.copy()), pool, PC, VS,
@@ -185,17 +194,19 @@ def test_dynconv_golden_fp32(golden_dir):
     dc = DynamicConv(c, d).eval()
     dc.load_state_dict({k: torch.as_tensor(v) for k, v in _dc_params(z).items()})
     dc = dc.cuda()
-    from srfdet_b200.plugin import set_precision
-    set_precision('fp32')
-    try:
-        out = dc(cuda(z['prop']), cuda(z['roi']))
-    finally:
-        set_precision('bf16')
-    assert rel_err(out.cpu().numpy(), z['out']) < 1e-4
+    from srfdet_b200.plugin import registry, set_precision
+    old = registry.get_precision()
+    for mode in ('fp32', 'fp32_simt'):      # golden dims (c, d) are tiny: both modes take the FFMA interaction kernel
+        set_precision(mode)
+        try:
+            out = dc(cuda(z['prop']), cuda(z['roi']))
+        finally:
+            set_precision(old)
+        assert rel_err(out.cpu().numpy(), z['out']) < 1e-4
 
 
 @pytest.mark.parametrize('c,d', [(128, 32), (256, 64)])
-@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 2e-2)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('fp32_simt', 1e-4), ('fp16', 1e-2), ('bf16', 2e-2)])
 def test_dynconv_production_dims_vs_oracle(c, d, precision, tol):
     from srfdet_b200.plugin import DynamicConv
     torch.manual_seed(1)
