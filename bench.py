@@ -221,7 +221,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='nusc_L', choices=sorted(WORKLOADS))
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32', 'bf16', 'fp32_simt'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying a CUDA graph of the frame')
     ap.add_argument('--nchw', action='store_true', help='RoI stage samples contiguous NCHW maps (reference layout) instead of channels_last')
@@ -313,7 +313,7 @@ def main():
     n_pts, c_pts = clouds_np[0].shape
     line = dict(metric='frames/s (voxelize+SparseEncoder+RoI fusion)', value=round(fps, 2), unit='frames/s', n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_dev / args.steps, 4), higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic',
+                scaling='weak', vs_baseline=None, dtype={'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f16x2 (hi+lo split operands, 3 MMAs per product, fp32 accumulate)', 'fp32_simt': 'f32'}[args.precision], data='synthetic',
                 config=dict(workload=args.workload, description=wl['desc'], frames_per_step_per_gpu=1,
                             parallelism=f'{world} independent frame replica(s), no data-path collective',
                             l2='512 MiB flush written between timed steps; 8 distinct clouds cycled',

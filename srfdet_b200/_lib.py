@@ -202,6 +202,22 @@ def f6(v):
 
 
 def make_geom(voxel_size, pc_range):
+    """Host-side srf_geom (same fp32 arithmetic as srf_geom_init: grid = rint((hi - lo) / vs), half
+    to even).  Pure Python on purpose: constructing the drop-in modules must not load the CUDA
+    library (bench.py's reference arm builds the same seeded weights on a host without using it)."""
+    import numpy as np
+    g = Geom()
+    for j in range(3):
+        vs, lo, hi = np.float32(voxel_size[j]), np.float32(pc_range[j]), np.float32(pc_range[3 + j])
+        g.vs[j], g.lo[j], g.hi[j] = float(vs), float(lo), float(hi)
+        g.grid[j] = int(np.rint(np.float32(np.float32(hi - lo) / vs)))
+        if g.grid[j] <= 0:
+            raise SrfError(f'empty grid on axis {j}')
+    return g
+
+
+def make_geom_c(voxel_size, pc_range):
+    """The same through the library's srf_geom_init (parity of the two is tested)."""
     g = Geom()
     check(load().srf_geom_init(ctypes.byref(g), f3(voxel_size), f6(pc_range)), 'srf_geom_init')
     return g

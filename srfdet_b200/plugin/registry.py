@@ -14,9 +14,10 @@ import os
 #   'fp32_simt' fp32 FFMA kernels (bit-level cross-check of the tensor-core modes; slow).
 PRECISIONS = ('fp16', 'fp32', 'bf16', 'fp32_simt')
 PRECISION = os.environ.get('SRFDET_B200_PRECISION', 'fp16')
-# element format of the split ('fp32') mode: 'bf16' (hi + lo = 16 significand bits, fp32 range)
-# or 'f16' (22 bits, range +-65504)
-SPLIT_FORMAT = os.environ.get('SRFDET_B200_SPLIT', 'bf16')
+# element format of the split ('fp32') mode: 'f16' (hi + lo = 22 significand bits, range +-65504;
+# measured 2e-6 .. 1e-5 against the oracle) or 'bf16' (16 bits, fp32 range; measured 5e-5 at 40k points,
+# too close to the 1e-4 bound at the full 300k-point frame to be the default)
+SPLIT_FORMAT = os.environ.get('SRFDET_B200_SPLIT', 'f16')
 
 
 def set_precision(p):

@@ -43,6 +43,10 @@ def test_host_only_entry_points(lib):
     assert list(g.grid) == [1472, 1472, 40]
     g = L.make_geom([0.05, 0.05, 0.1], [0, -40, -3, 70.4, 40, 1])
     assert list(g.grid) == [1408, 1600, 40]
+    for vs, pc in [([0.075, 0.075, 0.2], [-55.2, -55.2, -5.0, 55.2, 55.2, 3.0]), ([0.05, 0.05, 0.1], [0, -40, -3, 70.4, 40, 1]),
+                   ([0.1, 0.1, 0.15], [-76.8, -76.8, -2, 76.8, 76.8, 4]), ([0.3, 0.7, 0.25], [-1.05, 0, 0, 1.05, 4.55, 1.125])]:
+        a, b = L.make_geom(vs, pc), L.make_geom_c(vs, pc)       # host arithmetic == srf_geom_init
+        assert list(a.grid) == list(b.grid) and list(a.vs) == list(b.vs) and list(a.lo) == list(b.lo) and list(a.hi) == list(b.hi)
     assert lib.srf_index_bytes(41 * 1472 * 1472) > 2 * 41 * 1472 * 1472 // 8
     assert lib.srf_hard_voxelize_ws_bytes(300000, 10, 160000) > 0
     assert lib.srf_linear_tile_k(6272) == 128 and lib.srf_linear_tile_n(32) == 32

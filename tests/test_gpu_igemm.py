@@ -17,7 +17,7 @@ def _encs():
 
 # tolerance vs an fp64 matmul of the ROUNDED operands (plain forms: only summation order differs) or of
 # the fp32 operands (split forms: what is left is the 3-term product error, 2^-16 / 2^-21 relative)
-TOL = {'bf16': 2e-3, 'f16': 2e-3, 'bf16x2': 3e-5, 'f16x2': 3e-6}
+TOL = {'bf16': 2e-3, 'f16': 2e-3, 'bf16x2': 3e-5, 'f16x2': 2e-5}      # (f16x2: fp32 accumulation over K = 6272 dominates)
 
 
 def _round(t, name):
