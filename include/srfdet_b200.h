@@ -155,6 +155,25 @@ int srf_dynamic_vfe(const float* points, const int32_t* coors, int32_t n, const 
                     int32_t* d_num_voxels, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------- *
+ * Pillar path (srfdet_pillar_* configs).
+ * srf_pillar_vfe: PillarFeatureNetCustom.forward with its single PFNLayer fused
+ *   (voxel_encoders/pillar_encoder_custom.py:95-161, voxel_encoders/utils.py:109-147):
+ *   voxels (cap, t, c) zero-padded pillars from srf_hard_voxelize, num_points (cap), coors (cap,4)
+ *   (b,z,y,x); decoration (cluster offset, pillar-centre offset, range) -> mask -> Linear (BatchNorm1d
+ *   folded: w_folded (cout, F), b_folded (cout)) -> ReLU -> max | mean over the t slots -> out (cap, cout).
+ *   flags: bit0 with_cluster_center, bit1 with_voxel_center, bit2 with_distance, bit3 legacy, bit4 avg.
+ *   offsets = (vx/2 + x_min, vy/2 + y_min, vz/2 + z_min).  d_n (nullable): device row count.
+ * srf_pillars_scatter: mmdet3d PointPillarsScatter (cfg configs/nus/srfdet_pillar_nusc_L.py:53-54):
+ *   canvas (B, c, ny, nx) f32 (zeroed by the caller; (B, ny, nx, c) in memory when channels_last).
+ * ---------------------------------------------------------------------------------- */
+int srf_pillar_vfe(const float* voxels, const int32_t* num_points, const int32_t* coors, int32_t cap,
+                   const int32_t* d_n, int32_t t, int32_t c, const float* w_folded, const float* b_folded,
+                   int32_t cout, const float voxel_size_host[3], const float offsets_host[3], int32_t flags,
+                   float* out, void* stream);
+int srf_pillars_scatter(const float* feats, const int32_t* coors, int32_t cap, const int32_t* d_n, int32_t c,
+                        int32_t ny, int32_t nx, int32_t channels_last, float* canvas, void* stream);
+
+/* ---------------------------------------------------------------------------------- *
  * Rulebook: replaces spconv get_indice_pairs for SubMConv3d / SparseConv3d
  * (sparse_encoder_custom.py:84-107,165-215).  Output-stationary form:
  *   nbr[k * cap_out + o] = input row feeding output row o through kernel offset k

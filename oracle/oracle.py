@@ -571,3 +571,54 @@ def region_features_lidar(params, point_feats, boxes, prop_feats, pc_range, voxe
     if prop_feats is None:
         prop_feats = roi.reshape(roi.shape[0], roi.shape[1], -1).mean(-1)
     return dynamic_conv(params, prop_feats, roi, dynamic_dim), roi
+
+
+# ----------------------------------------------------------------------------------------
+# Pillar path
+# ----------------------------------------------------------------------------------------
+def pillar_feature_net(params, voxels, num_points, coors, voxel_size, pc_range, legacy=True, with_cluster_center=True,
+                       with_voxel_center=True, with_distance=False, mode='max', eps=1e-3):
+    """PillarFeatureNetCustom.forward (models/voxel_encoders/pillar_encoder_custom.py:95-161) with one
+    PFNLayer (models/voxel_encoders/utils.py:109-147).  voxels (N,T,C) zero padded, coors (N,4) b,z,y,x."""
+    f = torch.as_tensor(np.asarray(voxels, np.float32)).clone()
+    npts = torch.as_tensor(np.asarray(num_points)).to(torch.float32)
+    co = torch.as_tensor(np.asarray(coors)).to(torch.float32)
+    vx, vy, vz = [float(v) for v in voxel_size]
+    xo, yo, zo = vx / 2 + pc_range[0], vy / 2 + pc_range[1], vz / 2 + pc_range[2]
+    ls = [f]
+    if with_cluster_center:                                        # :114-119
+        mean = f[:, :, :3].sum(dim=1, keepdim=True) / npts.view(-1, 1, 1)
+        ls.append(f[:, :, :3] - mean)
+    if with_voxel_center:                                          # :122-144
+        ctr = torch.stack([co[:, 3] * vx + xo, co[:, 2] * vy + yo, co[:, 1] * vz + zo], -1).unsqueeze(1)
+        if legacy:
+            f[:, :, :3] = f[:, :, :3] - ctr                        # in place on the view: raw xyz channels change too
+            ls.append(f[:, :, :3])
+        else:
+            ls.append(f[:, :, :3] - ctr)
+    if with_distance:                                              # :146-148
+        ls.append(torch.norm(f[:, :, :3], 2, 2, keepdim=True))
+    x = torch.cat(ls, dim=-1)
+    t = x.shape[1]
+    mask = (npts.view(-1, 1).int() > torch.arange(t, dtype=torch.int32).view(1, -1)).unsqueeze(-1).to(x.dtype)   # utils.py:46-66
+    x = x * mask
+    w = torch.as_tensor(params['pfn_layers.0.linear.weight'])
+    x = x @ w.t()                                                  # utils.py:125
+    g, b = torch.as_tensor(params['pfn_layers.0.norm.weight']), torch.as_tensor(params['pfn_layers.0.norm.bias'])
+    mu, var = torch.as_tensor(params['pfn_layers.0.norm.running_mean']), torch.as_tensor(params['pfn_layers.0.norm.running_var'])
+    x = F.relu((x - mu) / torch.sqrt(var + eps) * g + b)           # BN1d eval over the channel dim, :126-128
+    if mode == 'max':
+        y = x.max(dim=1)[0]
+    else:
+        y = x.sum(dim=1) / npts.view(-1, 1)
+    return y.numpy()
+
+
+def pillars_scatter(feats, coors, batch_size, ny, nx):
+    """[3P] mmdet3d PointPillarsScatter.forward_batch: canvas[b, :, y*nx + x] = feats."""
+    feats = np.asarray(feats, np.float32)
+    c = feats.shape[1]
+    canvas = np.zeros((batch_size, c, ny * nx), np.float32)
+    coors = np.asarray(coors)
+    canvas[coors[:, 0], :, coors[:, 2] * nx + coors[:, 3]] = feats
+    return canvas.reshape(batch_size, c, ny, nx)

@@ -111,6 +111,9 @@ PROTOTYPES = {
     'srf_dynamic_vfe_ws_bytes': (c_size_t, [c_int64, c_int32]),
     'srf_dynamic_vfe': (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_int32), POINTER(VfeParams), c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'srf_pillar_vfe': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                 POINTER(c_float), POINTER(c_float), c_int32, c_void_p, c_void_p]),
+    'srf_pillars_scatter': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'srf_rulebook_build': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_void_p, c_int32, c_void_p,
                                      POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]),
     'srf_spconv_f32': (c_int32, [POINTER(ConvArgs), c_void_p]),

@@ -604,8 +604,9 @@ static int dispatch_dense(int tk, int tn, const IgemmArgs& a, int host_tiles, cu
   // (split operands use K slices of at most 64 channels: srf_linear_tile_k_enc)
 #define SRF_CASE(ci, co) if constexpr (!(SPLIT && ci > 64)) { if (tk == ci && tn == co) return launch_igemm<ci, co, false, SPLIT>(a, host_tiles, st); }
   SRF_CASE(128, 128) SRF_CASE(64, 128) SRF_CASE(32, 128) SRF_CASE(16, 128)
-  SRF_CASE(128, 64) SRF_CASE(64, 64) SRF_CASE(32, 64) SRF_CASE(128, 32) SRF_CASE(64, 32) SRF_CASE(32, 32)
-  SRF_CASE(128, 16) SRF_CASE(64, 16) SRF_CASE(16, 16)
+  SRF_CASE(128, 64) SRF_CASE(64, 64) SRF_CASE(32, 64) SRF_CASE(16, 64)
+  SRF_CASE(128, 32) SRF_CASE(64, 32) SRF_CASE(32, 32) SRF_CASE(16, 32)
+  SRF_CASE(128, 16) SRF_CASE(64, 16) SRF_CASE(32, 16) SRF_CASE(16, 16)
 #undef SRF_CASE
   set_error("dense igemm: unsupported tile k=%d n=%d", tk, tn);
   return SRF_ERR_UNSUPPORTED;

@@ -8,4 +8,5 @@ from .sparse_encoder import SparseBasicBlock, SparseEncoderCustom, make_sparse_c
 from .roi import (SingleRoIExtractor, bbox2roi, boxes3d_to_corners3d, img_feats_sampling_bboxes_roi,  # noqa: F401
                   points_feats_sampling_bboxes_roi)
 from .head import DynamicConv, SingleSRFDetHead, SingleSRFDetHeadLiDAR  # noqa: F401
+from .pillar import PFNLayer, PillarFeatureNetCustom, PointPillarsScatter  # noqa: F401
 from .detector import SRFDetPointPath  # noqa: F401

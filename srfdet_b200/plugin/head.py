@@ -66,7 +66,8 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None):
     if enc is not None:
         # shapes the tcgen05 tiles cannot cover (not multiples of 16, or of the tile above it) take the FFMA kernel
         tk = lib.srf_linear_tile_k_enc(k, enc)
-        if k % 16 or n % 16 or k % tk or (n > 128 and n % 128) or (ln is not None and n > 1024):
+        if min(k, tk) not in (16, 32, 64, 128) or min(n, 128) not in (16, 32, 64, 128) or k % tk or (n > 128 and n % 128) \
+                or (ln is not None and n > 1024):
             out = _linear(L.decode(x, k) if x.dtype != torch.float32 else x, lin, 'fp32_simt', cache, key, relu, ln)
             return _encode_out(out, enc if out_enc is None else out_enc)
     if enc is None:

@@ -47,6 +47,19 @@ class SparseConv3dParams(nn.Module):
         fan_in = in_channels * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
         nn.init.uniform_(self.weight, -(3.0 / fan_in) ** 0.5 * 1.7, (3.0 / fan_in) ** 0.5 * 1.7)
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        """Checkpoints written with spconv 1.x / mmcv's sparse ops store conv weights as
+        (kD,kH,kW,Cin,Cout); spconv 2 (this module's layout) as (Cout,kD,kH,kW,Cin).  Like mmdet3d's
+        spconv-2 load hook (mmdet3d/ops/spconv/overwrite_spconv/write_spconv2.py [3P]) the old layout is
+        permuted on load, so either kind of checkpoint reproduces the same result."""
+        key = prefix + 'weight'
+        w = state_dict.get(key)
+        k = self.kernel_size
+        if w is not None and tuple(w.shape) == (*k, self.in_channels, self.out_channels) \
+                and tuple(w.shape) != tuple(self.weight.shape):
+            state_dict[key] = w.permute(4, 0, 1, 2, 3).contiguous()
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def kio(self):
         """(kvol, cin, cout) view of the weight (accepts the spconv-1/mmcv layout
         (kD,kH,kW,Cin,Cout) when a checkpoint in that layout was loaded)."""

@@ -95,3 +95,49 @@ def test_dynamic_vfe_full_size_vs_oracle(kind):
     np.testing.assert_array_equal(vc.cpu().numpy(), rc)
     assert rel_err(vf.cpu().numpy(), rf) < 1e-4
     assert len(rc) > 40000
+
+
+# ---------------------------------------------------------------- pillar path
+@pytest.mark.parametrize('tag,kw', [('new', dict(legacy=False)), ('legacy', dict(legacy=True, with_distance=True)),
+                                    ('avg', dict(legacy=False, mode='avg'))])
+def test_pillar_vfe_golden(golden_dir, tag, kw):
+    """PillarFeatureNetCustom.forward (pillar_encoder_custom.py:95-161) vs the reference's own output."""
+    import os
+    from srfdet_b200.plugin import PillarFeatureNetCustom
+    z = np.load(os.path.join(golden_dir, 'pillar_vfe.npz'))
+    net = PillarFeatureNetCustom(in_channels=5, feat_channels=[64], voxel_size=[0.2, 0.2, 8],
+                                 point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], **kw).eval()
+    net.load_state_dict({k[len(tag) + 3:]: torch.as_tensor(z[k]) for k in z.files if k.startswith(tag + '.p.')}, strict=True)
+    out = net.cuda()(cuda(z['voxels']), cuda(z['num_points']), cuda(z['coors']))
+    np.testing.assert_allclose(out.cpu().numpy(), z[f'{tag}.out'], rtol=1e-5, atol=2e-5)
+
+
+def test_pillar_path_vs_oracle():
+    """hard voxelization (T=20, 40000 pillars, configs/nus/srfdet_pillar_nusc_L.py:37-54) ->
+    PillarFeatureNetCustom -> PointPillarsScatter at full size vs the oracle; no host sync."""
+    from oracle import oracle as O
+    from srfdet_b200 import synth
+    from srfdet_b200.plugin import PillarFeatureNetCustom, PointPillarsScatter, Voxelization
+    vs, pc = [0.2, 0.2, 8], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    pts = synth.cloud('nusc', 77)
+    torch.manual_seed(5)
+    net = PillarFeatureNetCustom(in_channels=5, feat_channels=[64], voxel_size=vs, point_cloud_range=pc, legacy=False).eval()
+    from util import randomize_bn_
+    randomize_bn_(net, 6)
+    v, c, n, _ = O.hard_voxelize(pts, vs, pc, 20, 40000)
+    coors = np.concatenate([np.zeros((len(c), 1), np.int32), c], 1)
+    ref = O.pillar_feature_net({k: t.numpy() for k, t in net.state_dict().items()}, v, n, coors, vs, pc, legacy=False)
+    ref_canvas = O.pillars_scatter(ref, coors, 1, 512, 512)
+    vox = Voxelization(vs, pc, 20, (40000, 40000)).eval()
+    o = vox.hard_padded(cuda(pts), batch_idx=0)
+    m = int(o['count'])
+    assert m == len(c)
+    np.testing.assert_array_equal(o['coors'][:m].cpu().numpy(), coors)
+    feats = net.cuda()(o['voxels'], o['num_points'], o['coors'], num_voxels=o['count'])
+    np.testing.assert_allclose(feats[:m].cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+    for cl in (False, True):
+        sc = PointPillarsScatter(64, (512, 512))
+        sc.channels_last = cl
+        canvas = sc(feats, o['coors'], batch_size=1, num_voxels=o['count'])
+        assert canvas.shape == (1, 64, 512, 512)
+        np.testing.assert_allclose(canvas.cpu().numpy(), ref_canvas, rtol=1e-5, atol=2e-5)

@@ -209,3 +209,14 @@ def test_sparse_conv_vs_dense_conv3d():
     full = F.conv3d(dense, torch.as_tensor(w2).permute(0, 4, 1, 2, 3).contiguous(), stride=(2, 1, 1))
     o = torch.as_tensor(oc, dtype=torch.int64)
     np.testing.assert_allclose(got, full[o[:, 0], :, o[:, 1], o[:, 2], o[:, 3]].numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('tag,kw', [('new', dict(legacy=False)), ('legacy', dict(legacy=True, with_distance=True)),
+                                    ('avg', dict(legacy=False, mode='avg'))])
+def test_pillar_vfe_golden(golden_dir, tag, kw):
+    """Oracle restatement of PillarFeatureNetCustom vs the reference's own output."""
+    z = _load(golden_dir, 'pillar_vfe.npz')
+    params = {k[len(tag) + 3:]: z[k] for k in z.files if k.startswith(tag + '.p.')}
+    out = O.pillar_feature_net(params, z['voxels'], z['num_points'], z['coors'], [0.2, 0.2, 8],
+                               [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], **kw)
+    np.testing.assert_allclose(out, z[f'{tag}.out'], rtol=1e-5, atol=1e-5)

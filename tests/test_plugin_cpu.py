@@ -110,3 +110,66 @@ def test_frame_partition_gloo_world2(tmp_path):
     r = torch.load(out)
     assert r['vals'] == [0.0, 11.0, 20.0, 31.0, 40.0, 51.0, 60.0]
     assert r['tmax'] == 2.0
+
+
+def test_spconv1_layout_checkpoint_loads_bit_exact():
+    """A state dict in the spconv-1 / mmcv weight layout (kD,kH,kW,Cin,Cout) loads into
+    SparseEncoderCustom -- through the PARENT module's load_state_dict -- and yields exactly the
+    spconv-2 weights (checkpoint import)."""
+    import torch
+    from srfdet_b200.plugin import SparseEncoderCustom
+    kw = dict(in_channels=5, sparse_shape=[41, 1472, 1472], output_channels=128,
+              encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+              encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    torch.manual_seed(0)
+    a = SparseEncoderCustom(**kw)
+    holder_a = torch.nn.ModuleDict(dict(pts_middle_encoder=a))
+    sd1 = {}
+    n_conv = 0
+    for k, v in holder_a.state_dict().items():
+        if v.dim() == 5:
+            sd1[k] = v.permute(1, 2, 3, 4, 0).contiguous()      # (Cout,kD,kH,kW,Cin) -> (kD,kH,kW,Cin,Cout)
+            n_conv += 1
+        else:
+            sd1[k] = v.clone()
+    assert n_conv == 21
+    torch.manual_seed(1)
+    b = SparseEncoderCustom(**kw)
+    holder_b = torch.nn.ModuleDict(dict(pts_middle_encoder=b))
+    missing, unexpected = holder_b.load_state_dict(sd1, strict=True)
+    assert not missing and not unexpected
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    # and the (kvol, cin, cout) views the kernels pack from are identical
+    for (ca, *_), (cb, *_) in zip(a.layer_plan(), b.layer_plan()):
+        assert torch.equal(ca.kio(), cb.kio())
+
+
+def test_weight_caches_follow_parent_load_state_dict():
+    """Packed / folded weight caches are keyed on (data_ptr, version) of their source tensors, so a
+    checkpoint loaded through ANY ancestor module (which never calls a child's load_state_dict) or an
+    in-place update invalidates them."""
+    import torch
+    from srfdet_b200.plugin import DynamicVFECustom, SparseEncoderCustom
+    from srfdet_b200.plugin.head import _cached
+    enc = SparseEncoderCustom(in_channels=4, sparse_shape=[41, 1600, 1408])
+    v0 = enc._weights_version()
+    parent = torch.nn.ModuleDict(dict(enc=enc))
+    parent.load_state_dict({k: v.clone() for k, v in parent.state_dict().items()})
+    v1 = enc._weights_version()
+    assert v0 != v1
+    with torch.no_grad():
+        enc.conv_input[1].running_var.add_(1.0)
+    assert enc._weights_version() != v1
+    vfe = DynamicVFECustom(in_channels=4, feat_channels=[4], with_cluster_center=True, with_voxel_center=True,
+                           voxel_size=[0.05, 0.05, 0.1], point_cloud_range=[0, -40, -3, 70.4, 40, 1],
+                           norm_cfg=dict(type='naiveSyncBN1dCustom', eps=1e-3, momentum=0.01))
+    w0 = vfe._weights_version()
+    torch.nn.ModuleDict(dict(v=vfe)).load_state_dict({'v.' + k: t.clone() for k, t in vfe.state_dict().items()})
+    assert vfe._weights_version() != w0
+    lin = torch.nn.Linear(8, 8)
+    cache, calls = {}, []
+    make = lambda: calls.append(1) or len(calls)
+    assert _cached(cache, 'k', (lin.weight,), make) == 1 and _cached(cache, 'k', (lin.weight,), make) == 1
+    torch.nn.Sequential(lin).load_state_dict({'0.weight': torch.zeros(8, 8), '0.bias': torch.zeros(8)})
+    assert _cached(cache, 'k', (lin.weight,), make) == 2
