@@ -186,6 +186,22 @@ int srf_rulebook_build(const void* in_index, const int32_t in_dims_host[4], cons
                        const int32_t ksize_host[3], const int32_t stride_host[3],
                        const int32_t pad_host[3], int32_t* nbr, uint32_t* tile_mask, void* stream);
 
+/* Rulebook of a dense 2-D conv (ksize x ksize, stride, zero padding) over (n, h, w) pixel rows in
+ * row-major order: lets the BEV backbone / neck convolutions (SECONDCustom, FPN;
+ * models/backbones/second_custom.py:23-91) run on srf_spconv_tc over NHWC activations.
+ * nbr (ksize*ksize, cap_out), cap_out a multiple of 128 >= n*ho*wo. */
+int srf_dense_rulebook(int32_t n, int32_t h, int32_t w, int32_t ksize, int32_t stride, int32_t pad,
+                       int32_t cap_out, int32_t* nbr, uint32_t* tile_mask, void* stream);
+
+/* (n, c, h, w) f32 NCHW (the layout SparseConvTensor.dense() emits) -> (n*h*w, c) pixel rows in a 16-bit
+ * encoding: the A operand of the first backbone convolution. */
+int srf_nchw_to_rows(const float* in, int32_t n, int32_t c, int32_t h, int32_t w, int32_t enc, void* out,
+                     void* stream);
+/* FPN top-down step on pixel rows in encoding enc: rows_hi (n,h,w,c) += nearest_upsample(rows_lo (n,h_lo,w_lo,c))
+ * (mmdet FPN.forward: F.interpolate(size=, mode='nearest')). */
+int srf_upsample_add(void* rows_hi, const void* rows_lo, int32_t n, int32_t h, int32_t w, int32_t h_lo,
+                     int32_t w_lo, int32_t c, int32_t enc, void* stream);
+
 /* ---------------------------------------------------------------------------------- *
  * Sparse convolution + folded BatchNorm1d + residual + ReLU (+ dense scatter).
  * Replaces spconv SubMConv3d/SparseConv3d forward, BN1d, ReLU, SparseBasicBlock residual
@@ -196,8 +212,8 @@ int srf_rulebook_build(const void* in_index, const int32_t in_dims_host[4], cons
  * srf_spconv_tc : tcgen05/TMEM implicit GEMM, fp32 accumulate.  in_dtype SRF_BF16 | SRF_F16 (one MMA
  *            per product) or SRF_BF16X2 | SRF_F16X2 (hi + lo operands, three MMAs per product: the
  *            tensor-core form of the reference's FP32 mode).  out_dtype: the same encoding, or
- *            SRF_F32.  w packed by srf_pack_weight_tc for the same encoding.  cin, cout in
- *            {16,32,64,128}.  srf_spconv_bf16 / srf_pack_weight_bf16: the SRF_BF16 forms (round 1 names).
+ *            SRF_F32.  w packed by srf_pack_weight_tc for the same encoding.  cin in
+ *            {16,32,64,128,256}, cout in {16,32,64,128} or a multiple of 128 (column tiles).  srf_spconv_bf16 / srf_pack_weight_bf16: the SRF_BF16 forms (round 1 names).
  * dense (nullable): write the result into a zeroed (B, cout*D, H, W) f32 map instead of
  * `out` (needs out_coors + out_dims_host).
  * ---------------------------------------------------------------------------------- */
@@ -249,14 +265,15 @@ int srf_f32_to_bf16(const float* in, int64_t rows, int32_t c, int32_t c_pad, voi
  * ---------------------------------------------------------------------------------- */
 /* srf_linear_tc: A (m,k) in a 16-bit encoding a_enc (plain or split), W packed by
  * srf_pack_linear_tc for the same encoding, out in out_enc (SRF_F32 or a 16-bit form of A's
- * element format), LayerNorm eps explicit.  K slices are min(k,128) wide (64 for split operands:
+ * element format), LayerNorm eps explicit, optional residual (m, n) in out's encoding added before
+ * the LayerNorm (norm(x + linear(y)) rows of the head: srfdet_head.py:2286-2287, 2304-2306).  K slices are min(k,128) wide (64 for split operands:
  * srf_linear_tile_k_enc).  The *_bf16 / un-suffixed functions are the SRF_BF16, eps = 1e-5 forms. */
 int srf_linear_tile_k_enc(int32_t k, int32_t enc);
 int srf_linear_splits_enc(int32_t k, int32_t enc, int32_t k_splits);
 int srf_pack_linear_tc(const float* w_f32, int32_t n, int32_t k, int32_t enc, void* w_packed, void* stream);
 int srf_linear_tc(const void* a, int32_t a_enc, int32_t m, int32_t k, const void* w_packed, int32_t n,
-                  const float* bias, int32_t epi, const float* ln_w, const float* ln_b, float ln_eps,
-                  void* out, int32_t out_enc, int32_t k_splits, void* stream);
+                  const float* bias, const void* residual, int32_t epi, const float* ln_w, const float* ln_b,
+                  float ln_eps, void* out, int32_t out_enc, int32_t k_splits, void* stream);
 int srf_linear_tile_k(int32_t k); /* host: K-slice width used by the packer (min(k,128)) */
 int srf_linear_tile_n(int32_t n); /* host: N tile width (min(n,128)) */
 int srf_linear_splits(int32_t k, int32_t k_splits); /* host: effective split count used for (k, k_splits) */
@@ -274,10 +291,11 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
 int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials,
                   const float* bias, const float* gamma, const float* beta, float eps, int32_t relu,
                   void* out, void* stream);
-/* same with separate encodings: in f32 | bf16 | f16, out any SRF_* encoding */
+/* same with separate encodings (in f32 | bf16 | f16, out any SRF_* encoding) and an optional f32
+ * residual (rows, n) added before the norm: out = act(LN(sum_p in[p] + bias + residual)) */
 int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, int32_t n_partials,
-                      const float* bias, const float* gamma, const float* beta, float eps, int32_t relu,
-                      void* out, int32_t out_enc, void* stream);
+                      const float* bias, const float* residual, const float* gamma, const float* beta, float eps,
+                      int32_t relu, void* out, int32_t out_enc, void* stream);
 
 /* ---------------------------------------------------------------------------------- *
  * Region features.
@@ -348,6 +366,49 @@ int srf_dynconv_interact(const void* roi, int32_t roi_dtype, const void* params,
                          int32_t k, int32_t c, int32_t d, const float* ln1_w, const float* ln1_b,
                          const float* ln2_w, const float* ln2_b, void* out, int32_t out_dtype,
                          void* stream);
+
+/* ---------------------------------------------------------------------------------- *
+ * Rest of a head stage, proposal generation and decoding, fp32.
+ * ---------------------------------------------------------------------------------- */
+/* nn.MultiheadAttention core of self_attn_lidar (srfdet_head.py:2281-2285): qkv (B*P, 3*H*hd) f32 =
+ * in_proj output (q | k | v), rows batch-major; out (B*P, H*hd) = softmax(q k^T / sqrt(hd)) v per
+ * (batch, head), in any encoding (A operand of the out_proj GEMM).  hd in {8,16,32}. */
+int srf_mha_attention(const float* qkv, int32_t n_batch, int32_t n_p, int32_t n_heads, int32_t head_dim,
+                      void* out, int32_t out_enc, void* stream);
+/* SingleSRFDetHead.apply_deltas_lidar (srfdet_head.py:2331-2420): deltas (k,dim), boxes (k,dim) with
+ * ABSOLUTE centres and log sizes, weights (dim) device -> out (k,dim) normalised centres, log sizes. */
+int srf_apply_deltas(const float* deltas, const float* boxes, int32_t k, int32_t dim, const float* weights,
+                     float scale_clamp, const float pc_range_host[6], float* out, void* stream);
+/* A (n, c, h, w) map read through element strides: NCHW or torch.channels_last tensors in place. */
+typedef struct srf_map {
+  const float* ptr;
+  int32_t c;
+  int64_t sn, sc, sh, sw;
+} srf_map;
+/* DPG staircase step (srfdet_head.py:521-533; mmcv ConvModule = depthwise Conv2d(3, s2, p1, bias=False) +
+ * BN2d(eval, folded) + ReLU) over cat(a, b) (b nullable): out (n, ca+cb, ho, wo) f32, NCHW or
+ * (channels_last_out) (n, ho, wo, ca+cb) in memory. */
+int srf_dwconv3x3_s2(const srf_map* a_host, const srf_map* b_host, int32_t n, int32_t h, int32_t w,
+                     const float* wt_folded, const float* bias_folded, int32_t relu, int32_t channels_last_out,
+                     float* out, void* stream);
+/* pfeat_34.sum(dim=1) over cat(a, b) (:534); group > 1 / (ho,wo) != (h,w): the image branch's nearest
+ * F.interpolate + sum over the cameras of a sample (:584-590).  out (n_samples, ho*wo). */
+int srf_channel_sum(const srf_map* a_host, const srf_map* b_host, int32_t n_samples, int32_t group, int32_t h,
+                    int32_t w, int32_t ho, int32_t wo, float* out, void* stream);
+/* out (m,n) = act(x (m,k) . W (n,k)^T + bias), m <= 8 rows (dpg_fc1 / dpg_fc2, :537-543) */
+int srf_gemv_f32(const float* x, int32_t m, int32_t k, const float* w, int32_t n, const float* bias,
+                 int32_t relu, float* out, void* stream);
+/* (logits_a (+ logits_b)/2) (B,E,P) -> softmax over E -> boxes (B,P,dim) = sum_e w emb_boxes[e,p] with the
+ * sigmoid of the centre coordinates (:403, when sigmoid_centres) and feats (B,P,c) = sum_e w emb_feats[e,p]
+ * (:597-640) */
+int srf_dpg_mix(const float* logits_a, const float* logits_b, int32_t n_batch, int32_t n_exp, int32_t n_p,
+                const float* emb_boxes, int32_t box_dim, const float* emb_feats, int32_t c, float* boxes,
+                float* feats, int32_t sigmoid_centres, void* stream);
+/* get_bboxes decode (:1245-1268 + core/bbox/util.py:41-81): scores = sigmoid(logits) (n_logits values);
+ * boxes (k,dim) [abs centre, log size, sin, cos (, vx, vy)] -> out (k,dim-1) [cx, cy, cz - h/2, w, l, h,
+ * atan2(sin,cos) (, vx, vy)] */
+int srf_decode_boxes(const float* logits, int64_t n_logits, const float* boxes, int32_t k, int32_t dim,
+                     float* scores, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -622,3 +622,166 @@ def pillars_scatter(feats, coors, batch_size, ny, nx):
     coors = np.asarray(coors)
     canvas[coors[:, 0], :, coors[:, 2] * nx + coors[:, 3]] = feats
     return canvas.reshape(batch_size, c, ny, nx)
+
+
+# ----------------------------------------------------------------------------------------
+# Dense BEV backbone + neck
+# ----------------------------------------------------------------------------------------
+def _t(v):
+    return torch.as_tensor(np.asarray(v), dtype=torch.float32)
+
+
+def _conv_bn_relu(x, p, conv, bn, stride, pad, eps, groups=1):
+    x = F.conv2d(x, _t(p[conv + '.weight']), None, stride=stride, padding=pad, groups=groups)
+    x = F.batch_norm(x, _t(p[bn + '.running_mean']), _t(p[bn + '.running_var']), _t(p[bn + '.weight']), _t(p[bn + '.bias']),
+                     False, 0.0, eps)
+    return F.relu(x)
+
+
+def second_custom(params, x, layer_nums, layer_strides, eps=1e-3):
+    """SECONDCustom.forward (models/backbones/second_custom.py:77-91): per block a strided 3x3 conv-BN-ReLU followed
+    by layer_num 3x3 conv-BN-ReLU; parameters keyed blocks.{i}.{3j} (conv) / blocks.{i}.{3j+1} (BN)."""
+    x = _t(x)
+    outs = []
+    for i, (ln, st) in enumerate(zip(layer_nums, layer_strides)):
+        for j in range(ln + 1):
+            x = _conv_bn_relu(x, params, f'blocks.{i}.{3 * j}', f'blocks.{i}.{3 * j + 1}', st if j == 0 else 1, 1, eps)
+        outs.append(x)
+    return [o.numpy() for o in outs]
+
+
+def fpn(params, feats, num_outs, eps=1e-3, extra_convs=True):
+    """[3P] mmdet 2.28.2 FPN.forward as configured by the reference (configs/nus/srfdet_voxel_nusc_L.py:66-75)."""
+    feats = [_t(f) for f in feats]
+    lat = [_conv_bn_relu(f, params, f'lateral_convs.{i}.conv', f'lateral_convs.{i}.bn', 1, 0, eps) for i, f in enumerate(feats)]
+    for i in range(len(lat) - 1, 0, -1):
+        lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode='nearest')
+    outs = [_conv_bn_relu(lat[i], params, f'fpn_convs.{i}.conv', f'fpn_convs.{i}.bn', 1, 1, eps) for i in range(len(lat))]
+    for i in range(len(lat), num_outs):
+        if extra_convs:
+            outs.append(_conv_bn_relu(outs[-1], params, f'fpn_convs.{i}.conv', f'fpn_convs.{i}.bn', 2, 1, eps))
+        else:
+            outs.append(F.max_pool2d(outs[-1], 1, stride=2))
+    return [o.numpy() for o in outs]
+
+
+# ----------------------------------------------------------------------------------------
+# SRFDetHead: proposal generation, chained stages, decoding (SURVEY.md 8f ranks 2, 3)
+# ----------------------------------------------------------------------------------------
+def _sub(params, prefix):
+    return {k[len(prefix):]: v for k, v in params.items() if k.startswith(prefix)}
+
+
+def _dpg_logits(params, feats, conv_prefix, fc1, fc2, group=1, resize=None, eps=1e-3):
+    """Staircase of depthwise stride-2 ConvModules + channel sum + two FCs (srfdet_head.py:521-543 / :560-595)."""
+    feats = [_t(f) for f in feats]
+    x = None
+    for l in range(len(feats) - 1):
+        inp = feats[l] if x is None else torch.cat([feats[l], x], dim=1)
+        x = _conv_bn_relu(inp, params, f'{conv_prefix}.{l}.conv', f'{conv_prefix}.{l}.bn', 2, 1, eps, groups=inp.shape[1])
+    last = torch.cat([feats[-1], x], dim=1)
+    if resize is not None:
+        last = F.interpolate(last, list(resize))
+    if group > 1:
+        last = last.view(last.shape[0] // group, group, *last.shape[1:]).sum(dim=1)
+    s = last.sum(dim=1).flatten(1, 2)
+    h = F.relu(F.linear(s, _t(params[fc1 + '.weight']), _t(params[fc1 + '.bias'])))
+    return F.linear(h, _t(params[fc2 + '.weight']), _t(params[fc2 + '.bias']))
+
+
+def dpg_init_proposals(params, img_feats, point_feats, n_exp, n_p, use_img, is_kitti=False):
+    """SRFDetHead._get_init_proposals with DPG (srfdet_head.py:506-640) -> boxes (bs,n_p,dim), feats (bs,n_p,C)."""
+    bs = point_feats[0].shape[0]
+    w = _dpg_logits(params, point_feats, 'dpg_dw_convs_lidar', 'dpg_fc1_lidar', 'dpg_fc2_lidar').reshape(bs, n_exp, n_p)
+    if use_img:
+        flat = [np.asarray(f).reshape(-1, *f.shape[2:]) for f in img_feats]
+        wi = _dpg_logits(params, flat, 'dpg_dw_convs_img', 'dpg_fc1_img', 'dpg_fc2_img', group=flat[0].shape[0] // bs,
+                         resize=(30, 15) if is_kitti else (30, 30)).reshape(bs, n_exp, n_p)
+        w = (w + wi) / 2
+    w = w.softmax(1)
+    eb = _t(params['init_proposal_boxes.weight']).view(n_exp, n_p, -1)
+    ef = _t(params['init_proposal_feats.weight']).view(n_exp, n_p, -1)
+    boxes = (w.unsqueeze(-1) * eb.unsqueeze(0)).sum(1)
+    feats = (w.unsqueeze(-1) * ef.unsqueeze(0)).sum(1)
+    return boxes.numpy(), feats.numpy()
+
+
+def apply_deltas(deltas, boxes, weights, scale_clamp, pc_range):
+    """SingleSRFDetHead.apply_deltas_lidar (srfdet_head.py:2331-2420)."""
+    d, b = _t(deltas), _t(boxes)
+    w = [float(v) for v in weights]
+    size = torch.exp(b[:, 3:6])
+    dxyz = torch.stack([d[:, j] / w[j] for j in range(3)], -1)
+    dwlh = torch.stack([d[:, 3 + j] / w[3 + j] for j in range(3)], -1).clamp(max=scale_clamp)
+    ctr = dxyz * size + b[:, 0:3]
+    psize = torch.exp(dwlh) * size
+    lo = torch.tensor(pc_range[:3], dtype=torch.float32)
+    span = torch.tensor([pc_range[3] - pc_range[0], pc_range[4] - pc_range[1], pc_range[5] - pc_range[2]], dtype=torch.float32)
+    ctr = ((ctr - lo) / span).clamp(min=0.0, max=1.0)
+    return torch.cat([ctr, psize.log(), d[:, 6:len(w)]], dim=-1).numpy()
+
+
+def single_head_stage(p, img_feats, point_feats, boxes, prop, lidar2img, cfg):
+    """SingleSRFDetHead(.LiDAR).forward (srfdet_head.py:2221-2326 / 1455-1529), batch 1.
+    boxes (1,n_p,dim) normalised centres -- MUTATED in place like the reference; prop (n_p, C)."""
+    pc, vs = cfg['pc_range'], cfg['voxel_size']
+    n_p, c = boxes.shape[1], cfg['C']
+    if img_feats is not None:
+        img = img_roi_feats(img_feats, boxes.copy(), lidar2img, pc, list(cfg['istrides']))
+        pts = points_roi_feats(point_feats, boxes, pc, vs, list(cfg['strides']))
+        roi = fusion_proj(img, pts, p['output_fused_proj.weight'], p['output_fused_proj.bias'])
+    else:
+        roi = points_roi_feats(point_feats, boxes, pc, vs, list(cfg['strides']))
+    x = _t(prop)
+    heads = cfg['attn_heads']
+    qkv = F.linear(x, _t(p['self_attn_lidar.in_proj_weight']), _t(p['self_attn_lidar.in_proj_bias']))
+    q, k, v = [t.view(n_p, heads, c // heads).transpose(0, 1) for t in qkv.chunk(3, dim=-1)]
+    att = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(c // heads), dim=-1) @ v
+    att = att.transpose(0, 1).reshape(n_p, c)
+    x = F.layer_norm(x + F.linear(att, _t(p['self_attn_lidar.out_proj.weight']), _t(p['self_attn_lidar.out_proj.bias'])), (c,),
+                     _t(p['norm1_lidar.weight']), _t(p['norm1_lidar.bias']))
+    x2 = _t(dynamic_conv(_sub(p, 'inst_interact_lidar.'), x.numpy(), roi, cfg['d']))
+    obj = F.layer_norm(x + x2, (c,), _t(p['norm2_lidar.weight']), _t(p['norm2_lidar.bias']))
+    ff = F.linear(F.relu(F.linear(obj, _t(p['linear1_lidar.weight']), _t(p['linear1_lidar.bias']))), _t(p['linear2_lidar.weight']),
+                  _t(p['linear2_lidar.bias']))
+    obj = F.layer_norm(obj + ff, (c,), _t(p['norm3_lidar.weight']), _t(p['norm3_lidar.bias']))
+
+    def tower(prefix, n):
+        f = obj
+        for t in range(n):
+            f = F.relu(F.layer_norm(F.linear(f, _t(p[f'{prefix}.{3 * t}.weight'])), (c,), _t(p[f'{prefix}.{3 * t + 1}.weight']),
+                                    _t(p[f'{prefix}.{3 * t + 1}.bias'])))
+        return f
+    logits = F.linear(tower('cls_module_lidar', cfg['n_cls']), _t(p['class_logits_lidar.weight']), _t(p['class_logits_lidar.bias']))
+    deltas = F.linear(tower('reg_module_lidar', cfg['n_reg']), _t(p['bboxes_delta_lidar.weight']), _t(p['bboxes_delta_lidar.bias']))
+    pred = apply_deltas(deltas.numpy(), boxes.reshape(n_p, -1), cfg['bbox_weights'], cfg['scale_clamp'], pc)
+    return logits.numpy(), pred, obj.numpy()
+
+
+def srfdet_head_forward(params, img_feats, point_feats, lidar2img, cfg):
+    """SRFDetHead.forward (srfdet_head.py:371-498), batch 1: DPG -> sigmoid -> chained stages -> centre
+    de-normalisation.  -> logits (S,1,n_p,cls), boxes (S,1,n_p,dim)."""
+    use_img = img_feats is not None
+    boxes, prop = dpg_init_proposals(params, img_feats, point_feats, cfg['n_exp'], cfg['n_p'], use_img)
+    boxes = boxes.copy()
+    boxes[..., :3] = 1.0 / (1.0 + np.exp(-boxes[..., :3].astype(np.float64))).astype(np.float32)
+    prop = prop[0]
+    lg, bx = [], []
+    for s in range(cfg['stages']):
+        logits, pred, prop = single_head_stage(_sub(params, f'head_series_lidar.{s}.'), img_feats, point_feats, boxes, prop, lidar2img, cfg)
+        lg.append(logits[None])
+        bx.append(pred[None].copy())
+        boxes = pred[None].copy()
+    lg, bx = np.stack(lg), np.stack(bx)
+    pc = cfg['pc_range']
+    bx[..., :3] = bx[..., :3] * np.array([pc[3] - pc[0], pc[4] - pc[1], pc[5] - pc[2]], np.float32) + np.array(pc[:3], np.float32)
+    return lg, bx
+
+
+def decode_boxes(logits, boxes):
+    """get_bboxes decode (srfdet_head.py:1245-1268, core/bbox/util.py:41-81): sigmoid, exp sizes, atan2, bottom centre."""
+    lg, b = _t(logits), _t(boxes)
+    rot = torch.atan2(b[..., 6:7], b[..., 7:8])
+    out = torch.cat([b[..., 0:3], b[..., 3:6].exp(), rot, b[..., 8:]], dim=-1)
+    out[..., 2] = out[..., 2] - out[..., 5] * 0.5
+    return torch.sigmoid(lg).numpy(), out.numpy()

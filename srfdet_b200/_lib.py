@@ -78,6 +78,17 @@ class Pyramid(Structure):
                 ('n_levels', c_int32), ('channels', c_int32), ('channels_last', c_int32)]
 
 
+class Map(Structure):
+    _fields_ = [('ptr', c_void_p), ('c', c_int32), ('sn', c_int64), ('sc', c_int64), ('sh', c_int64), ('sw', c_int64)]
+
+
+def map_view(t):
+    """srf_map of a (n, c, h, w) fp32 CUDA tensor in whatever memory format it has (NCHW or channels_last)."""
+    assert t.dim() == 4 and t.is_cuda and str(t.dtype) == 'torch.float32'
+    sn, sc, sh, sw = t.stride()
+    return Map(t.data_ptr(), t.shape[1], sn, sc, sh, sw)
+
+
 _I4 = c_int32 * 4
 _I3 = c_int32 * 3
 _F3 = c_float * 3
@@ -114,6 +125,9 @@ PROTOTYPES = {
     'srf_pillar_vfe': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                  POINTER(c_float), POINTER(c_float), c_int32, c_void_p, c_void_p]),
     'srf_pillars_scatter': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_dense_rulebook': (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    'srf_nchw_to_rows': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_upsample_add': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     'srf_rulebook_build': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_void_p, c_int32, c_void_p,
                                      POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]),
     'srf_spconv_f32': (c_int32, [POINTER(ConvArgs), c_void_p]),
@@ -128,10 +142,18 @@ PROTOTYPES = {
     'srf_linear_tile_k_enc': (c_int32, [c_int32, c_int32]),
     'srf_linear_splits_enc': (c_int32, [c_int32, c_int32, c_int32]),
     'srf_pack_linear_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
-    'srf_linear_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+    'srf_linear_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_float, c_void_p, c_int32, c_int32, c_void_p]),
-    'srf_layernorm_enc': (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32,
-                                    c_void_p, c_int32, c_void_p]),
+    'srf_layernorm_enc': (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                    c_int32, c_void_p, c_int32, c_void_p]),
+    'srf_mha_attention': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    'srf_apply_deltas': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_float, POINTER(c_float), c_void_p, c_void_p]),
+    'srf_dwconv3x3_s2': (c_int32, [POINTER(Map), POINTER(Map), c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_channel_sum': (c_int32, [POINTER(Map), POINTER(Map), c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_gemv_f32': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    'srf_dpg_mix': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                              c_void_p, c_int32, c_void_p]),
+    'srf_decode_boxes': (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     'srf_dynconv_interact_tc': (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                           c_float, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     'srf_pack_linear_bf16': (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

@@ -119,7 +119,8 @@ __device__ int g_trace_n[64];
 template <int CIN, int COUT, bool SPARSE, bool SPLIT>
 struct Cfg {
   // input channels carried by one slot member; an offset takes KSPL consecutive slots
-  static constexpr int KC = !SPLIT ? CIN : (CIN == 64 ? (SPARSE ? SRF_SPLIT_KC64 : 64) : (CIN == 128 ? SRF_SPLIT_KC128 : CIN));
+  static constexpr int KC = !SPLIT ? (CIN > 128 ? 128 : CIN)
+                                   : (CIN == 64 ? (SPARSE ? SRF_SPLIT_KC64 : 64) : (CIN >= 128 ? SRF_SPLIT_KC128 : CIN));
   static constexpr int KSPL = CIN / KC;
   static constexpr int NJ = KC / 16;                     // MMA K-steps per member (x3 when split)
   static constexpr int CH = (SPLIT ? 2 : 1) * KC / 8;    // 16-byte chunks per A row per slot member (hi planes, then lo planes)
@@ -524,7 +525,7 @@ igemm_umma_kernel(const IgemmArgs a) {
           float v[NC];
 #pragma unroll
           for (int cc = 0; cc < NC; cc += 16) tc_ld16(taddr + c0 + cc, v + cc);
-          if (row < m_rows && !DBG(8)) epilogue_chunk<COUT, NC>(a, row, c0, v);
+          if (row < m_rows && !DBG(8)) epilogue_chunk<COUT, NC>(a, row, nt * COUT + c0, v);
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
@@ -593,9 +594,9 @@ template <bool SPLIT>
 static int dispatch_sparse(int cin, int cout, const IgemmArgs& a, int host_tiles, cudaStream_t st) {
 #define SRF_CASE(ci, co) if (cin == ci && cout == co) return launch_igemm<ci, co, true, SPLIT>(a, host_tiles, st);
   SRF_CASE(16, 16) SRF_CASE(16, 32) SRF_CASE(32, 32) SRF_CASE(32, 64) SRF_CASE(64, 64) SRF_CASE(64, 128)
-  SRF_CASE(128, 128) SRF_CASE(128, 64) SRF_CASE(64, 32) SRF_CASE(32, 16)
+  SRF_CASE(128, 128) SRF_CASE(128, 64) SRF_CASE(64, 32) SRF_CASE(32, 16) SRF_CASE(256, 128) SRF_CASE(256, 64)
 #undef SRF_CASE
-  set_error("sparse igemm: unsupported channel pair cin=%d cout=%d", cin, cout);
+  set_error("sparse igemm: unsupported channel pair cin=%d cout tile=%d", cin, cout);
   return SRF_ERR_UNSUPPORTED;
 }
 
@@ -642,6 +643,8 @@ extern "C" int srf_prof_read_t(unsigned long long* host, int launch) {   // laun
 
 extern "C" {
 
+int srf_conv_tile_n(int32_t cout);
+
 static bool use_warp16() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("SRF_CONV16_WARP"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -670,7 +673,9 @@ int srf_spconv_tc(const srf_conv_args* c, void* stream) {
   a.d_n_out = c->d_n_out;
   a.cap_out = c->cap_out;
   a.kvol = c->kvol;
-  a.n_tiles = 1;
+  const int tn = srf_conv_tile_n(c->cout);
+  SRF_CHECK_ARG(c->cout % tn == 0 && (tn == c->cout || !c->dense), "srf_spconv_tc: cout > 128 must be a multiple of 128 (and not dense-scattered)");
+  a.n_tiles = c->cout / tn;
   a.w = (const uint16_t*)c->w;
   a.bias = c->bias;
   a.residual = c->residual;
@@ -685,8 +690,8 @@ int srf_spconv_tc(const srf_conv_args* c, void* stream) {
   a.D = c->out_dims[1];
   a.H = c->out_dims[2];
   a.W = c->out_dims[3];
-  return split ? dispatch_sparse<true>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream)
-               : dispatch_sparse<false>(c->cin, c->cout, a, c->cap_out / 128, (cudaStream_t)stream);
+  return split ? dispatch_sparse<true>(c->cin, tn, a, c->cap_out / 128 * a.n_tiles, (cudaStream_t)stream)
+               : dispatch_sparse<false>(c->cin, tn, a, c->cap_out / 128 * a.n_tiles, (cudaStream_t)stream);
 }
 
 int srf_spconv_bf16(const srf_conv_args* c, void* stream) { return srf_spconv_tc(c, stream); }
@@ -694,8 +699,10 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) { return srf_spconv_tc
 // K chunk per ring slot of the sparse kernel (the packer lays the weights out per chunk)
 int srf_pack_weight_kc(int32_t cin, int32_t enc) {
   if (!enc_is_split(enc)) return cin;
-  return cin == 64 ? SRF_SPLIT_KC64 : (cin == 128 ? SRF_SPLIT_KC128 : cin);
+  return cin == 64 ? SRF_SPLIT_KC64 : (cin >= 128 ? SRF_SPLIT_KC128 : cin);
 }
+// output-channel tile of the sparse kernel: layers wider than 128 outputs run as cout / 128 column tiles
+int srf_conv_tile_n(int32_t cout) { return cout > 128 ? 128 : cout; }
 
 int srf_linear_tile_k_enc(int32_t k, int32_t enc) {
   // K slice per ring slot of the dense tcgen05 GEMM: 128 channels (64 for split operands, whose
@@ -715,8 +722,8 @@ int srf_linear_splits_enc(int32_t k, int32_t enc, int32_t k_splits) {
 int srf_linear_splits(int32_t k, int32_t k_splits) { return srf_linear_splits_enc(k, SRF_BF16, k_splits); }
 
 int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
-                  int32_t epi, const float* ln_w, const float* ln_b, float ln_eps, void* out, int32_t out_enc, int32_t k_splits,
-                  void* stream) {
+                  const void* residual, int32_t epi, const float* ln_w, const float* ln_b, float ln_eps, void* out, int32_t out_enc,
+                  int32_t k_splits, void* stream) {
   SRF_CHECK_ARG(a_in && w_packed && out && m >= 0 && k > 0 && n > 0, "srf_linear_tc: bad args");
   SRF_CHECK_ARG(enc_is_16(a_enc), "srf_linear_tc: A must be bf16 / f16 / split");
   SRF_CHECK_ARG(out_enc == SRF_F32 || (enc_is_16(out_enc) && enc_is_f16(out_enc) == enc_is_f16(a_enc)),
@@ -737,6 +744,7 @@ int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const v
   a.n_tiles = n / tn;
   a.w = (const uint16_t*)w_packed;
   a.bias = bias;
+  a.residual = residual;
   a.relu = epi & 1;
   a.ln = (epi & 2) ? 1 : 0;
   a.ln_w = ln_w;
@@ -749,7 +757,7 @@ int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const v
   a.out_lo_off = n;
   a.k_splits = 1;
   if (k_splits > 1) {
-    SRF_CHECK_ARG(epi == 0 && !bias && out_enc == SRF_F32, "srf_linear_tc: split-K needs epi=0, no bias and an f32 output of k_splits slabs");
+    SRF_CHECK_ARG(epi == 0 && !bias && !residual && out_enc == SRF_F32, "srf_linear_tc: split-K needs epi=0, no bias / residual and an f32 output of k_splits slabs");
     const int kper = (a.kvol + k_splits - 1) / k_splits;
     a.k_splits = (a.kvol + kper - 1) / kper;   // every split owns at least one K slice
   }
@@ -760,7 +768,7 @@ int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const v
 int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
                     int32_t epi, const float* ln_w, const float* ln_b, void* out, int32_t out_dtype, int32_t k_splits,
                     void* stream) {
-  return srf_linear_tc(a_bf16, SRF_BF16, m, k, w_packed, n, bias, epi, ln_w, ln_b, 1e-5f, out, out_dtype, k_splits, stream);
+  return srf_linear_tc(a_bf16, SRF_BF16, m, k, w_packed, n, bias, nullptr, epi, ln_w, ln_b, 1e-5f, out, out_dtype, k_splits, stream);
 }
 
 }  // extern "C"

@@ -283,6 +283,23 @@ __global__ void __launch_bounds__(256) rulebook_kernel(const uint32_t* __restric
   }
 }
 
+__global__ void dense_rulebook_kernel(int n, int h, int w, int ho, int wo, int ks, int stride, int pad, int cap_out,
+                                      int32_t* __restrict__ nbr, uint32_t* __restrict__ tile_mask) {
+  const int64_t total = (int64_t)cap_out * ks * ks;
+  const int n_out = n * ho * wo;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(e % cap_out), k = (int)(e / cap_out);
+    int src = -1;
+    if (row < n_out) {
+      const int ox = row % wo, oy = (row / wo) % ho, img = row / (wo * ho);
+      const int iy = oy * stride - pad + k / ks, ix = ox * stride - pad + k % ks;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) src = (img * h + iy) * w + ix;
+    }
+    nbr[e] = src;
+    if (k == 0 && (row & 127) == 0) tile_mask[row >> 7] = row < n_out ? ((1u << (ks * ks)) - 1u) : 0u;
+  }
+}
+
 }  // namespace srf
 
 using namespace srf;
@@ -390,6 +407,22 @@ int srf_index_perm(const void* index, const int32_t dims[4], const int32_t* coor
   SRF_COUNT(1);
   index_lookup_kernel<true><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
       v.bits, v.rank, dims4(dims), (const int4*)coors, n, d_n, perm);
+  SRF_LAUNCH_CHECK();
+  return SRF_OK;
+}
+
+// Rulebook of a DENSE 2-D convolution over (n, h, w) row-major pixel rows (the BEV backbone / neck
+// convs of SURVEY.md 8f rank 1 run on the same gather-GEMM kernel as the sparse layers): every
+// output pixel exists, a neighbour is missing only in the zero padding.  Static per shape.
+int srf_dense_rulebook(int32_t n, int32_t h, int32_t w, int32_t ksize, int32_t stride, int32_t pad, int32_t cap_out, int32_t* nbr,
+                       uint32_t* tile_mask, void* stream) {
+  SRF_CHECK_ARG(nbr && tile_mask && n >= 1 && h >= 1 && w >= 1 && ksize >= 1 && ksize * ksize <= 27 && stride >= 1 && pad >= 0,
+                "srf_dense_rulebook: bad args");
+  const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (w + 2 * pad - ksize) / stride + 1;
+  SRF_CHECK_ARG(cap_out % 128 == 0 && cap_out >= n * ho * wo, "srf_dense_rulebook: cap_out must be a multiple of 128 covering n*ho*wo");
+  SRF_COUNT(1);
+  dense_rulebook_kernel<<<grid_for((int64_t)cap_out * ksize * ksize, 256), 256, 0, (cudaStream_t)stream>>>(n, h, w, ho, wo, ksize, stride, pad,
+                                                                                                       cap_out, nbr, tile_mask);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }

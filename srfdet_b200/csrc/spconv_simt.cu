@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(128) spconv_smallcin_kernel(ConvDev a) {
 
 // (kvol, cin, cout) f32 -> 16-bit elements in UMMA "core matrix" order, per kernel offset k and
 // K chunk q of kc input channels:   [k][q][part][kc/8][co][ci%8]   (one 16-byte K-chunk per output
-// channel row; part = hi only, or hi then lo for the split encodings)
-__global__ void pack_weight_kernel(const float* __restrict__ w, int kvol, int cin, int cout, int kc, int enc,
+// channel row; part = hi only, or hi then lo for the split encodings); more than 128 output channels are
+// laid out as column tiles [nt][k][q][part][kc/8][128][8]
+__global__ void pack_weight_kernel(const float* __restrict__ w, int kvol, int cin, int cout, int kc, int tn, int enc,
                                    uint16_t* __restrict__ out) {
   const bool f16 = enc_is_f16(enc);
   const int parts = enc_is_split(enc) ? 2 : 1;
@@ -185,12 +186,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int kvol, int ci
     int ci = (int)(t % cin);
     int k = (int)(t / cin);
     const int q = ci / kc, cl = ci % kc;
-    const int64_t member = ((int64_t)k * (cin / kc) + q) * parts;           // in units of kc*cout elements
-    const int64_t inner = ((int64_t)(cl / 8) * cout + co) * 8 + (cl % 8);
+    const int nt = co / tn, col = co % tn;                                   // column tiles of tn output channels
+    const int64_t member = (((int64_t)nt * kvol + k) * (cin / kc) + q) * parts;   // in units of kc*tn elements
+    const int64_t inner = ((int64_t)(cl / 8) * tn + col) * 8 + (cl % 8);
     const float v = w[e];
     const uint16_t h = pack16(f16, v);
-    out[member * kc * cout + inner] = h;
-    if (parts == 2) out[(member + 1) * kc * cout + inner] = pack16(f16, v - unpack16(f16, h));
+    out[member * kc * tn + inner] = h;
+    if (parts == 2) out[(member + 1) * kc * tn + inner] = pack16(f16, v - unpack16(f16, h));
   }
 }
 
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 // The row is read once into registers (n <= 32*LN_MAXPL), then reduced with shuffles.
 constexpr int LN_MAXPL = 16;   // values per lane -> n <= 512
 __global__ void layernorm_rows_kernel(const void* __restrict__ in, int in_enc, int64_t rows, int n, int n_partials,
-                                      const float* __restrict__ bias, const float* __restrict__ g,
+                                      const float* __restrict__ bias, const float* __restrict__ resid, const float* __restrict__ g,
                                       const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc) {
   int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -304,7 +306,7 @@ __global__ void layernorm_rows_kernel(const void* __restrict__ in, int in_enc, i
     if (j < n) {
       float t = ld_enc(in, in_enc, (size_t)row, n, j);
       for (int p = 1; p < n_partials; ++p) t += ld_enc(in, in_enc, (size_t)(p * rows + row), n, j);   // slab order: deterministic
-      v[i] = t + (bias ? bias[j] : 0.f);
+      v[i] = t + (bias ? bias[j] : 0.f) + (resid ? resid[row * n + j] : 0.f);
       s += v[i];
     }
   }
@@ -330,7 +332,7 @@ __global__ void layernorm_rows_kernel(const void* __restrict__ in, int in_enc, i
 // One block per row, one thread per column (n <= 1024): used when split-K slabs have to be
 // summed -- 4-32 warps per row instead of one keeps enough loads in flight.
 __global__ void layernorm_cols_kernel(const void* __restrict__ in, int in_enc, int64_t rows, int n, int n_partials,
-                                      const float* __restrict__ bias, const float* __restrict__ g,
+                                      const float* __restrict__ bias, const float* __restrict__ resid, const float* __restrict__ g,
                                       const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc) {
   __shared__ float red[2][32];
   const int64_t row = blockIdx.x;
@@ -339,6 +341,7 @@ __global__ void layernorm_cols_kernel(const void* __restrict__ in, int in_enc, i
   if (j < n) {
     for (int p = 0; p < n_partials; ++p) v += ld_enc(in, in_enc, (size_t)(p * rows + row), n, j);   // slab order: deterministic
     v += bias ? bias[j] : 0.f;
+    v += resid ? resid[row * n + j] : 0.f;
   }
   float s = j < n ? v : 0.f;
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -422,6 +425,7 @@ int srf_spconv_f32(const srf_conv_args* a, void* stream) {
 }
 
 int srf_pack_weight_kc(int32_t cin, int32_t enc);   // igemm_umma.cu: K chunk per ring slot for (cin, enc)
+int srf_conv_tile_n(int32_t cout);
 int srf_linear_tile_k_enc(int32_t k, int32_t enc);
 int srf_linear_tile_n(int32_t n);
 
@@ -429,7 +433,7 @@ int srf_pack_weight_tc(const float* w, int32_t kvol, int32_t cin, int32_t cout, 
   SRF_CHECK_ARG(w && packed && kvol > 0 && cin % 8 == 0 && cout % 8 == 0 && enc_is_16(enc), "srf_pack_weight_tc: bad args");
   int64_t total = (int64_t)kvol * cin * cout;
   SRF_COUNT(1);
-  pack_weight_kernel<<<lgrid2(total, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cout, srf_pack_weight_kc(cin, enc), enc, (uint16_t*)packed);
+  pack_weight_kernel<<<lgrid2(total, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cout, srf_pack_weight_kc(cin, enc), srf_conv_tile_n(cout), enc, (uint16_t*)packed);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }
@@ -485,7 +489,8 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
 }
 
 int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
-                      const float* gamma, const float* beta, float eps, int32_t relu, void* out, int32_t out_enc, void* stream) {
+                      const float* residual, const float* gamma, const float* beta, float eps, int32_t relu,
+                      void* out, int32_t out_enc, void* stream) {
   if (n_partials < 1) n_partials = 1;
   SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
   SRF_CHECK_ARG(in_enc == SRF_F32 || in_enc == SRF_BF16 || in_enc == SRF_F16, "srf_layernorm: input must be f32 / bf16 / f16");
@@ -494,20 +499,20 @@ int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, i
   SRF_COUNT(1);
   if (n_partials > 1 && n <= 1024) {
     const int threads = (n + 31) / 32 * 32;
-    layernorm_cols_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, gamma, beta, eps, relu, out, out_enc);
+    layernorm_cols_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, residual, gamma, beta, eps, relu, out, out_enc);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }
   int wpb = 4;
   int grid = (int)((rows + wpb - 1) / wpb);
-  layernorm_rows_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, gamma, beta, eps, relu, out, out_enc);
+  layernorm_rows_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, residual, gamma, beta, eps, relu, out, out_enc);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }
 
 int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
                   const float* gamma, const float* beta, float eps, int32_t relu, void* out, void* stream) {
-  return srf_layernorm_enc(in, dtype, rows, n, n_partials, bias, gamma, beta, eps, relu, out, dtype, stream);
+  return srf_layernorm_enc(in, dtype, rows, n, n_partials, bias, nullptr, gamma, beta, eps, relu, out, dtype, stream);
 }
 
 }  // extern "C"

@@ -26,6 +26,14 @@ def _f(t):
     return t.detach().float().contiguous()
 
 
+class _LinearView:
+    """(weight (n,k), bias) pair with nn.Linear's attribute names (MultiheadAttention.in_proj_*, folded 1x1 convs)."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+        self.out_features, self.in_features = weight.shape
+
+
 def _cached(cache, key, src, make):
     """Packed / folded form of `src` tensors, rebuilt when any of them was replaced or written
     in place (load_state_dict at any level of the module tree, optimizer step, manual edit)."""
@@ -49,7 +57,7 @@ def encode_rows(x, enc):
     return out
 
 
-def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None):
+def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None, residual=None):
     """nn.Linear (+LayerNorm +ReLU) on the library's GEMMs.
 
     x: (M,K) fp32, or an (M, K|2K) tensor already in the activation encoding of `precision`.
@@ -68,17 +76,20 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None):
         tk = lib.srf_linear_tile_k_enc(k, enc)
         if min(k, tk) not in (16, 32, 64, 128) or min(n, 128) not in (16, 32, 64, 128) or k % tk or (n > 128 and n % 128) \
                 or (ln is not None and n > 1024):
-            out = _linear(L.decode(x, k) if x.dtype != torch.float32 else x, lin, 'fp32_simt', cache, key, relu, ln)
+            out = _linear(L.decode(x, k) if x.dtype != torch.float32 else x, lin, 'fp32_simt', cache, key, relu, ln, residual=residual)
             return _encode_out(out, enc if out_enc is None else out_enc)
     if enc is None:
         x = _f(x)
         w = _f(lin.weight)
         out = torch.empty((m, n), dtype=torch.float32, device=dev)
-        fuse_relu = relu and ln is None
+        fuse_relu = relu and ln is None and residual is None
         L.check(lib.srf_linear_f32(L.ptr(x), m, k, L.ptr(w), n, L.ptr(bias), int(fuse_relu), L.ptr(out), st), 'srf_linear_f32')
         if ln is not None:
-            L.check(lib.srf_layernorm(L.ptr(out), L.F32, m, n, 1, None, L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)), ln.eps,
-                                      int(relu), L.ptr(out), st), 'srf_layernorm')
+            L.check(lib.srf_layernorm_enc(L.ptr(out), L.F32, m, n, 1, None, L.ptr(residual), L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)),
+                                          ln.eps, int(relu), L.ptr(out), L.F32, st), 'srf_layernorm')
+        elif residual is not None:
+            out = out + residual
+            out = torch.relu_(out) if relu else out
         return out
     if x.dtype == torch.float32:
         x = encode_rows(x, enc)
@@ -102,11 +113,11 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None):
     if ln is not None and tiles * 4 <= 148 and kvol >= 8:
         splits = lib.srf_linear_splits_enc(k, enc, min(kvol, max(1, 148 // tiles)))
         part = torch.empty((splits, m, n), dtype=torch.float32, device=dev)
-        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, None, 0, None, None, eps, L.ptr(part), L.F32, splits, st),
+        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, None, None, 0, None, None, eps, L.ptr(part), L.F32, splits, st),
                 'srf_linear_tc')
         out = alloc(out_enc)
-        L.check(lib.srf_layernorm_enc(L.ptr(part), L.F32, m, n, splits, L.ptr(bias), L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)),
-                                      eps, int(relu), L.ptr(out), out_enc, st), 'srf_layernorm')
+        L.check(lib.srf_layernorm_enc(L.ptr(part), L.F32, m, n, splits, L.ptr(bias), L.ptr(residual), L.ptr(_f(ln.weight)),
+                                      L.ptr(_f(ln.bias)), eps, int(relu), L.ptr(out), out_enc, st), 'srf_layernorm')
         return out
     fuse_ln = ln is not None and n <= 128
     epi = (1 if relu and (ln is None or fuse_ln) else 0) | (2 if fuse_ln else 0)
@@ -114,15 +125,16 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None):
     lnb = _f(ln.bias) if fuse_ln else None
     if ln is not None and not fuse_ln:
         tmp = alloc(L.F32)
-        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), 0, None, None, eps, L.ptr(tmp), L.F32, 1, st),
+        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), None, 0, None, None, eps, L.ptr(tmp), L.F32, 1, st),
                 'srf_linear_tc')
         out = alloc(out_enc)
-        L.check(lib.srf_layernorm_enc(L.ptr(tmp), L.F32, m, n, 1, None, L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)), eps, int(relu),
-                                      L.ptr(out), out_enc, st), 'srf_layernorm')
+        L.check(lib.srf_layernorm_enc(L.ptr(tmp), L.F32, m, n, 1, None, L.ptr(residual), L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)), eps,
+                                      int(relu), L.ptr(out), out_enc, st), 'srf_layernorm')
         return out
     out = alloc(out_enc)
-    L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), epi, L.ptr(lnw), L.ptr(lnb), eps, L.ptr(out), out_enc,
-                              1, st), 'srf_linear_tc')
+    assert residual is None or out_enc == L.F32, 'a fused residual is read in the output encoding (fp32 here)'
+    L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), L.ptr(residual), epi, L.ptr(lnw), L.ptr(lnb), eps,
+                              L.ptr(out), out_enc, 1, st), 'srf_linear_tc')
     return out
 
 
@@ -217,8 +229,50 @@ class _SingleHeadBase(nn.Module):
         self.scale_clamp = scale_clamp
         self.bbox_weights = bbox_weights
 
-    # dense tail of a stage ('next' rows): attention, interaction, FFN, towers, box update
+    # dense tail of a stage: attention, interaction, FFN, towers, box update -- all on this
+    # library's kernels (tcgen05 GEMMs with bias / residual / LayerNorm / ReLU epilogues, fp32 attention core)
     def _stage_tail(self, roi_feats_kc, bboxes, prop_feats, bs, n_p, precision=None):
+        precision = precision or registry.get_precision()
+        lib = L.load()
+        C = self.feat_channels_lidar
+        enc = registry.act_enc(precision)
+        act = L.F32 if enc is None else enc
+        cache = self.__dict__.setdefault('_tail_cache', {})
+        dev = bboxes.device
+        st = L.stream_ptr()
+        k = bs * n_p
+        x = _f(prop_feats.reshape(k, C))
+        # self-attention over the proposals of a sample (srfdet_head.py:2281-2287)
+        mha = self.self_attn_lidar
+        qkv = _linear(x, _LinearView(mha.in_proj_weight, mha.in_proj_bias), precision, cache, 'in_proj', out_enc=L.F32)
+        att = torch.empty((k, L.enc_width(act, C)), dtype=L.enc_torch_dtype(act), device=dev)
+        L.check(lib.srf_mha_attention(L.ptr(qkv), bs, n_p, mha.num_heads, C // mha.num_heads, L.ptr(att), act, st), 'srf_mha_attention')
+        prop = _linear(att, mha.out_proj, precision, cache, 'out_proj', ln=self.norm1_lidar, residual=x, out_enc=L.F32)
+        # instance interaction (:2289-2297)
+        prop2 = self.inst_interact_lidar.forward_kc(prop, roi_feats_kc, precision)
+        obj = torch.empty_like(prop)
+        L.check(lib.srf_layernorm_enc(L.ptr(prop2), L.F32, k, C, 1, None, L.ptr(prop), L.ptr(_f(self.norm2_lidar.weight)),
+                                      L.ptr(_f(self.norm2_lidar.bias)), self.norm2_lidar.eps, 0, L.ptr(obj), L.F32, st), 'srf_layernorm')
+        # FFN (:2299-2304)
+        hid = _linear(obj, self.linear1_lidar, precision, cache, 'ffn1', relu=True)
+        obj = _linear(hid, self.linear2_lidar, precision, cache, 'ffn2', ln=self.norm3_lidar, residual=obj, out_enc=L.F32)
+        # towers (:2306-2313): (Linear(no bias), LayerNorm, ReLU) x n, then the two small projections
+        obj_e = encode_rows(obj, act) if act != L.F32 else obj
+
+        def tower(mods, tag):
+            f = obj_e
+            for t in range(0, len(mods), 3):
+                last = t + 3 >= len(mods)
+                f = _linear(f, mods[t], precision, cache, (tag, t), relu=True, ln=mods[t + 1], out_enc=L.F32 if last else None)
+            return f if f.dtype == torch.float32 else L.decode(f, C)
+        cls_f, reg_f = tower(self.cls_module_lidar, 'cls'), tower(self.reg_module_lidar, 'reg')
+        logits = _linear(cls_f, self.class_logits_lidar, 'fp32_simt', cache, 'logits')
+        deltas = _linear(reg_f, self.bboxes_delta_lidar, 'fp32_simt', cache, 'deltas')
+        pred = self.apply_deltas_lidar(deltas, bboxes.view(-1, len(self.bbox_weights)))
+        return logits.view(bs, n_p, -1), pred.view(bs, n_p, -1), obj
+
+    def _stage_tail_torch(self, roi_feats_kc, bboxes, prop_feats, bs, n_p, precision=None):
+        """The same rows as plain torch ops (cross-check of the kernel path in the tests)."""
         C = self.feat_channels_lidar
         prop = prop_feats.view(bs, n_p, C).permute(1, 0, 2)
         prop2 = self.self_attn_lidar(prop, prop, value=prop)[0]
@@ -240,20 +294,16 @@ class _SingleHeadBase(nn.Module):
 
     def apply_deltas_lidar(self, deltas, boxes):
         """srfdet_head.py:2331-2420 (boxes carry ABSOLUTE centres after the in-place de-normalisation)."""
-        boxes = boxes.to(deltas.dtype)
-        w = self.bbox_weights
-        d = deltas
-        ctr = boxes[:, 0:3]
-        size = torch.exp(boxes[:, 3:6])
-        dxyz = torch.stack([d[:, 0] / w[0], d[:, 1] / w[1], d[:, 2] / w[2]], -1)
-        dwlh = torch.stack([d[:, 3] / w[3], d[:, 4] / w[4], d[:, 5] / w[5]], -1).clamp(max=self.scale_clamp)
-        pred_ctr = dxyz * size + ctr
-        pred_size = torch.exp(dwlh) * size
-        r = self.pc_range_lidar
-        lo = pred_ctr.new_tensor(r[:3])
-        span = pred_ctr.new_tensor([r[3] - r[0], r[4] - r[1], r[5] - r[2]])
-        pred_ctr = ((pred_ctr - lo) / span).clamp(min=0.0, max=1.0)
-        return torch.cat([pred_ctr, pred_size.log(), d[:, 6:len(w)]], dim=-1)
+        deltas, boxes = _f(deltas), _f(boxes)
+        k, dim = deltas.shape
+        key = ('bbox_weights', str(deltas.device))
+        cache = self.__dict__.setdefault('_tail_cache', {})
+        if key not in cache:
+            cache[key] = torch.tensor([float(v) for v in self.bbox_weights], dtype=torch.float32, device=deltas.device)
+        out = torch.empty_like(deltas)
+        L.check(L.load().srf_apply_deltas(L.ptr(deltas), L.ptr(boxes), k, dim, L.ptr(cache[key]), float(self.scale_clamp),
+                                          L.f6(self.pc_range_lidar), L.ptr(out), L.stream_ptr()), 'srf_apply_deltas')
+        return out
 
 
 @HEADS.register_module()
@@ -335,10 +385,9 @@ class SingleSRFDetHead(_SingleHeadBase):
             return pts_roi
         raise ValueError('inconsistent fusion inputs')
 
-    def forward(self, img_feats, point_feats, bboxes, prop_feats, pooler, img_metas, pooler_img=None, precision=None):
+    def forward(self, img_feats, point_feats, bboxes, prop_feats, pooler, img_metas, pooler_img=None, precision=None, lidar2img=None):
         bs, n_p = bboxes.shape[:2]
-        lidar2img = None
-        if img_feats is not None:
+        if img_feats is not None and lidar2img is None:
             import numpy as np
             lidar2img = torch.as_tensor(np.asarray([m['lidar2img'] for m in img_metas]), dtype=torch.float32,
                                         device=bboxes.device)

@@ -84,6 +84,8 @@ MIDDLE_ENCODERS = Registry('middle_encoder')
 ROI_EXTRACTORS = Registry('roi_extractor')
 HEADS = Registry('head')
 NORM_LAYERS = Registry('norm_layer')
+BACKBONES = Registry('backbone')
+NECKS = Registry('neck')
 DETECTORS = Registry('detector')
 
 
@@ -97,6 +99,16 @@ def build_middle_encoder(cfg):
 
 def build_roi_extractor(cfg):
     return ROI_EXTRACTORS.build(cfg)
+
+
+def build_backbone(cfg):
+    cfg = dict(cfg)
+    cfg.pop('init_cfg', None)
+    return BACKBONES.build(cfg)
+
+
+def build_neck(cfg):
+    return NECKS.build(cfg)
 
 
 def build_head(cfg):

@@ -1,0 +1,226 @@
+"""SRFDetHead (mmdet3d_plugin/models/sparse_heads/srfdet_head.py:49-1340), inference path
+(SURVEY.md 8f rank 3): Dynamic Proposal Generation `_get_init_proposals` (:506-655), the cascade of
+`num_heads` single-head stages with box chaining `forward` (:371-498) and `get_bboxes` decoding
+(:1228-1340) -- same registry name, constructor arguments and state-dict keys, so the reference
+configs and checkpoints load unchanged.  Everything per frame runs on this library's kernels and
+is free of host synchronisation (the whole head captures into one CUDA graph); training-only
+members (losses, assigners, samplers) are accepted and ignored.
+"""
+import copy
+import ctypes
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from . import registry
+from .bev_backbone import ConvModule
+from .head import _cached, _f
+from .registry import HEADS, build_head, build_roi_extractor
+from .voxel_encoder import fold_bn
+
+
+@HEADS.register_module()
+class SRFDetHead(nn.Module):
+    def __init__(self, use_img=False, num_classes=4, feat_channels_lidar=256, feat_channels_img=256, hidden_dim=128,
+                 lidar_feat_lvls=4, img_feat_lvls=4, num_proposals=128, num_heads=6, deep_supervision=True, prior_prob=0.01,
+                 is_kitti=False, with_lidar_encoder=False, grid_size=None, out_size_factor=8, lidar_encoder_cfg=None,
+                 code_weights=None, with_dpg=True, num_dpg_exp=4, single_head_lidar=None, single_head_img=None,
+                 roi_extractor_lidar=None, roi_extractor_img=None, sync_cls_avg_factor=True, loss_cls=None, loss_bbox=None,
+                 train_cfg=None, test_cfg=None, init_cfg=None, pretrained=None):
+        super().__init__()
+        if with_lidar_encoder:
+            raise NotImplementedError('with_lidar_encoder=True (deformable-attention BEV encoder) is not used by any reference config')
+        self.num_classes, self.use_img = num_classes, use_img
+        self.feat_channels_lidar, self.feat_channels_img, self.hidden_dim = feat_channels_lidar, feat_channels_img, hidden_dim
+        self.lidar_feat_lvls, self.img_feat_lvls = lidar_feat_lvls, img_feat_lvls
+        self.num_proposals, self.num_heads, self.deep_supervision = num_proposals, num_heads, deep_supervision
+        self.is_kitti = is_kitti
+        self.pc_range = single_head_lidar['pc_range']
+        self.test_cfg = dict(test_cfg or {})
+        self.with_dpg, self.num_dpg_exp = with_dpg, num_dpg_exp
+        self.grid_size, self.out_size_factor = grid_size, out_size_factor
+        dim = len(code_weights)
+        c = feat_channels_lidar
+        n_emb = (num_dpg_exp if with_dpg else 1) * num_proposals
+        self.init_proposal_boxes = nn.Embedding(n_emb, dim)
+        self.init_proposal_feats = nn.Embedding(n_emb, c)
+        if with_dpg:
+            bn2d = dict(type='BN2d', eps=1e-3, momentum=0.01)
+            self.dpg_dw_convs_lidar = nn.ModuleList([ConvModule(c * (l + 1), c * (l + 1), 3, stride=2, padding=1, groups=c * (l + 1), norm_cfg=bn2d)
+                                                     for l in range(lidar_feat_lvls - 1)])
+            last = [int(grid_size[j] / (out_size_factor * 2 ** (lidar_feat_lvls - 1))) for j in range(2)]
+            self.dpg_fc1_lidar = nn.Linear(last[0] * last[1], 1024)
+            self.dpg_fc2_lidar = nn.Linear(1024, num_dpg_exp * num_proposals)
+            if use_img:
+                self.dpg_dw_convs_img = nn.ModuleList([ConvModule(hidden_dim * (l + 1), hidden_dim * (l + 1), 3, stride=2, padding=1,
+                                                                  groups=hidden_dim * (l + 1), norm_cfg=bn2d) for l in range(img_feat_lvls - 1)])
+                self.last_imgfmap = (30, 15) if is_kitti else (30, 30)
+                self.dpg_fc1_img = nn.Linear(self.last_imgfmap[0] * self.last_imgfmap[1], 1500)
+                self.dpg_fc2_img = nn.Linear(1500, num_dpg_exp * num_proposals)
+        single = copy.deepcopy(dict(single_head_lidar))
+        single.update(num_classes=num_classes, feat_channels=feat_channels_lidar,
+                      pooler_resolution=roi_extractor_lidar['roi_layer'].get('output_size'), use_focal_loss=True, use_fed_loss=False,
+                      is_kitti=is_kitti)
+        proto = build_head(single)
+        self.head_series_lidar = nn.ModuleList([copy.deepcopy(proto) for _ in range(num_heads)])
+        self.roi_extractor_lidar = build_roi_extractor(roi_extractor_lidar)
+        self.roi_extractor_img = None
+        if use_img:
+            if hidden_dim != feat_channels_img:
+                # channel reduction of the image FPN maps (:151-162, :404-416): image-backbone side, plain torch conv
+                self.img_convs = nn.ModuleList([nn.Conv2d(feat_channels_img, hidden_dim, 3, padding=1) for _ in range(img_feat_lvls)])
+            self.roi_extractor_img = build_roi_extractor(roi_extractor_img)
+        self.code_weights = nn.Parameter(torch.tensor(code_weights, dtype=torch.float32), requires_grad=False)
+        self.use_nms = self.test_cfg.get('use_nms', True)
+        self.nms_fn = None      # rotated NMS is third-party (mmdet3d box3d_multiclass_nms): plug it in here when use_nms=True
+        self._cache = {}
+        self.eval()
+
+    # ------------------------------------------------------------------ Dynamic Proposal Generation
+    def _staircase(self, feats, convs, tag):
+        """pfeat_34 = cat(f3, dw2(cat(f2, dw1(cat(f1, dw0(f0)))))) (:521-533): returns (f_last, x3 map, h, w)."""
+        lib = L.load()
+        st = L.stream_ptr()
+        n = feats[0].shape[0]
+        x = None
+        for l, cm in enumerate(convs):
+            a = feats[l]
+            h, w = a.shape[2], a.shape[3]
+            src = [cm.conv.weight, cm.bn.weight, cm.bn.bias, cm.bn.running_mean, cm.bn.running_var]
+            wt, bias = _cached(self._cache, (tag, l, str(a.device)), src,
+                               lambda cm=cm, a=a: tuple(t.to(a.device).contiguous() for t in
+                                                        (fold_bn(cm.conv.weight, cm.bn)[0].flatten(1), fold_bn(cm.conv.weight, cm.bn)[1])))
+            cl = a.stride(1) == 1                     # torch.channels_last map -> channel-fastest kernel, channels_last result
+            ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            ctot = a.shape[1] + (x.shape[1] if x is not None else 0)
+            buf = torch.empty((n, ho, wo, ctot) if cl else (n, ctot, ho, wo), dtype=torch.float32, device=a.device)
+            ma = L.map_view(a)
+            mb = L.map_view(x) if x is not None else L.Map(None, 0, 0, 0, 0, 0)
+            L.check(lib.srf_dwconv3x3_s2(ctypes.byref(ma), ctypes.byref(mb), n, h, w, L.ptr(wt), L.ptr(bias), 1, int(cl), L.ptr(buf), st),
+                    'srf_dwconv3x3_s2')
+            x = buf.permute(0, 3, 1, 2) if cl else buf
+        return feats[len(convs)], x
+
+    def _dpg_logits(self, feats, convs, fc1, fc2, tag, group=1, resize=None):
+        lib = L.load()
+        st = L.stream_ptr()
+        f_last, x = self._staircase(feats, convs, tag)
+        n_img, h, w = f_last.shape[0], f_last.shape[2], f_last.shape[3]
+        n_samples = n_img // group
+        ho, wo = resize if resize is not None else (h, w)
+        s = torch.empty((n_samples, ho * wo), dtype=torch.float32, device=f_last.device)
+        ma, mb = L.map_view(f_last), L.map_view(x)
+        L.check(lib.srf_channel_sum(ctypes.byref(ma), ctypes.byref(mb), n_samples, group, h, w, ho, wo, L.ptr(s), st), 'srf_channel_sum')
+        hid = torch.empty((n_samples, fc1.out_features), dtype=torch.float32, device=s.device)
+        L.check(lib.srf_gemv_f32(L.ptr(s), n_samples, fc1.in_features, L.ptr(_f(fc1.weight)), fc1.out_features, L.ptr(_f(fc1.bias)), 1,
+                                 L.ptr(hid), st), 'srf_gemv_f32')
+        out = torch.empty((n_samples, fc2.out_features), dtype=torch.float32, device=s.device)
+        L.check(lib.srf_gemv_f32(L.ptr(hid), n_samples, fc2.in_features, L.ptr(_f(fc2.weight)), fc2.out_features, L.ptr(_f(fc2.bias)), 0,
+                                 L.ptr(out), st), 'srf_gemv_f32')
+        return out          # (bs, n_exp * n_p)
+
+    def _get_init_proposals(self, img_feats, point_feats, sigmoid_centres=False):
+        """-> (boxes (bs, n_p, dim), feats (bs, n_p, C)).  sigmoid_centres=True additionally applies
+        `bboxes[..., :3].sigmoid()` of forward (:403) inside the mixing kernel."""
+        bs = point_feats[0].shape[0]
+        dev = point_feats[0].device
+        dim, c = self.init_proposal_boxes.weight.shape[1], self.feat_channels_lidar
+        eb, ef = _f(self.init_proposal_boxes.weight), _f(self.init_proposal_feats.weight)
+        if not self.with_dpg:
+            boxes = eb.unsqueeze(0).repeat(bs, 1, 1)
+            if sigmoid_centres:
+                boxes[..., :3] = boxes[..., :3].sigmoid()
+            return boxes, ef.unsqueeze(0).repeat(bs, 1, 1)
+        point_feats = [f.float() for f in point_feats]
+        la = self._dpg_logits(point_feats, self.dpg_dw_convs_lidar, self.dpg_fc1_lidar, self.dpg_fc2_lidar, 'dpg_l')
+        lb = None
+        if self.use_img:
+            flat = [f.float().reshape(-1, *f.shape[2:]) if f.dim() == 5 else f.float() for f in img_feats]     # (bs*n_cam, C, H, W)
+            n_cam = flat[0].shape[0] // bs
+            lb = self._dpg_logits(flat, self.dpg_dw_convs_img, self.dpg_fc1_img, self.dpg_fc2_img, 'dpg_i', group=n_cam,
+                                  resize=self.last_imgfmap)
+        boxes = torch.empty((bs, self.num_proposals, dim), dtype=torch.float32, device=dev)
+        feats = torch.empty((bs, self.num_proposals, c), dtype=torch.float32, device=dev)
+        L.check(L.load().srf_dpg_mix(L.ptr(la), L.ptr(lb), bs, self.num_dpg_exp, self.num_proposals, L.ptr(eb), dim, L.ptr(ef), c,
+                                     L.ptr(boxes), L.ptr(feats), 1 if sigmoid_centres else 0, L.stream_ptr()), 'srf_dpg_mix')
+        return boxes, feats
+
+    # ------------------------------------------------------------------ forward / decode
+    def _image_maps(self, img_feats):
+        if img_feats is None or not self.use_img:
+            return None
+        if self.hidden_dim != self.feat_channels_img and img_feats[0].shape[-3] == self.feat_channels_img:
+            out = []
+            for i, f in enumerate(img_feats):
+                bs, n_cam = f.shape[:2]
+                y = self.img_convs[i](f.reshape(bs * n_cam, *f.shape[2:]))
+                out.append(y.reshape(bs, n_cam, *y.shape[1:]))
+            return out
+        return list(img_feats)
+
+    @torch.no_grad()
+    def forward(self, img_feats, point_feats, img_metas=None, lidar2img=None, precision=None):
+        """img_feats: list of (bs, n_cam, C, H, W) | None; point_feats: list of (bs, C, H, W) BEV maps (NCHW or
+        torch.channels_last).  -> (pred_logits (#stages, bs, n_p, #cls), pred_bboxes (#stages, bs, n_p, dim)) with
+        absolute centres and log sizes, like the reference (:474-498).  lidar2img (n_cam,4,4) tensor may replace
+        img_metas[*]['lidar2img'] (keeps the call free of host work)."""
+        img_feats = self._image_maps(img_feats)
+        bboxes, prop = self._get_init_proposals(img_feats, point_feats, sigmoid_centres=True)
+        if self.use_img and lidar2img is None:
+            import numpy as np
+            lidar2img = torch.as_tensor(np.asarray([m['lidar2img'] for m in img_metas]), dtype=torch.float32, device=bboxes.device)
+        logits_all, boxes_all = [], []
+        for stage in self.head_series_lidar:
+            if self.use_img:
+                logits, pred, prop = stage(img_feats, point_feats, bboxes, prop, self.roi_extractor_lidar, img_metas,
+                                           pooler_img=self.roi_extractor_img, precision=precision, lidar2img=lidar2img)
+            else:
+                logits, pred, prop = stage(point_feats, bboxes, prop, self.roi_extractor_lidar, img_metas, precision=precision)
+            logits_all.append(logits)
+            boxes_all.append(pred)
+            bboxes = pred.clone()                  # :428 / :445 -- the stage mutates its input boxes in place
+        if not self.deep_supervision:
+            logits_all, boxes_all = logits_all[-1:], boxes_all[-1:]
+        logits_all, boxes_all = torch.stack(logits_all), torch.stack(boxes_all)
+        r = self.pc_range
+        span = boxes_all.new_tensor([r[3] - r[0], r[4] - r[1], r[5] - r[2]])
+        boxes_all[..., :3] = boxes_all[..., :3] * span + boxes_all.new_tensor(r[:3])
+        return logits_all, boxes_all
+
+    @torch.no_grad()
+    def decode(self, pred_logits, pred_bboxes):
+        """Last stage -> (scores (bs, n_p, #cls), boxes (bs, n_p, dim-1) [cx,cy,cz_bottom,w,l,h,yaw(,vx,vy)]) (:1245-1268)."""
+        logits, boxes = _f(pred_logits[-1]), _f(pred_bboxes[-1])
+        bs, n_p, dim = boxes.shape
+        scores = torch.empty_like(logits)
+        out = torch.empty((bs, n_p, dim - 1), dtype=torch.float32, device=boxes.device)
+        L.check(L.load().srf_decode_boxes(L.ptr(logits), logits.numel(), L.ptr(boxes), bs * n_p, dim, L.ptr(scores), L.ptr(out),
+                                          L.stream_ptr()), 'srf_decode_boxes')
+        return scores, out
+
+    @torch.no_grad()
+    def get_bboxes(self, pred_logits, pred_bboxes, img_metas=None):
+        """:1228-1340.  -> per sample [boxes (n, dim-1), scores (n,), labels (n,)]; boxes are wrapped in
+        img_metas[i]['box_type_3d'] when given."""
+        scores, boxes = self.decode(pred_logits, pred_bboxes)
+        cfg = self.test_cfg
+        results = []
+        for i in range(scores.shape[0]):
+            sc, bx = scores[i], boxes[i]
+            if self.use_nms:
+                if self.nms_fn is None:
+                    raise NotImplementedError('test_cfg.use_nms=True needs the third-party rotated NMS: set head.nms_fn = '
+                                              'lambda boxes, scores, cfg: (boxes, scores, labels)  (e.g. mmdet3d box3d_multiclass_nms)')
+                bx, sc, labels = self.nms_fn(bx, sc, cfg)
+            else:
+                sc, idx = sc.flatten(0, 1).topk(cfg['max_per_img'])
+                labels = idx % self.num_classes
+                bx = bx[idx // self.num_classes]
+            rng = torch.tensor(cfg['post_center_range'], device=sc.device)
+            mask = (bx[..., :3] >= rng[:3]).all(1) & (bx[..., :3] <= rng[3:]).all(1)
+            bx, sc, labels = bx[mask], sc[mask], labels[mask]
+            if img_metas is not None and 'box_type_3d' in img_metas[i]:
+                bx = img_metas[i]['box_type_3d'](bx, bx.shape[-1])
+            results.append([bx, sc, labels])
+        return results

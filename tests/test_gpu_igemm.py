@@ -44,7 +44,7 @@ def _run(m, k, n, enc_name='bf16', relu=False, ln=False, out='f32', seed=0, eps=
     out_enc = L.F32 if out == 'f32' else (enc if out == 'same' else {True: L.F16, False: L.BF16}[enc in (L.F16, L.F16X2)])
     o = torch.empty((m, L.enc_width(out_enc, n)), dtype=L.enc_torch_dtype(out_enc), device='cuda')
     epi = (1 if relu else 0) | (2 if ln else 0)
-    L.check(lib.srf_linear_tc(L.ptr(ae), enc, m, k, L.ptr(wp), n, L.ptr(bias), epi, L.ptr(lnw) if ln else None,
+    L.check(lib.srf_linear_tc(L.ptr(ae), enc, m, k, L.ptr(wp), n, L.ptr(bias), None, epi, L.ptr(lnw) if ln else None,
                               L.ptr(lnb) if ln else None, eps, L.ptr(o), out_enc, 1, st), 'linear')
     torch.cuda.synchronize()
     if L.enc_is_split(enc):
@@ -111,7 +111,7 @@ def test_linear_split_k(m, k, n, splits, enc):
     L.check(lib.srf_pack_linear_tc(L.ptr(w), n, k, e, L.ptr(wp), st), 'pack')
     eff = lib.srf_linear_splits_enc(k, e, splits)
     part = torch.empty((eff, m, n), dtype=torch.float32, device='cuda')
-    L.check(lib.srf_linear_tc(L.ptr(ae), e, m, k, L.ptr(wp), n, None, 0, None, None, 1e-5, L.ptr(part), L.F32, splits, st), 'linear')
+    L.check(lib.srf_linear_tc(L.ptr(ae), e, m, k, L.ptr(wp), n, None, None, 0, None, None, 1e-5, L.ptr(part), L.F32, splits, st), 'linear')
     if L.enc_is_split(e):
         ref = (a.double() @ w.double().t()).float()
     else:

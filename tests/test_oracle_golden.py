@@ -220,3 +220,58 @@ def test_pillar_vfe_golden(golden_dir, tag, kw):
     out = O.pillar_feature_net(params, z['voxels'], z['num_points'], z['coors'], [0.2, 0.2, 8],
                                [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], **kw)
     np.testing.assert_allclose(out, z[f'{tag}.out'], rtol=1e-5, atol=1e-5)
+
+
+def _head_inputs(z, tag):
+    """Parameters (large tensors regenerated from their hash seeds) and inputs of the srfdet_head fixture."""
+    from srfdet_b200 import synth
+    C = int(z['C'])
+    params = {k[len(tag) + 3:]: z[k] for k in z.files if k.startswith(tag + '.p.')}
+    for k in z.files:
+        if k.startswith(tag + '.big.'):
+            name = k[len(tag) + 5:]
+            seed, scale = z[k]
+            shape = {'dpg_fc2_lidar.weight': (4 * int(z['P']), 1024), 'dpg_fc1_img.weight': (1500, 900),
+                     'dpg_fc2_img.weight': (4 * int(z['P']), 1500)}[name]
+            params[name] = synth.hash_field(shape, int(seed)) * np.float32(scale)
+    pf = [synth.hash_field((1, C, 32 // 2 ** i, 32 // 2 ** i), int(z['feat_seed']) + i) for i in range(4)]
+    imf = [synth.hash_field((1, 6, C, 232 // 2 ** i, 400 // 2 ** i), int(z['ifeat_seed']) + i) for i in range(4)] if tag == 'fusion' else None
+    cfg = dict(pc_range=z['pc_range'].tolist(), voxel_size=z['voxel_size'].tolist(), C=C, strides=[8, 16, 32, 64], istrides=[4, 8, 16, 32],
+               attn_heads=2, d=4, n_cls=2, n_reg=3, bbox_weights=[1.0] * 8 + [0.2, 0.2], scale_clamp=float(np.log(100000.0 / 16)),
+               n_exp=4, n_p=int(z['P']), stages=int(z['stages']))
+    return params, pf, imf, cfg
+
+
+@pytest.mark.parametrize('tag', ['lidar', 'fusion'])
+def test_srfdet_head_golden(golden_dir, tag):
+    """Oracle restatement of SRFDetHead (DPG, chained stages, decode) vs the reference's own outputs."""
+    z = _load(golden_dir, 'srfdet_head.npz')
+    params, pf, imf, cfg = _head_inputs(z, tag)
+    b0, f0 = O.dpg_init_proposals(params, imf, pf, cfg['n_exp'], cfg['n_p'], imf is not None)
+    np.testing.assert_allclose(b0, z[f'{tag}.init_boxes'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(f0, z[f'{tag}.init_feats'], rtol=1e-4, atol=1e-5)
+    logits, boxes = O.srfdet_head_forward(params, imf, pf, z['lidar2img'], cfg)
+    # (fusion: one proposal's image rectangle sits within float rounding of a RoIAlign sampling threshold in the
+    # C loop vs torchvision -- same effect as tests/test_gpu_roi_head.py::test_img_roi_production_size_vs_oracle)
+    tol = 2e-4 if tag == 'lidar' else 1e-3
+    np.testing.assert_allclose(logits, z[f'{tag}.logits'], rtol=0, atol=tol)
+    np.testing.assert_allclose(boxes, z[f'{tag}.boxes'], rtol=0, atol=tol)
+    scores, dec = O.decode_boxes(logits[-1], boxes[-1])
+    sc, idx = torch.as_tensor(scores[0]).flatten().topk(20)
+    bx = torch.as_tensor(dec[0])[idx // 10]
+    rng = torch.tensor([-40.0, -40.0, -10.0, 40.0, 40.0, 10.0])
+    m = (bx[:, :3] >= rng[:3]).all(1) & (bx[:, :3] <= rng[3:]).all(1)
+    np.testing.assert_array_equal((idx % 10)[m].numpy(), z[f'{tag}.det_labels'])
+    np.testing.assert_allclose(bx[m].numpy(), z[f'{tag}.det_boxes'], rtol=0, atol=tol)
+    np.testing.assert_allclose(sc[m].numpy(), z[f'{tag}.det_scores'], rtol=0, atol=1e-5)
+
+
+def test_second_fpn_golden(golden_dir):
+    """Oracle SECONDCustom (reference-owned forward) + FPN restatement vs the fixture."""
+    z = _load(golden_dir, 'second_fpn.npz')
+    feats = O.second_custom({k[2:]: z[k] for k in z.files if k.startswith('b.')}, z['x'], [2, 2], [1, 2])
+    for i, f in enumerate(feats):
+        np.testing.assert_allclose(f, z[f'feat{i}'], rtol=0, atol=1e-5)
+    outs = O.fpn({k[2:]: z[k] for k in z.files if k.startswith('n.')}, feats, 4)
+    for i, o in enumerate(outs):
+        np.testing.assert_allclose(o, z[f'out{i}'], rtol=0, atol=1e-5)
