@@ -62,6 +62,21 @@ def region_stages(state, geom, d, strides=(8, 16, 32, 64), istrides=(4, 8, 16, 3
     return prop
 
 
+def full_chain(state, bev):
+    """SECONDCustom -> FPN -> SRFDetHead (DPG, chained stages) -> decode on the dense BEV map (scope 'full')."""
+    cfg = state['head_cfg']
+    feats = O.second_custom(state['backbone'], bev, [5, 5], [1, 2])
+    pyramid = O.fpn(state['neck'], feats, 4, extra_convs=cfg['extra_convs'])
+    img = state.get('img_feats')
+    l2i = state['lidar2img'][None] if img is not None else None
+    logits, boxes = O.srfdet_head_forward(state['head'], img, pyramid, l2i, cfg)
+    scores, dec = O.decode_boxes(logits[-1], boxes[-1])
+    return np.concatenate([dec[0], scores[0]], axis=1), dict(pyramid=pyramid, logits=logits, boxes=boxes)
+
+
 def run_frame(state, kind, geom, d, points):
     torch.set_num_threads(max(1, torch.get_num_threads()))
-    return encode(state, kind, geom, points), region_stages(state, geom, d)
+    bev = encode(state, kind, geom, points)
+    if state.get('scope') == 'full':
+        return bev, full_chain(state, bev)[0]
+    return bev, region_stages(state, geom, d)

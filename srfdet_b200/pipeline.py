@@ -1,6 +1,13 @@
 """Frame pipeline of the measured hot path (BASELINE.json metric: frames/s of
 voxelize + SparseEncoder + region fusion), assembled from the drop-in modules.
 
+Two scopes:
+  scope='full' (default): the reference's whole LiDAR(+camera) forward after the image backbone --
+      points -> Voxelization (+VFE) -> SparseEncoderCustom -> SECONDCustom -> FPN -> SRFDetHead (Dynamic
+      Proposal Generation, 5 CHAINED stages: RoI sampling on the REAL FPN maps [+ 6-camera image RoIs + fusion],
+      self-attention, DynamicConv, FFN, towers, apply_deltas feeding the next stage's boxes) -> decode.
+  scope='path': the round-1 definition (SURVEY.md 8a rows only), kept for continuity:
+
 One frame =
   points (N,C) --Voxelization(+HardSimpleVFE | DynamicVFECustom)--> voxel features
          --SparseEncoderCustom--> dense BEV map (1, 256, H, W)
@@ -60,12 +67,67 @@ MODEL_CFG = {
 }
 
 HEAD_CFG = {  # feat channels C, dynamic dim d, BEV base size, box dims (Appendix A of SURVEY.md)
-    'nusc': dict(C=128, d=32, bev_hw=(184, 184), box_dim=10),
-    'waymo': dict(C=128, d=32, bev_hw=(192, 192), box_dim=8),
-    'kitti': dict(C=256, d=64, bev_hw=(200, 176), box_dim=8),
+    'nusc': dict(C=128, d=32, bev_hw=(184, 184), box_dim=10, ff=512, grid=[1472, 1472, 40], classes=10),
+    'waymo': dict(C=128, d=32, bev_hw=(192, 192), box_dim=8, ff=512, grid=[1536, 1536, 40], classes=3),
+    'kitti': dict(C=256, d=64, bev_hw=(200, 176), box_dim=8, ff=1024, grid=[1600, 1408, 40], classes=3),
 }
+
+
+def backbone_cfg(kind):
+    """pts_backbone / pts_neck / bbox_head of the reference configs (configs/nus/srfdet_voxel_nusc_L.py:55-141,
+    configs/nus/srfdet_voxel_nusc_LC.py:84-179, configs/waymo/srfdet_dvoxel_waymo_L.py:60-152,
+    configs/kitti/srfdet_voxel_kitti_L.py:65-160)."""
+    h = HEAD_CFG[kind]
+    neck = dict(type='FPN', norm_cfg=dict(type='BN2d', eps=1e-3, momentum=0.01), act_cfg=dict(type='ReLU'), in_channels=[128, 256],
+                out_channels=h['C'], start_level=0, num_outs=4)
+    if kind != 'kitti':
+        neck['add_extra_convs'] = 'on_output'
+    return dict(pts_backbone=dict(type='SECONDCustom', in_channels=256, out_channels=[128, 256], layer_nums=[5, 5], layer_strides=[1, 2],
+                                  norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), conv_cfg=dict(type='Conv2d', bias=False)),
+                pts_neck=neck)
+
+
+def head_cfg(kind, fusion):
+    h = HEAD_CFG[kind]
+    layer = MODEL_CFG[kind]['pts_voxel_layer']
+    wts = [1.0] * 8 + ([0.2, 0.2] if h['box_dim'] == 10 else [])
+    single = dict(type='SingleSRFDetHead' if fusion else 'SingleSRFDetHeadLiDAR', num_cls_convs=2, num_reg_convs=3, dim_feedforward=h['ff'],
+                  num_heads=8, dropout=0.1, act_cfg=dict(type='ReLU', inplace=True), dynamic_conv=dict(dynamic_dim=h['d'], dynamic_num=2),
+                  pc_range=layer['point_cloud_range'], voxel_size=layer['voxel_size'], bbox_weights=wts)
+    if fusion:
+        single['use_fusion'] = True
+    roi = lambda strides: dict(type='SingleRoIExtractor', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                               out_channels=h['C'], featmap_strides=strides)
+    return dict(type='SRFDetHead', use_img=fusion, num_classes=h['classes'], feat_channels_lidar=h['C'], feat_channels_img=256,
+                hidden_dim=128, lidar_feat_lvls=4, img_feat_lvls=4, num_proposals=N_PROP, num_heads=N_STAGES, deep_supervision=True,
+                with_lidar_encoder=False, grid_size=h['grid'], out_size_factor=8, code_weights=wts, with_dpg=True, num_dpg_exp=4,
+                single_head_lidar=single, roi_extractor_lidar=roi([8, 16, 32, 64]), roi_extractor_img=roi([4, 8, 16, 32]),
+                test_cfg=dict(use_nms=False, max_per_img=300, post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]))
 N_STAGES = 5
 N_PROP = 900
+
+
+def init_synthetic_head(head, seed):
+    """Synthetic weights of SRFDetHead (no checkpoints offline): default torch inits, then (a) proposal embeddings spread over
+    the range with car-like log sizes, (b) box-delta projections scaled down so five chained refinements stay in range."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        w = head.init_proposal_boxes.weight
+        w[:, :3] = torch.randn(w.shape[0], 3, generator=g) * 1.2
+        w[:, 3:6] = torch.log(torch.tensor([1.9, 4.6, 1.7])) + torch.randn(w.shape[0], 3, generator=g) * 0.3
+        w[:, 6:8] = torch.nn.functional.normalize(torch.randn(w.shape[0], 2, generator=g), dim=1)
+        for st in head.head_series_lidar:
+            st.bboxes_delta_lidar.weight.mul_(0.05)
+            st.bboxes_delta_lidar.bias.zero_()
+
+
+def init_synthetic_backbone(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in module.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                fan_in = m.in_channels // m.groups * m.kernel_size[0] * m.kernel_size[1]
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)
 
 
 def _randomize_bn(module, seed):
@@ -83,7 +145,10 @@ class RegionFeaturePipeline:
     projection of srfdet_voxel_nusc_LC.  Weights: torch.manual_seed(0) random init with
     non-trivial BatchNorm statistics (no checkpoints offline)."""
 
-    def __init__(self, kind='nusc', fusion=False, device='cuda', precision=None, seed=0, channels_last=True, use_graph=False):
+    def __init__(self, kind='nusc', fusion=False, device='cuda', precision=None, seed=0, channels_last=True, use_graph=False,
+                 scope='path'):
+        assert scope in ('path', 'full')
+        self.scope = scope
         self.kind, self.fusion, self.device = kind, fusion, torch.device(device)
         self.use_graph = use_graph
         self._graphs = {}
@@ -118,11 +183,36 @@ class RegionFeaturePipeline:
         self.stage_boxes = [torch.as_tensor(synth.proposals(seed + 20 + s, N_PROP, self.box_dim, 1)).to(self.device)
                             for s in range(N_STAGES)]
         self.prop0 = (torch.randn(N_PROP, self.C, generator=torch.Generator().manual_seed(seed + 30))).to(self.device)
+        self.backbone = self.neck = self.head = None
+        self.last = None
+        if scope == 'full':
+            from .plugin import registry as R
+            torch.manual_seed(seed + 40)
+            cfg = backbone_cfg(kind)
+            self.backbone = R.build_backbone(cfg['pts_backbone'])
+            self.neck = R.build_neck(cfg['pts_neck'])
+            self.head = R.build_head(head_cfg(kind, fusion))
+            init_synthetic_backbone(self.backbone, seed + 41)
+            init_synthetic_backbone(self.neck, seed + 42)
+            init_synthetic_head(self.head, seed + 43)
+            for i, m in enumerate((self.backbone, self.neck, self.head)):
+                _randomize_bn(m, seed + 44 + i)
+            self.backbone, self.neck, self.head = [m.to(self.device).eval() for m in (self.backbone, self.neck, self.head)]
 
     def state(self):
         """Weights / synthetic inputs as numpy, for the CPU oracle."""
         sd = lambda m: {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
-        return dict(encoder=sd(self.detector.pts_middle_encoder),
+        full = {}
+        if self.scope == 'full':
+            h = HEAD_CFG[self.kind]
+            layer = MODEL_CFG[self.kind]['pts_voxel_layer']
+            full = dict(backbone=sd(self.backbone), neck=sd(self.neck), head=sd(self.head),
+                        head_cfg=dict(pc_range=layer['point_cloud_range'], voxel_size=layer['voxel_size'], C=self.C, strides=[8, 16, 32, 64],
+                                      istrides=[4, 8, 16, 32], attn_heads=8, d=self.d, n_cls=2, n_reg=3,
+                                      bbox_weights=[1.0] * 8 + ([0.2, 0.2] if self.box_dim == 10 else []),
+                                      scale_clamp=float(np.log(100000.0 / 16)), n_exp=4, n_p=N_PROP, stages=N_STAGES,
+                                      extra_convs=self.kind != 'kitti'))
+        return dict(scope=self.scope, **full, encoder=sd(self.detector.pts_middle_encoder),
                     vfe=sd(self.detector.pts_voxel_encoder),
                     dynconv=[sd(m) for m in self.dynconvs],
                     fuse=[sd(m) for m in self.fuse] if self.fusion else None,
@@ -198,8 +288,23 @@ class RegionFeaturePipeline:
         return prop
 
     @torch.no_grad()
+    def full_chain(self, bev):
+        """dense BEV map -> SECONDCustom -> FPN -> SRFDetHead (DPG, chained stages) -> decode.
+        Returns the last stage's object features; logits / boxes / decoded results in self.last."""
+        from .plugin.bev_backbone import nchw_to_rows, _tc_enc
+        n, c, h, w = bev.shape
+        feats = self.backbone.forward_rows(nchw_to_rows(bev, _tc_enc(self.precision)), n, h, w, self.precision)
+        pyramid = self.neck.forward_rows(feats, n, self.precision)
+        logits, boxes = self.head(self.img_feats if self.fusion else None, pyramid, None, lidar2img=self.lidar2img, precision=self.precision)
+        scores, dec = self.head.decode(logits, boxes)
+        self.last = dict(pyramid=pyramid, logits=logits, boxes=boxes, scores=scores, det_boxes=dec)
+        return torch.cat([dec[0], scores[0]], dim=1)          # (P, box_dim-1 + classes): what a caller post-processes
+
+    @torch.no_grad()
     def _run_frame_eager(self, points):
         bev = self.encode(points)
+        if self.scope == 'full':
+            return bev, self.full_chain(bev)
         return bev, self.region_stages()
 
     @torch.no_grad()
@@ -212,7 +317,7 @@ class RegionFeaturePipeline:
         overwrites."""
         if not self.use_graph:
             return self._run_frame_eager(points)
-        key = (tuple(points.shape), self.precision)
+        key = (tuple(points.shape), self.precision, self.scope)
         g = self._graphs.get(key)
         if g is None:
             static_in = torch.empty_like(points)
@@ -236,7 +341,7 @@ class RegionFeaturePipeline:
     @torch.no_grad()
     def run_frame_host(self, points_pinned):
         """Public end-to-end call: HOST (pinned) points in, HOST region features out."""
-        key = (tuple(points_pinned.shape), self.precision)
+        key = (tuple(points_pinned.shape), self.precision, self.scope)
         if self.use_graph and key in self._graphs:
             pts = self._graphs[key][1]                      # H2D straight into the graph's input buffer
             pts.copy_(points_pinned, non_blocking=True)

@@ -1,0 +1,210 @@
+"""Rows f1-f3 of SURVEY.md 8 on CUDA: dense BEV backbone + neck (SECONDCustom, FPN), the kernel-based
+stage tail (attention, FFN, towers, apply_deltas), Dynamic Proposal Generation, the chained stage
+loop of SRFDetHead.forward and the get_bboxes decode -- against the fixtures produced by the
+reference's own Python (tests/golden/make_golden_r2.py) and against torch / the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from srfdet_b200 import synth
+from test_oracle_golden import _head_inputs
+from util import cuda, randomize_bn_, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _z(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ---------------------------------------------------------------------------------------- f1
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('fp16', 1e-2)])
+def test_second_fpn_golden(golden_dir, precision, tol):
+    from srfdet_b200.plugin import FPN, SECONDCustom
+    z = _z(golden_dir, 'second_fpn.npz')
+    net = SECONDCustom(in_channels=32, out_channels=[16, 32], layer_nums=[2, 2], layer_strides=[1, 2],
+                       norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), conv_cfg=dict(type='Conv2d', bias=False)).eval()
+    net.load_state_dict({k[2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith('b.')}, strict=True)
+    neck = FPN(in_channels=[16, 32], out_channels=16, num_outs=4, start_level=0, add_extra_convs='on_output',
+               norm_cfg=dict(type='BN2d', eps=1e-3, momentum=0.01), act_cfg=dict(type='ReLU')).eval()
+    sd = {k[2:]: torch.as_tensor(z[k]) for k in z.files if k.startswith('n.')}
+    for k in list(neck.state_dict()):
+        if k.endswith('num_batches_tracked'):
+            sd[k] = neck.state_dict()[k]
+    neck.load_state_dict(sd, strict=True)
+    feats = net.cuda()(cuda(z['x']), precision=precision)
+    for i, f in enumerate(feats):
+        assert f.shape == z[f'feat{i}'].shape
+        assert rel_err(f.cpu().numpy(), z[f'feat{i}']) < tol
+    outs = neck.cuda()(feats, precision=precision)
+    assert len(outs) == 4
+    for i, o in enumerate(outs):
+        assert o.shape == z[f'out{i}'].shape
+        assert o.is_contiguous(memory_format=torch.channels_last) or o.shape[1] == 1
+        assert rel_err(o.cpu().numpy(), z[f'out{i}']) < tol * 2
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('fp16', 1e-2)])
+def test_second_fpn_production_dims_vs_torch(precision, tol):
+    """configs/nus/srfdet_voxel_nusc_L.py:55-75 dims (256 -> [128, 256] @ 184^2 / 92^2, FPN 128 x 4 levels) on a sparse
+    184 x 184 map vs torch conv2d fp32 (cuDNN with TF32 disabled)."""
+    from srfdet_b200.plugin import FPN, SECONDCustom
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    net = SECONDCustom(in_channels=256, out_channels=[128, 256], layer_nums=[5, 5], layer_strides=[1, 2],
+                       norm_cfg=dict(type='BN', eps=1e-3, momentum=0.01), conv_cfg=dict(type='Conv2d', bias=False)).eval()
+    neck = FPN(in_channels=[128, 256], out_channels=128, num_outs=4, start_level=0, add_extra_convs='on_output',
+               norm_cfg=dict(type='BN2d', eps=1e-3, momentum=0.01), act_cfg=dict(type='ReLU')).eval()
+    for m in list(net.modules()) + list(neck.modules()):
+        if isinstance(m, torch.nn.Conv2d):
+            torch.nn.init.kaiming_normal_(m.weight, nonlinearity='relu')
+    randomize_bn_(net, 4)
+    randomize_bn_(neck, 5)
+    net, neck = net.cuda(), neck.cuda()
+    g = torch.Generator().manual_seed(6)
+    x = (torch.randn(1, 256, 184, 184, generator=g) * (torch.rand(1, 1, 184, 184, generator=g) < 0.4)).cuda()
+    with torch.no_grad():
+        ref, t = [], x
+        for blk in net.blocks:
+            t = blk(t)
+            ref.append(t)
+        sd = {k: v.cpu().numpy() for k, v in neck.state_dict().items()}
+        ref_outs = O.fpn(sd, [r.cpu().numpy() for r in ref], 4)
+    feats = net(x, precision=precision)
+    for f, r in zip(feats, ref):
+        assert rel_err(f.cpu().numpy(), r.cpu().numpy()) < tol
+    outs = neck(feats, precision=precision)
+    assert [tuple(o.shape) for o in outs] == [(1, 128, 184, 184), (1, 128, 92, 92), (1, 128, 46, 46), (1, 128, 23, 23)]
+    for o, r in zip(outs, ref_outs):
+        assert rel_err(o.cpu().numpy(), r) < tol * 2
+
+
+# ---------------------------------------------------------------------------------------- f2
+@pytest.mark.parametrize('c,heads,n_p,bs', [(128, 8, 900, 1), (256, 8, 300, 2), (16, 2, 24, 1)])
+def test_mha_attention_vs_torch(c, heads, n_p, bs):
+    from srfdet_b200 import _lib as L
+    torch.manual_seed(0)
+    mha = torch.nn.MultiheadAttention(c, heads).cuda().eval()
+    x = torch.randn(n_p, bs, c, device='cuda')
+    with torch.no_grad():
+        ref = mha(x, x, value=x)[0]                                             # (n_p, bs, c)
+        rows = x.permute(1, 0, 2).reshape(bs * n_p, c).contiguous()
+        qkv = torch.nn.functional.linear(rows, mha.in_proj_weight, mha.in_proj_bias).contiguous()
+        att = torch.empty((bs * n_p, c), device='cuda')
+        L.check(L.load().srf_mha_attention(L.ptr(qkv), bs, n_p, heads, c // heads, L.ptr(att), L.F32, L.stream_ptr()), 'attn')
+        got = torch.nn.functional.linear(att, mha.out_proj.weight, mha.out_proj.bias).view(bs, n_p, c).permute(1, 0, 2)
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('fp32_simt', 2e-4), ('fp16', 1e-2)])
+def test_stage_tail_kernels_vs_torch(precision, tol):
+    """Production dims (900 proposals, C 128, d 32, ff 512, 8 heads): the kernel path of a whole stage
+    (attention, interaction, FFN, towers, projections, apply_deltas) vs the same rows as torch ops."""
+    from srfdet_b200.plugin import SingleSRFDetHeadLiDAR
+    pc, vs = [-55.2, -55.2, -5.0, 55.2, 55.2, 3.0], [0.075, 0.075, 0.2]
+    torch.manual_seed(2)
+    head = SingleSRFDetHeadLiDAR(num_classes=10, feat_channels=128, dim_feedforward=512, num_cls_convs=2, num_reg_convs=3, num_heads=8,
+                                 dropout=0.1, dynamic_conv=dict(dynamic_dim=32, dynamic_num=2), pc_range=pc, voxel_size=vs).eval().cuda()
+    with torch.no_grad():
+        head.bboxes_delta_lidar.weight.mul_(0.1)
+    g = torch.Generator().manual_seed(3)
+    roi = torch.randn(900, 49, 128, generator=g).cuda()
+    prop = torch.randn(1, 900, 128, generator=g).cuda()
+    boxes = cuda(synth.proposals(4, 900, 10, 1))
+    boxes[..., :3] = boxes[..., :3] * boxes.new_tensor([110.4, 110.4, 8.0]) + boxes.new_tensor(pc[:3])     # absolute centres
+    with torch.no_grad():
+        ref = head._stage_tail_torch(roi, boxes, prop, 1, 900, 'fp32_simt')
+        got = head._stage_tail(roi, boxes, prop, 1, 900, precision)
+    for a, b, name in zip(got, ref, ('logits', 'pred', 'obj')):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < tol, name
+
+
+# ---------------------------------------------------------------------------------------- f3
+def _build_head(z, tag):
+    from srfdet_b200.plugin import SRFDetHead
+    params, pf, imf, cfg = _head_inputs(z, tag)
+    use_img = tag == 'fusion'
+    C = cfg['C']
+    single = dict(type='SingleSRFDetHead' if use_img else 'SingleSRFDetHeadLiDAR', num_cls_convs=2, num_reg_convs=3, dim_feedforward=32,
+                  num_heads=2, dropout=0.1, act_cfg=dict(type='ReLU', inplace=True), dynamic_conv=dict(dynamic_dim=4, dynamic_num=2),
+                  pc_range=cfg['pc_range'], voxel_size=cfg['voxel_size'])
+    if use_img:
+        single['use_fusion'] = True
+    head = SRFDetHead(use_img=use_img, num_classes=10, feat_channels_lidar=C, feat_channels_img=C, hidden_dim=C, lidar_feat_lvls=4,
+                      img_feat_lvls=4, num_proposals=cfg['n_p'], num_heads=cfg['stages'], deep_supervision=True, grid_size=[256, 256, 40],
+                      out_size_factor=8, code_weights=[1.0] * 8 + [0.2, 0.2], with_dpg=True, num_dpg_exp=4, single_head_lidar=single,
+                      roi_extractor_lidar=dict(type='SingleRoIExtractor', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                               out_channels=C, featmap_strides=[8, 16, 32, 64]),
+                      roi_extractor_img=dict(type='SingleRoIExtractor', roi_layer=dict(type='RoIAlign', output_size=7, sampling_ratio=2),
+                                             out_channels=C, featmap_strides=[4, 8, 16, 32]),
+                      test_cfg=dict(use_nms=False, max_per_img=20, post_center_range=[-40.0, -40.0, -10.0, 40.0, 40.0, 10.0]))
+    missing, unexpected = head.load_state_dict({k: torch.as_tensor(v) for k, v in params.items()}, strict=True)
+    return head.cuda(), pf, imf, cfg
+
+
+@pytest.mark.parametrize('tag', ['lidar', 'fusion'])
+@pytest.mark.parametrize('maps_cl', [False, True])
+def test_srfdet_head_golden(golden_dir, tag, maps_cl):
+    """SRFDetHead: _get_init_proposals, the chained 3-stage forward and the get_bboxes decode vs the reference's outputs
+    (the reference's state dict loads with strict=True)."""
+    z = _z(golden_dir, 'srfdet_head.npz')
+    head, pf, imf, cfg = _build_head(z, tag)
+    pf = [cuda(f) for f in pf]
+    imf = [cuda(f) for f in imf] if imf is not None else None
+    if maps_cl:
+        pf = [f.contiguous(memory_format=torch.channels_last) for f in pf]
+        imf = [f[0].contiguous(memory_format=torch.channels_last).unsqueeze(0) for f in imf] if imf is not None else None
+    b0, f0 = head._get_init_proposals(imf, pf)
+    np.testing.assert_allclose(b0.cpu().numpy(), z[f'{tag}.init_boxes'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(f0.cpu().numpy(), z[f'{tag}.init_feats'], rtol=1e-4, atol=1e-5)
+    metas = [dict(lidar2img=z['lidar2img'][0])]
+    tol = 3e-4 if tag == 'lidar' else 1e-3
+    logits, boxes = head(imf, pf, metas, precision='fp32')
+    np.testing.assert_allclose(logits.cpu().numpy(), z[f'{tag}.logits'], rtol=0, atol=tol)
+    np.testing.assert_allclose(boxes.cpu().numpy(), z[f'{tag}.boxes'], rtol=0, atol=tol)
+    res = head.get_bboxes(logits, boxes)
+    np.testing.assert_array_equal(res[0][2].cpu().numpy(), z[f'{tag}.det_labels'])
+    np.testing.assert_allclose(res[0][0].cpu().numpy(), z[f'{tag}.det_boxes'], rtol=0, atol=tol)
+    np.testing.assert_allclose(res[0][1].cpu().numpy(), z[f'{tag}.det_scores'], rtol=0, atol=1e-5)
+    # the 16-bit mode of the same chain stays within its tolerance of the reference's boxes
+    lg16, bx16 = head(imf, pf, metas, precision='fp16')
+    # (fusion fixture: one proposal's image rectangle sits on a RoIAlign sampling threshold, see test_oracle_golden.py)
+    assert rel_err(bx16.cpu().numpy(), z[f'{tag}.boxes']) < 1e-2
+    assert rel_err(lg16.cpu().numpy(), z[f'{tag}.logits']) < (1e-2 if tag == 'lidar' else 2e-2)
+
+
+# ---------------------------------------------------------------------------------------- whole chain
+@pytest.mark.parametrize('kind,fusion', [('nusc', False), ('nusc', True), ('waymo', False), ('kitti', False)])
+@pytest.mark.parametrize('n_points', [30000, 0])
+def test_full_chain_vs_oracle(kind, fusion, n_points):
+    """points -> voxelize -> SparseEncoder -> SECONDCustom -> FPN -> DPG -> 5 CHAINED stages -> decode of every BASELINE
+    config (n_points = 0: the configuration's full cloud) vs the CPU oracle: BEV map, FPN pyramid, logits and boxes of
+    all stages.  Box tolerances: centres as a fraction of the range, log sizes / sin / cos / velocity absolute."""
+    from oracle import cpu_pipeline
+    from srfdet_b200.pipeline import RegionFeaturePipeline
+    pipe = RegionFeaturePipeline(kind, fusion=fusion, precision='fp32', scope='full')
+    pts = synth.cloud(kind, 43, n_points=n_points or None)
+    state = pipe.state()
+    ref_bev = cpu_pipeline.encode(state, kind, synth.GEOM[kind], pts)
+    ref_out, ref = cpu_pipeline.full_chain(state, ref_bev)
+    pc = synth.GEOM[kind]['pc_range']
+    span = np.array([pc[3] - pc[0], pc[4] - pc[1], pc[5] - pc[2]], np.float32)
+    for precision, tol in [('fp32', 1e-4), ('fp16', 1e-2)]:
+        pipe.precision = precision
+        bev, out = pipe.run_frame(cuda(pts))
+        last = pipe.last
+        assert rel_err(bev.cpu().numpy(), ref_bev) < tol, precision
+        for lvl in range(4):
+            assert rel_err(last['pyramid'][lvl].cpu().numpy(), ref['pyramid'][lvl]) < tol * 2, (precision, lvl)
+        # five chained LayerNorm-normalised stages on top of RoI geometry (exp / atan2 / sin / cos differ in the last
+        # ulp between CUDA and libm): logits and boxes get 5x the feature tolerance in the FP32 mode
+        t_chain = 5e-4 if precision == 'fp32' else 1e-2
+        assert rel_err(last['logits'].cpu().numpy(), ref['logits']) < t_chain, precision
+        gb, rb = last['boxes'].cpu().numpy(), ref['boxes']
+        assert (np.abs(gb[..., :3] - rb[..., :3]) / span).max() < t_chain, precision
+        assert np.abs(gb[..., 3:] - rb[..., 3:]).max() < t_chain, precision
+        assert out.shape == ref_out.shape

@@ -26,11 +26,23 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
 
 
+def box_errors(last, ref, pc):
+    """Errors of the chained head outputs: FPN level 0, logits of all stages, boxes of all stages split into
+    centres (as a fraction of the range), log sizes and (sin, cos, v) -- absolute differences."""
+    span = np.array([pc[3] - pc[0], pc[4] - pc[1], pc[5] - pc[2]], np.float32)
+    gb, rb = last['boxes'].cpu().numpy(), ref['boxes']
+    return dict(fpn0=rel(last['pyramid'][0].cpu().numpy(), ref['pyramid'][0]), fpn3=rel(last['pyramid'][3].cpu().numpy(), ref['pyramid'][3]),
+                logits=rel(last['logits'].cpu().numpy(), ref['logits']),
+                centre_frac=float((np.abs(gb[..., :3] - rb[..., :3]) / span).max()), logsize_abs=float(np.abs(gb[..., 3:6] - rb[..., 3:6]).max()),
+                rest_abs=float(np.abs(gb[..., 6:] - rb[..., 6:]).max()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workloads', default='nusc_L,nusc_LC,waymo_L,kitti_L')
     ap.add_argument('--precisions', default='fp32,fp16,bf16,fp32_simt')
     ap.add_argument('--points', type=int, default=0, help='0 = the configuration\'s full cloud')
+    ap.add_argument('--scope', default='full', choices=['full', 'path'])
     ap.add_argument('--out', default=None)
     args = ap.parse_args()
     O.build_c()
@@ -38,10 +50,15 @@ def main():
     res = {}
     for wl in args.workloads.split(','):
         kind, fusion = WL[wl]
-        pipe = RegionFeaturePipeline(kind, fusion=fusion, precision='fp32')
+        pipe = RegionFeaturePipeline(kind, fusion=fusion, precision='fp32', scope=args.scope)
         pts = synth.cloud(kind, 1000, n_points=args.points or None)
         t0 = time.perf_counter()
-        ref_bev, ref_obj = cpu_pipeline.run_frame(pipe.state(), kind, synth.GEOM[kind], pipe.d, pts)
+        state = pipe.state()
+        ref_bev = cpu_pipeline.encode(state, kind, synth.GEOM[kind], pts)
+        if args.scope == 'full':
+            ref_obj, ref_x = cpu_pipeline.full_chain(state, ref_bev)
+        else:
+            ref_obj, ref_x = cpu_pipeline.region_stages(state, synth.GEOM[kind], pipe.d), None
         t_cpu = time.perf_counter() - t0
         res[wl] = dict(points=int(pts.shape[0]), oracle_s=round(t_cpu, 2))
         for prec in args.precisions.split(','):
@@ -51,6 +68,8 @@ def main():
             b, o = bev.cpu().numpy(), obj.cpu().numpy()
             res[wl][prec] = dict(bev=rel(b, ref_bev), obj=rel(o, ref_obj),
                                  bev_rms=float(np.sqrt(((b - ref_bev) ** 2).mean()) / np.sqrt((ref_bev ** 2).mean())))
+            if ref_x is not None:
+                res[wl][prec].update(box_errors(pipe.last, ref_x, synth.GEOM[kind]['pc_range']))
             print(wl, prec, res[wl][prec], flush=True)
     s = json.dumps(res, indent=1)
     if args.out:
