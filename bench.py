@@ -1,15 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- frames/s of the SRFDet3D point-cloud -> region-feature hot path on B200.
 
-  python bench.py --gpus N --steps K --warmup W [--workload nusc_L|nusc_LC|waymo_L|kitti_L]
+  python bench.py --gpus N --steps K --warmup W [--workload nusc_LC|nusc_L|waymo_L|kitti_L]
+                  [--scope full|path] [--precision fp16|fp32|bf16|fp32_simt] [--frames-in-flight F]
   torchrun ... bench.py --gpus N ...          (one rank per GPU; frames are independent)
   python bench.py --impl reference ...        (restated reference CPU path on the host cores)
 
-A step = ONE frame per rank: hard/dynamic voxelization (+VFE) -> SparseEncoder -> 5 stages
-of region fusion (BEV RoIAlign [+ 6-camera image RoIAlign + fusion Linear] -> DynamicConv).
+A step = F frames per rank (F = --frames-in-flight, default 1), each frame one pass of the hot path:
+  scope 'full' (default): hard/dynamic voxelization (+VFE) -> SparseEncoder -> SECOND + FPN -> Dynamic Proposal
+      Generation -> 5 CHAINED stages (BEV RoIAlign on the real FPN maps [+ 6-camera image RoIAlign + fusion Linear],
+      self-attention, DynamicConv, FFN, towers, apply_deltas -> next stage's boxes) -> decode;
+  scope 'path': the round-1 definition (voxelize -> SparseEncoder -> 5 stages of RoIAlign + DynamicConv on synthetic
+      FPN maps and fixed boxes), kept for continuity.
 `value` = frames/s over all ranks with the point clouds already resident in HBM;
-`e2e` = the same through the public host-buffer call (pinned host points in, host region
-features out, H2D + D2H inside the timed region).  Prints ONE JSON line on rank 0.
+`e2e` = the same through the public host-buffer call (pinned host points in, host results out, H2D + D2H inside
+the timed region).  Prints ONE JSON line on rank 0; the extra objects are described in DESIGN.md 6:
+`roofline` (dominant kernel), `kernels` (every kernel family of a frame, CUDA-event timed, with algorithmic
+bytes / flops and roofline fraction), `modes` (other precision / scope / workload settings, including the
+FP32-precision mode), `frames_in_flight_sweep` (BASELINE config 5 on one GPU), `cpu_baseline`.
 """
 import argparse
 import json
@@ -23,20 +31,28 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     'nusc_L': dict(kind='nusc', fusion=False, desc='srfdet_voxel_nusc_L: 300k-pt 10-sweep nuScenes-shaped cloud, hard voxelization '
-                   '0.075/0.075/0.2 m (1472x1472x41), 21-layer SparseEncoder, 900 proposals x 5 stages BEV RoIAlign + DynamicConv'),
-    'nusc_LC': dict(kind='nusc', fusion=True, desc='srfdet_voxel_nusc_LC: nusc_L + 6-view image RoIAlign (1600x928) + fusion Linear'),
+                   '0.075/0.075/0.2 m (1472x1472x41), 21-layer SparseEncoder, 900 proposals x 5 stages'),
+    'nusc_LC': dict(kind='nusc', fusion=True, desc='srfdet_voxel_nusc_LC: nusc_L + 6-view image RoIAlign (1600x928 views, 4 FPN levels) + fusion Linear'),
     'waymo_L': dict(kind='waymo', fusion=False, desc='srfdet_dvoxel_waymo_L: 180k-pt cloud, dynamic voxelization + DynamicVFE'),
     'kitti_L': dict(kind='kitti', fusion=False, desc='srfdet_voxel_kitti_L: 120k-pt cloud, dynamic voxelization + DynamicVFE, C=256 head'),
 }
+SCOPES = {
+    'full': 'voxelize -> SparseEncoder -> SECONDCustom + FPN -> DPG -> 5 chained stages (RoI sampling on the real FPN maps, attention, '
+            'DynamicConv, FFN, towers, apply_deltas) -> decode',
+    'path': 'voxelize -> SparseEncoder -> 5 stages of RoI sampling + DynamicConv on synthetic FPN maps and fixed boxes (round-1 definition)',
+}
+DTYPES = {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f16x2 (hi+lo split operands on tcgen05, 3 MMAs per product, fp32 accumulate: FP32-mode tolerance 1e-4)',
+          'fp32_simt': 'f32'}
 N_CLOUDS = 8
+METRIC = 'frames/s (voxelize+SparseEncoder+RoI fusion)'
 
 
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'], src='measured')
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'], src='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback (B200_PROFILING.md)')
 
 
 class ClockSampler:
@@ -89,80 +105,57 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
 
 
-def conv_roofline(pipe, pts, pk, torch):
-    """Per-launch CUDA-event timing of every sparse-conv launch of one frame (events on the
-    launching stream), with the ALGORITHMIC flops / bytes of each layer from its rulebook."""
+def kernel_families(pipe, pts, pk, torch, reps=3):
+    """CUDA-event timing of every C-ABI call of one eagerly launched frame (events on the launching stream, a spin
+    kernel hides the host's enqueue latency), grouped into kernel families with their ALGORITHMIC work."""
+    from srfdet_b200 import _lib as L
+    from srfdet_b200 import profiling
     enc = pipe.detector.pts_middle_encoder
     for _ in range(2):
-        pipe.encode(pts)
-    rows = None
-    reps = 5
-    for r in range(reps):
+        pipe._run_frame_eager(pts)
+    best = None
+    for _ in range(reps):
         enc.profile = []
-        # a spin kernel keeps the GPU busy while the host enqueues the whole encoder, so the events
-        # bracket kernel execution only (no host launch latency between an event and its kernel)
-        torch.cuda._sleep(30_000_000)
-        pipe.encode(pts)
-        torch.cuda.synchronize()
+        with profiling.capture() as cap:
+            torch.cuda._sleep(60_000_000)
+            pipe._run_frame_eager(pts)
+            torch.cuda.synchronize()
         prof, enc.profile = enc.profile, None
-        if rows is None:
-            rows = []
-            for e in prof:
-                n_out, n_in = int(e['n_out']), int(e['n_in'])
-                pairs = int((e['nbr'][:, :n_out] >= 0).sum())
-                flops = 2.0 * pairs * e['cin'] * e['cout']
-                byts = n_in * e['cin'] * e['in_bytes'] + n_out * e['cout'] * e['out_bytes'] + \
-                    e['kvol'] * e['cin'] * e['cout'] * e['in_bytes'] + 4.0 * e['kvol'] * n_out
-                rows.append(dict(layer=e['layer'], kernel='igemm_umma' if e['umma'] else 'spconv_f32', subm=e['subm'],
-                                 cin=e['cin'], cout=e['cout'], kvol=e['kvol'], n_in=n_in, n_out=n_out, pairs=pairs,
-                                 flops=flops, bytes=byts, ms=[]))
-        for row, e in zip(rows, prof):
-            row['ms'].append(e['start'].elapsed_time(e['end']))
-    for row in rows:
-        ms = sorted(row.pop('ms'))
-        row['ms'] = ms[len(ms) // 2]
-        row['tflops'] = row['flops'] / (row['ms'] * 1e-3) / 1e12
-        row['gbs'] = row['bytes'] / (row['ms'] * 1e-3) / 1e9
-    umma = [r for r in rows if r['kernel'] == 'igemm_umma']
-    tot_ms = sum(r['ms'] for r in umma)
-    tot_fl = sum(r['flops'] for r in umma)
-    # dominant kernel = the instantiation with the largest share of the step; its numbers are per-launch averages
-    groups = {}
-    for r in (umma or rows):
-        groups.setdefault((r['cin'], r['cout']), []).append(r)
-    key, grp = max(groups.items(), key=lambda kv: sum(r['ms'] for r in kv[1]))
-    n = len(grp)
-    ms = sum(r['ms'] for r in grp) / n
-    flops = sum(r['flops'] for r in grp) / n
-    byts = sum(r['bytes'] for r in grp) / n
-    tflops, gbs = flops / (ms * 1e-3) / 1e12, byts / (ms * 1e-3) / 1e9
-    # roofline side: arithmetic intensity against the ridge of the two measured peaks
-    ridge = pk['tf_sust'] * 1e12 / (pk['hbm'] * 1e9)
-    hbm_bound = flops / byts < ridge
-    name = f"igemm_umma_kernel<{key[0]},{key[1]}>"
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
-            t = json.load(f)['kernels'].get(name)
-        if t:
-            traffic = t['dram_read_bytes'] + t['dram_write_bytes']
-            traffic_src = 'profiles/r01_ncu_traffic.json (ncu --set full, dram read+write per launch, cold cache)'
-    except (OSError, ValueError, KeyError):
-        pass
-    roof = dict(bound='hbm' if hbm_bound else 'tensor',
-                kernel=f"{name} ({n} launches per frame: layers {[r['layer'] for r in grp]}, SubM k27, "
-                       f"{grp[0]['n_out']} rows, {grp[0]['pairs']} pairs)",
-                achieved=round(gbs if hbm_bound else tflops, 2), peak=pk['hbm'] if hbm_bound else pk['tf_sust'],
-                unit='GB/s' if hbm_bound else 'TFLOP/s',
-                frac=round(gbs / pk['hbm'] if hbm_bound else tflops / pk['tf_sust'], 4),
-                traffic=traffic, traffic_source=traffic_src,
-                peak_source=f"{pk['src']} {'HBM copy bandwidth' if hbm_bound else 'bf16 sustained'}", launch_ms=round(ms, 4),
-                algorithmic_flops_per_launch=flops, algorithmic_bytes_per_launch=byts,
-                arithmetic_intensity=round(flops / byts, 1), ridge=round(ridge, 1),
-                tensor_frac_of_same_launch=round(tflops / pk['tf_sust'], 4), hbm_frac_of_same_launch=round(gbs / pk['hbm'], 4),
-                share_of_step_ms=round(sum(r['ms'] for r in grp), 4),
-                all_umma_launches=dict(n=len(umma), ms=round(tot_ms, 4), tflops=round(tot_fl / (tot_ms * 1e-3) / 1e12, 2) if tot_ms else None))
-    return roof, rows
+        # sparse-conv work from the rulebooks, in call order
+        sparse = []
+        for e in prof:
+            n_out, n_in = int(e['n_out']), int(e['n_in'])
+            pairs = int((e['nbr'][:, :n_out] >= 0).sum())
+            es_in, es_out = e['in_bytes'], e['out_bytes']
+            sparse.append((2.0 * pairs * e['cin'] * e['cout'],
+                           n_in * e['cin'] * es_in + n_out * e['cout'] * es_out + e['kvol'] * e['cin'] * e['cout'] * es_in + 4.0 * e['kvol'] * n_out,
+                           dict(layer=e['layer'], n_in=n_in, n_out=n_out, pairs=pairs)))
+        it = iter(sparse)
+
+        def conv_work(s):
+            if s['kvol'] == 9:                                      # dense BEV conv: every in-bounds neighbour is a pair
+                rows = s['cap']
+                es = profiling.ES[s['in_enc']]
+                return 2.0 * rows * 9 * s['cin'] * s['cout'], s['in_rows'] * s['cin'] * es + rows * s['cout'] * profiling.ES[s['out_enc']] + 9 * s['cin'] * s['cout'] * es
+            f, b, _ = next(it)
+            return f, b
+        n_vox = int(enc.last_counts[0])
+        ctx = dict(n_points=int(pts.shape[0]), c_points=int(pts.shape[1]), n_voxels=n_vox, conv_work=conv_work)
+        fams = profiling.families(cap, ctx, pk)
+        tot = sum(f['ms'] for f in fams)
+        if best is None or tot < best[0]:
+            best = (tot, fams, sparse)
+    tot, fams, sparse = best
+    for f in fams:
+        f['share_of_kernel_time'] = round(f['ms'] / tot, 4)
+    return fams, round(tot, 4), [dict(flops=f, bytes=b, **d) for f, b, d in sparse]
+
+
+def pipe_enc(pipe):
+    from srfdet_b200 import _lib as L
+    from srfdet_b200.plugin import registry
+    e = registry.act_enc(pipe.precision)
+    return L.F32 if e is None else e
 
 
 def cpu_frame_seconds(state, kind, d, pts_np, torch):
@@ -173,8 +166,12 @@ def cpu_frame_seconds(state, kind, d, pts_np, torch):
     return time.perf_counter() - t0
 
 
+CPU_SAMPLE = ('full frames through the oracle port of the reference CPU path (mmcv CPU voxelize loop in C, spconv native gather-mm-scatter '
+              'with torch.mm, torch CPU conv2d backbone / neck, RoIAlign C loop over the host threads, torch CPU attention / linear / bmm / layer_norm)')
+
+
 def run_reference(args, wl):
-    """--impl reference: the restated reference CPU path (oracle) on the host cores."""
+    """--impl reference: the restated reference CPU path (oracle) on the host cores, same workload and scope."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -186,31 +183,32 @@ def run_reference(args, wl):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     kind = wl['kind']
-    state = build_cpu_state(kind, wl['fusion'], torch)
+    state = build_cpu_state(kind, wl['fusion'], args.scope)
     d = P.HEAD_CFG[kind]['d']
     clouds = [synth.cloud(kind, 1000 + i) for i in range(2)]
-    for i in range(args.warmup):
+    warm = min(args.warmup, 2)          # a CPU frame takes seconds: keep the whole run within a few minutes
+    for i in range(warm):
         cpu_frame_seconds(state, kind, d, clouds[i % 2], torch)
     t0 = time.perf_counter()
     for i in range(args.steps):
         cpu_frame_seconds(state, kind, d, clouds[i % 2], torch)
     dt = time.perf_counter() - t0
     fps = args.steps / dt
-    line = dict(metric='frames/s (voxelize+SparseEncoder+RoI fusion)', value=round(fps, 4), unit='frames/s', n_gpus=args.gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=round(dt / args.steps * 1e3, 2), higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=args.workload, description=wl['desc'], frames_per_step=1),
+    line = dict(metric=METRIC, value=round(fps, 4), unit='frames/s', n_gpus=args.gpus, steps=args.steps, warmup=warm,
+                ms_per_step=round(dt / args.steps * 1e3, 2), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', impl='reference',
+                config=dict(workload=args.workload, scope=args.scope, description=wl['desc'], frames_per_step_per_gpu=1),
                 cpu_baseline=dict(value=round(fps, 4), unit='frames/s', cores=cores, kind='port',
-                                  sample=f'{args.steps} full frames ({clouds[0].shape[0]} points each) through the oracle port '
-                                         '(mmcv CPU voxelize loop in C, spconv native gather-mm-scatter with torch.mm, RoIAlign C loop, torch CPU bmm)'),
+                                  sample=f'{args.steps} {CPU_SAMPLE}; {clouds[0].shape[0]} points per frame'),
                 e2e=dict(value=round(fps, 4), unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
-def build_cpu_state(kind, fusion, torch):
-    """Same seeded weights / synthetic maps as RegionFeaturePipeline, built without CUDA."""
+def build_cpu_state(kind, fusion, scope):
+    """Same seeded weights / synthetic maps as the GPU arm's pipeline, built on the host.  Constructing the
+    modules does not load the CUDA library (srfdet_b200/_lib.py:make_geom is host arithmetic)."""
     from srfdet_b200.pipeline import RegionFeaturePipeline
-    pipe = RegionFeaturePipeline(kind, fusion=fusion, device='cpu', precision='fp32')
+    pipe = RegionFeaturePipeline(kind, fusion=fusion, device='cpu', precision='fp32', scope=scope)
     return pipe.state()
 
 
@@ -220,12 +218,15 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='nusc_L', choices=sorted(WORKLOADS))
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32', 'bf16', 'fp32_simt'])
+    ap.add_argument('--workload', default='nusc_LC', choices=sorted(WORKLOADS))
+    ap.add_argument('--scope', default='full', choices=sorted(SCOPES))
+    ap.add_argument('--precision', default='fp16', choices=sorted(DTYPES))
+    ap.add_argument('--frames-in-flight', type=int, default=1, help='frames per rank per step, each its own CUDA graph on its own stream')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the modes / sweep / kernel-family measurements (timed value and e2e only)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying a CUDA graph of the frame')
-    ap.add_argument('--nchw', action='store_true', help='RoI stage samples contiguous NCHW maps (reference layout) instead of channels_last')
-    ap.add_argument('--layers-out', default=None, help='write the per-layer sparse-conv table (JSON) here')
+    ap.add_argument('--nchw', action='store_true', help='path scope: RoI stage samples contiguous NCHW maps instead of channels_last')
+    ap.add_argument('--kernels-out', default=None, help='write the kernel-family table and the per-layer sparse-conv work (JSON) here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     wl = WORKLOADS[args.workload]
@@ -247,12 +248,6 @@ def main():
     lib = L.load()
     pk = peaks()
     kind = wl['kind']
-    pipe = RegionFeaturePipeline(kind, fusion=wl['fusion'], precision=args.precision, channels_last=not args.nchw)
-    eager = pipe._run_frame_eager
-    # distinct frames per rank, resident on the device (value) and in pinned host memory (e2e)
-    clouds_np = [synth.cloud(kind, 1000 * (rank + 1) + i) for i in range(N_CLOUDS)]
-    clouds_dev = [torch.as_tensor(c).cuda() for c in clouds_np]
-    clouds_pin = [torch.as_tensor(c).pin_memory() for c in clouds_np]
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
     def barrier():
@@ -260,43 +255,113 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, inputs, steps, warmup):
+    def make_pipe(workload, scope, precision):
+        w = WORKLOADS[workload]
+        pipe = RegionFeaturePipeline(w['kind'], fusion=w['fusion'], precision=precision, channels_last=not args.nchw, scope=scope)
+        if scope == 'full':
+            pipe.calibrate(torch.as_tensor(synth.cloud(w['kind'], 999)).cuda())
+        return pipe
+
+    def clouds_for(kind_):
+        c = [synth.cloud(kind_, 1000 * (rank + 1) + i) for i in range(N_CLOUDS)]
+        return c, [torch.as_tensor(x).cuda() for x in c], [torch.as_tensor(x).pin_memory() for x in c]
+
+    def timed(pipe, inputs, steps, warmup, fif, host):
+        """`steps` steps of `fif` concurrent frames; events on the current stream bracket each step; L2 flushed between."""
+        def step(i):
+            batch = [inputs[(i * fif + j) % N_CLOUDS] for j in range(fif)]
+            if fif == 1 and not host:
+                pipe.run_frame(batch[0])
+            elif fif == 1:
+                pipe.run_frame_host(batch[0])
+            else:
+                pipe.run_frames(batch, host=host)
         for i in range(warmup):
-            fn(inputs[i % N_CLOUDS])
+            step(i)
         barrier()
         evs = []
         for i in range(steps):
-            flush.zero_()                                # evict the previous frame from L2 (not timed)
+            flush.zero_()                                # evict the previous frames from L2 (not timed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn(inputs[i % N_CLOUDS])
+            step(i)
             e1.record()
             evs.append((e0, e1))
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
         return frames.max_over_ranks(ms, 'cuda')
 
+    pipe = make_pipe(args.workload, args.scope, args.precision)
+    clouds_np, clouds_dev, clouds_pin = clouds_for(kind)
+    fif = max(1, args.frames_in_flight)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    eager(clouds_dev[0])
+    pipe._run_frame_eager(clouds_dev[0])
     n0 = lib.srf_launch_count()
-    eager(clouds_dev[0])
+    pipe._run_frame_eager(clouds_dev[0])
     launches_per_frame = int(lib.srf_launch_count() - n0)      # this library's kernels per frame (counted eagerly)
     pipe.use_graph = not args.no_graph
-    ms_dev = timed(pipe.run_frame, clouds_dev, args.steps, args.warmup)
-    ms_e2e = timed(pipe.run_frame_host, clouds_pin, args.steps, args.warmup)
+    ms_dev = timed(pipe, clouds_dev, args.steps, args.warmup, fif, host=False)
+    ms_e2e = timed(pipe, clouds_pin, args.steps, args.warmup, fif, host=True)
     clocks = sampler.stop() if rank == 0 else None
-    fps = world * args.steps / (ms_dev * 1e-3)
-    fps_e2e = world * args.steps / (ms_e2e * 1e-3)
+    fps = world * args.steps * fif / (ms_dev * 1e-3)
+    fps_e2e = world * args.steps * fif / (ms_e2e * 1e-3)
+    out_bytes = int(pipe.run_frame(clouds_dev[0])[1].numel() * 4)
 
-    roof = rows = cpu = None
-    pipe.use_graph = False
-    if rank == 0:
-        roof, rows = conv_roofline(pipe, clouds_dev[0], pk, torch)
-        if args.layers_out:
-            with open(args.layers_out, 'w') as f:
-                json.dump(dict(workload=args.workload, precision=args.precision, layers=rows), f, indent=1)
+    kernels = roof = modes = sweep = cpu = None
+    kernel_ms = None
+    if rank == 0 and not args.no_extras:
+        # ---- kernel families of one frame (eager, CUDA events per call)
+        pipe.use_graph = False
+        kernels, kernel_ms, sparse_layers = kernel_families(pipe, clouds_dev[0], pk, torch)
+        pipe.use_graph = not args.no_graph
+        if args.kernels_out:
+            with open(args.kernels_out, 'w') as f:
+                json.dump(dict(workload=args.workload, scope=args.scope, precision=args.precision, kernel_ms_per_frame=kernel_ms,
+                               families=kernels, sparse_conv_layers=sparse_layers), f, indent=1)
+        dom = kernels[0]
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')) as f:
+                t = json.load(f)['families'].get(dom['family'])
+            if t:
+                traffic, traffic_src = t['dram_bytes_per_launch'], 'profiles/r02_ncu_traffic.json (ncu --set full, dram read+write per launch, cold cache)'
+        except (OSError, ValueError, KeyError):
+            pass
+        n = dom['launches']
+        roof = dict(bound=dom['bound'], kernel=f"{dom['family']} ({n} launches per frame; entry points {dom['entry_points']})",
+                    achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'], traffic=traffic, traffic_source=traffic_src,
+                    peak_source=f"{pk['src']} {'HBM copy bandwidth' if dom['bound'] == 'hbm' else 'bf16 sustained'}",
+                    launch_ms=round(dom['ms'] / n, 4), algorithmic_flops_per_launch=dom['flops'] / n, algorithmic_bytes_per_launch=dom['bytes'] / n,
+                    share_of_step_ms=dom['ms'], share_of_kernel_time=dom['share_of_kernel_time'],
+                    note='dominant kernel family of the frame; every family is listed under "kernels"')
+        # ---- other modes: the FP32-precision mode of the same workload, and the round-1 scope / LiDAR-only workload
+        if world == 1:
+            modes = {}
+            for tag, (w_, s_, p_) in {'fp32 (reference precision, hi+lo split tcgen05)': (args.workload, args.scope, 'fp32'),
+                                      'nusc_L full fp16': ('nusc_L', 'full', 'fp16'),
+                                      'nusc_L path fp16 (round-1 definition)': ('nusc_L', 'path', 'fp16'),
+                                      'nusc_LC path fp16 (round-1 definition)': ('nusc_LC', 'path', 'fp16')}.items():
+                if (w_, s_, p_) == (args.workload, args.scope, args.precision):
+                    continue
+                p2 = make_pipe(w_, s_, p_)
+                p2.use_graph = True
+                _, cd, cp = (clouds_np, clouds_dev, clouds_pin) if WORKLOADS[w_]['kind'] == kind else clouds_for(WORKLOADS[w_]['kind'])
+                st = max(10, args.steps // 2)
+                m1 = timed(p2, cd, st, 3, 1, host=False)
+                m2 = timed(p2, cp, st, 3, 1, host=True)
+                modes[tag] = dict(workload=w_, scope=s_, precision=p_, value=round(st / (m1 * 1e-3), 2), e2e=round(st / (m2 * 1e-3), 2),
+                                  ms_per_step=round(m1 / st, 4), steps=st)
+                del p2
+                torch.cuda.empty_cache()
+            # ---- frames in flight on one GPU (BASELINE config 5)
+            sweep = {}
+            for f_ in (1, 2, 4, 8):
+                st = max(6, args.steps // 2)
+                m1 = timed(pipe, clouds_dev, st, 3, f_, host=False)
+                m2 = timed(pipe, clouds_pin, st, 3, f_, host=True)
+                sweep[str(f_)] = dict(value=round(st * f_ / (m1 * 1e-3), 2), e2e=round(st * f_ / (m2 * 1e-3), 2))
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
@@ -304,28 +369,30 @@ def main():
             cpu_frame_seconds(state, kind, pipe.d, synth.cloud(kind, 1, n_points=20000), torch)   # warm caches / build
             t = cpu_frame_seconds(state, kind, pipe.d, clouds_np[0], torch)
             cpu = dict(value=round(1.0 / t, 4), unit='frames/s', cores=cores, kind='port',
-                       sample=f'1 full frame ({clouds_np[0].shape[0]} points) through the oracle port of the reference CPU path, {t:.1f} s')
+                       sample=f'1 {CPU_SAMPLE}; {clouds_np[0].shape[0]} points, {t:.1f} s')
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
     n_pts, c_pts = clouds_np[0].shape
-    line = dict(metric='frames/s (voxelize+SparseEncoder+RoI fusion)', value=round(fps, 2), unit='frames/s', n_gpus=world,
-                steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_dev / args.steps, 4), higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype={'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f16x2 (hi+lo split operands, 3 MMAs per product, fp32 accumulate)', 'fp32_simt': 'f32'}[args.precision], data='synthetic',
-                config=dict(workload=args.workload, description=wl['desc'], frames_per_step_per_gpu=1,
+    line = dict(metric=METRIC, value=round(fps, 2), unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=round(ms_dev / args.steps, 4), higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=DTYPES[args.precision], data='synthetic',
+                config=dict(workload=args.workload, scope=args.scope, description=wl['desc'], scope_description=SCOPES[args.scope],
+                            frames_per_step_per_gpu=fif,
                             parallelism=f'{world} independent frame replica(s), no data-path collective',
                             l2='512 MiB flush written between timed steps; 8 distinct clouds cycled',
-                            roi_map_layout='NCHW contiguous' if args.nchw else 'torch.channels_last (NHWC in memory)',
                             launch='eager' if args.no_graph else 'one CUDA graph per frame (captured once, replayed)',
-                            excluded='dense BEV backbone/FPN, image backbone, attention/FFN rows of the head (SURVEY 8f): RoI stage samples synthetic FPN maps'),
+                            weights='synthetic: seeded random init, BatchNorm2d statistics of the dense backbone / neck / DPG calibrated on one frame',
+                            excluded='image backbone (VoVNet/FPN: the image branch samples synthetic image FPN maps), rotated NMS'),
                 clocks=clocks,
-                e2e=dict(value=round(fps_e2e, 2), unit='frames/s', h2d_bytes_per_step=int(n_pts * c_pts * 4),
-                         d2h_bytes_per_step=int(900 * pipe.C * 4), ms_per_step=round(ms_e2e / args.steps, 4)),
-                gpu_launches=launches_per_frame * args.steps,
-                gpu_launches_per_step=launches_per_frame,
-                roofline=roof, cpu_baseline=cpu)
+                e2e=dict(value=round(fps_e2e, 2), unit='frames/s', h2d_bytes_per_step=int(n_pts * c_pts * 4 * fif),
+                         d2h_bytes_per_step=out_bytes * fif, ms_per_step=round(ms_e2e / args.steps, 4)),
+                gpu_launches=launches_per_frame * args.steps * fif,
+                gpu_launches_per_frame=launches_per_frame,
+                roofline=roof, kernels=kernels, kernel_ms_per_frame_eager=kernel_ms, modes=modes, frames_in_flight_sweep=sweep,
+                cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
 
 

@@ -457,9 +457,21 @@ def roi_align(feat, rois, spatial_scale, out_size=7, sampling_ratio=2):
     n, c, h, w = feat.shape
     k = rois.shape[0]
     out = np.zeros((k, c, out_size, out_size), np.float32)
-    if k:
-        _lib().orc_roi_align(_p(feat), n, c, h, w, _p(rois), k, ctypes.c_float(spatial_scale),
-                             out_size, out_size, sampling_ratio, _p(out))
+    if not k:
+        return out
+    lib = _lib()
+
+    def run(lo, hi):
+        lib.orc_roi_align(_p(feat), n, c, h, w, _p(rois[lo:hi]), hi - lo, ctypes.c_float(spatial_scale), out_size, out_size,
+                          sampling_ratio, _p(out[lo:hi]))
+    nt = min(os.cpu_count() or 1, max(1, k // 32))
+    if nt <= 1:
+        run(0, k)
+    else:       # RoIs are independent: one slice per host thread (ctypes releases the GIL; results do not depend on nt)
+        from concurrent.futures import ThreadPoolExecutor
+        edges = np.linspace(0, k, nt + 1).astype(int)
+        with ThreadPoolExecutor(nt) as ex:
+            list(ex.map(lambda i: run(int(edges[i]), int(edges[i + 1])), range(nt)))
     return out
 
 

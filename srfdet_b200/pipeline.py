@@ -288,6 +288,55 @@ class RegionFeaturePipeline:
         return prop
 
     @torch.no_grad()
+    def calibrate(self, points):
+        """Set-up step for the synthetic weights of scope 'full' (no checkpoints offline): give every BatchNorm2d of the
+        dense backbone, the neck and the DPG staircase the running statistics of its own input on one calibration
+        frame -- what training would have produced -- so activations stay O(1) through the 12 + 6 conv layers
+        instead of growing heavy tails (random statistics make the chained head ill-conditioned: max / std of the
+        FPN maps reaches 40).  Plain torch ops, run once, not part of any measured frame."""
+        import torch.nn.functional as F
+        assert self.scope == 'full'
+        g = torch.Generator().manual_seed(12345)
+
+        def fit(conv, bn, x, stride, pad, groups=1):
+            y = F.conv2d(x, conv.weight, None, stride=stride, padding=pad, groups=groups)
+            bn.running_mean.copy_(y.mean((0, 2, 3)))
+            bn.running_var.copy_(y.var((0, 2, 3), unbiased=False).clamp_min(1e-6))
+            bn.weight.copy_((torch.rand(bn.weight.shape, generator=g) * 0.5 + 0.75).to(y.device))
+            bn.bias.copy_((torch.randn(bn.bias.shape, generator=g) * 0.1).to(y.device))
+            return F.relu(F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps))
+        old_tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            x = self.detector.extract_point_features([points], precision='fp32').float().contiguous()
+            feats = []
+            for block in self.backbone.blocks:
+                for j in range(0, len(block), 3):
+                    x = fit(block[j], block[j + 1], x, block[j].stride[0], 1)
+                feats.append(x)
+            lat = [fit(cm.conv, cm.bn, f, 1, 0) for cm, f in zip(self.neck.lateral_convs, feats)]
+            for i in range(len(lat) - 1, 0, -1):
+                lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode='nearest')
+            outs = [fit(self.neck.fpn_convs[i].conv, self.neck.fpn_convs[i].bn, lat[i], 1, 1) for i in range(len(lat))]
+            for i in range(len(lat), self.neck.num_outs):
+                if self.neck.add_extra_convs:
+                    outs.append(fit(self.neck.fpn_convs[i].conv, self.neck.fpn_convs[i].bn, outs[-1], 2, 1))
+                else:
+                    outs.append(F.max_pool2d(outs[-1], 1, stride=2))
+
+            def staircase(convs, maps):
+                xx = None
+                for l, cm in enumerate(convs):
+                    inp = maps[l] if xx is None else torch.cat([maps[l], xx], dim=1)
+                    xx = fit(cm.conv, cm.bn, inp, 2, 1, groups=inp.shape[1])
+            staircase(self.head.dpg_dw_convs_lidar, outs)
+            if self.fusion:
+                staircase(self.head.dpg_dw_convs_img, [f[0].contiguous() for f in self.img_feats])
+        finally:
+            torch.backends.cudnn.allow_tf32 = old_tf32
+        self._graphs = {}
+
+    @torch.no_grad()
     def full_chain(self, bev):
         """dense BEV map -> SECONDCustom -> FPN -> SRFDetHead (DPG, chained stages) -> decode.
         Returns the last stage's object features; logits / boxes / decoded results in self.last."""
@@ -308,7 +357,30 @@ class RegionFeaturePipeline:
         return bev, self.region_stages()
 
     @torch.no_grad()
-    def run_frame(self, points):
+    def run_frames(self, clouds, host=False):
+        """Frame-level concurrency on one GPU (BASELINE config 5): frame i of `clouds` runs as its own CUDA graph
+        (slot i: private input / intermediate / output buffers) on its own stream; the streams fork from and
+        join the current stream.  host=True: `clouds` are pinned host tensors, results come back as pinned host
+        tensors (H2D / D2H on the frame's stream).  Returns the per-frame outputs."""
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_slot_streams'):
+            self._slot_streams = []
+        while len(self._slot_streams) < len(clouds):
+            self._slot_streams.append(torch.cuda.Stream())
+        fork = main.record_event()
+        outs = []
+        for i, pts in enumerate(clouds):
+            st = self._slot_streams[i]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                outs.append(self.run_frame_host(pts, slot=i, sync=False) if host else self.run_frame(pts, slot=i))
+            main.wait_event(st.record_event())
+        if host:
+            main.synchronize()
+        return outs
+
+    @torch.no_grad()
+    def run_frame(self, points, slot=0):
         """points (N,C) fp32 CUDA tensor -> (dense BEV map, region features (P,C)).
 
         use_graph=True: the whole frame (every kernel reads its counts from device memory, so
@@ -317,7 +389,7 @@ class RegionFeaturePipeline:
         overwrites."""
         if not self.use_graph:
             return self._run_frame_eager(points)
-        key = (tuple(points.shape), self.precision, self.scope)
+        key = (tuple(points.shape), self.precision, self.scope, slot)
         g = self._graphs.get(key)
         if g is None:
             static_in = torch.empty_like(points)
@@ -339,16 +411,20 @@ class RegionFeaturePipeline:
         return out
 
     @torch.no_grad()
-    def run_frame_host(self, points_pinned):
+    def run_frame_host(self, points_pinned, slot=0, sync=True):
         """Public end-to-end call: HOST (pinned) points in, HOST region features out."""
-        key = (tuple(points_pinned.shape), self.precision, self.scope)
+        key = (tuple(points_pinned.shape), self.precision, self.scope, slot)
         if self.use_graph and key in self._graphs:
             pts = self._graphs[key][1]                      # H2D straight into the graph's input buffer
             pts.copy_(points_pinned, non_blocking=True)
         else:
             pts = points_pinned.to(self.device, non_blocking=True)
-        bev, obj = self.run_frame(pts)
-        out = torch.empty(obj.shape, dtype=obj.dtype, pin_memory=True)
+        bev, obj = self.run_frame(pts, slot=slot)
+        hkey = ('host_out', tuple(obj.shape), slot)
+        out = self._graphs.get(hkey)
+        if out is None:
+            out = self._graphs[hkey] = torch.empty(obj.shape, dtype=obj.dtype, pin_memory=True)
         out.copy_(obj, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if sync:
+            torch.cuda.current_stream().synchronize()
         return bev, out

@@ -188,6 +188,7 @@ def test_full_chain_vs_oracle(kind, fusion, n_points):
     from srfdet_b200.pipeline import RegionFeaturePipeline
     pipe = RegionFeaturePipeline(kind, fusion=fusion, precision='fp32', scope='full')
     pts = synth.cloud(kind, 43, n_points=n_points or None)
+    pipe.calibrate(cuda(synth.cloud(kind, 44, n_points=n_points or None)))     # synthetic weights: BatchNorm2d statistics of a calibration frame
     state = pipe.state()
     ref_bev = cpu_pipeline.encode(state, kind, synth.GEOM[kind], pts)
     ref_out, ref = cpu_pipeline.full_chain(state, ref_bev)

@@ -31,7 +31,9 @@ def box_errors(last, ref, pc):
     centres (as a fraction of the range), log sizes and (sin, cos, v) -- absolute differences."""
     span = np.array([pc[3] - pc[0], pc[4] - pc[1], pc[5] - pc[2]], np.float32)
     gb, rb = last['boxes'].cpu().numpy(), ref['boxes']
-    return dict(fpn0=rel(last['pyramid'][0].cpu().numpy(), ref['pyramid'][0]), fpn3=rel(last['pyramid'][3].cpu().numpy(), ref['pyramid'][3]),
+    stages = last['logits'].shape[0]
+    lg, rl = last['logits'].cpu().numpy(), ref['logits']
+    return dict(logits_per_stage=[rel(lg[i], rl[i]) for i in range(stages)], fpn0=rel(last['pyramid'][0].cpu().numpy(), ref['pyramid'][0]), fpn3=rel(last['pyramid'][3].cpu().numpy(), ref['pyramid'][3]),
                 logits=rel(last['logits'].cpu().numpy(), ref['logits']),
                 centre_frac=float((np.abs(gb[..., :3] - rb[..., :3]) / span).max()), logsize_abs=float(np.abs(gb[..., 3:6] - rb[..., 3:6]).max()),
                 rest_abs=float(np.abs(gb[..., 6:] - rb[..., 6:]).max()))
@@ -52,6 +54,8 @@ def main():
         kind, fusion = WL[wl]
         pipe = RegionFeaturePipeline(kind, fusion=fusion, precision='fp32', scope=args.scope)
         pts = synth.cloud(kind, 1000, n_points=args.points or None)
+        if args.scope == 'full':
+            pipe.calibrate(torch.as_tensor(synth.cloud(kind, 999, n_points=args.points or None)).cuda())
         t0 = time.perf_counter()
         state = pipe.state()
         ref_bev = cpu_pipeline.encode(state, kind, synth.GEOM[kind], pts)
