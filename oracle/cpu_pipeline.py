@@ -69,9 +69,10 @@ def full_chain(state, bev):
     pyramid = O.fpn(state['neck'], feats, 4, extra_convs=cfg['extra_convs'])
     img = state.get('img_feats')
     l2i = state['lidar2img'][None] if img is not None else None
-    logits, boxes = O.srfdet_head_forward(state['head'], img, pyramid, l2i, cfg)
+    trace = {}
+    logits, boxes = O.srfdet_head_forward(state['head'], img, pyramid, l2i, cfg, trace=trace)
     scores, dec = O.decode_boxes(logits[-1], boxes[-1])
-    return np.concatenate([dec[0], scores[0]], axis=1), dict(pyramid=pyramid, logits=logits, boxes=boxes)
+    return np.concatenate([dec[0], scores[0]], axis=1), dict(pyramid=pyramid, logits=logits, boxes=boxes, trace=trace)
 
 
 def run_frame(state, kind, geom, d, points):

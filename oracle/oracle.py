@@ -770,7 +770,7 @@ def single_head_stage(p, img_feats, point_feats, boxes, prop, lidar2img, cfg):
     return logits.numpy(), pred, obj.numpy()
 
 
-def srfdet_head_forward(params, img_feats, point_feats, lidar2img, cfg):
+def srfdet_head_forward(params, img_feats, point_feats, lidar2img, cfg, trace=None):
     """SRFDetHead.forward (srfdet_head.py:371-498), batch 1: DPG -> sigmoid -> chained stages -> centre
     de-normalisation.  -> logits (S,1,n_p,cls), boxes (S,1,n_p,dim)."""
     use_img = img_feats is not None
@@ -779,11 +779,17 @@ def srfdet_head_forward(params, img_feats, point_feats, lidar2img, cfg):
     boxes[..., :3] = 1.0 / (1.0 + np.exp(-boxes[..., :3].astype(np.float64))).astype(np.float32)
     prop = prop[0]
     lg, bx = [], []
+    if trace is not None:
+        trace.update(init_boxes=boxes.copy(), init_prop=prop.copy(), stage_in=[], stage_out=[])
     for s in range(cfg['stages']):
+        if trace is not None:
+            trace['stage_in'].append((boxes.copy(), prop.copy()))
         logits, pred, prop = single_head_stage(_sub(params, f'head_series_lidar.{s}.'), img_feats, point_feats, boxes, prop, lidar2img, cfg)
         lg.append(logits[None])
         bx.append(pred[None].copy())
         boxes = pred[None].copy()
+        if trace is not None:
+            trace['stage_out'].append((logits.copy(), pred.copy(), prop.copy()))
     lg, bx = np.stack(lg), np.stack(bx)
     pc = cfg['pc_range']
     bx[..., :3] = bx[..., :3] * np.array([pc[3] - pc[0], pc[4] - pc[1], pc[5] - pc[2]], np.float32) + np.array(pc[:3], np.float32)

@@ -119,6 +119,10 @@ def init_synthetic_head(head, seed):
         for st in head.head_series_lidar:
             st.bboxes_delta_lidar.weight.mul_(0.05)
             st.bboxes_delta_lidar.bias.zero_()
+        # DPG: the FC input is a sum over 4C ReLU channels (O(C) per pixel); scale fc1 so the expert logits are O(1)
+        # and the softmax over experts MIXES the embeddings (a trained gate), instead of a brittle hard selection
+        for fc in [getattr(head, n) for n in ('dpg_fc1_lidar', 'dpg_fc1_img') if hasattr(head, n)]:
+            fc.weight.mul_(1.0 / (2.0 * head.feat_channels_lidar))
 
 
 def init_synthetic_backbone(module, seed):
@@ -347,6 +351,7 @@ class RegionFeaturePipeline:
         logits, boxes = self.head(self.img_feats if self.fusion else None, pyramid, None, lidar2img=self.lidar2img, precision=self.precision)
         scores, dec = self.head.decode(logits, boxes)
         self.last = dict(pyramid=pyramid, logits=logits, boxes=boxes, scores=scores, det_boxes=dec)
+        self.last_pyramid = pyramid
         return torch.cat([dec[0], scores[0]], dim=1)          # (P, box_dim-1 + classes): what a caller post-processes
 
     @torch.no_grad()

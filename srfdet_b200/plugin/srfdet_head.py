@@ -184,8 +184,11 @@ class SRFDetHead(nn.Module):
             logits_all, boxes_all = logits_all[-1:], boxes_all[-1:]
         logits_all, boxes_all = torch.stack(logits_all), torch.stack(boxes_all)
         r = self.pc_range
-        span = boxes_all.new_tensor([r[3] - r[0], r[4] - r[1], r[5] - r[2]])
-        boxes_all[..., :3] = boxes_all[..., :3] * span + boxes_all.new_tensor(r[:3])
+        key = ('range', str(boxes_all.device))          # device constants are created once (eagerly), never inside a graph capture
+        if key not in self._cache:
+            self._cache[key] = (boxes_all.new_tensor([r[3] - r[0], r[4] - r[1], r[5] - r[2]]), boxes_all.new_tensor(r[:3]))
+        span, lo = self._cache[key]
+        boxes_all[..., :3] = boxes_all[..., :3] * span + lo
         return logits_all, boxes_all
 
     @torch.no_grad()

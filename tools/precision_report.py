@@ -39,6 +39,31 @@ def box_errors(last, ref, pc):
                 rest_abs=float(np.abs(gb[..., 6:] - rb[..., 6:]).max()))
 
 
+def teacher_forced(pipe, ref, prec):
+    """Every stage of the head fed with the ORACLE's inputs of that stage (FPN pyramid, boxes, proposal features):
+    isolates each stage's own error from the amplification of the chained loop."""
+    tr = ref['trace']
+    head = pipe.head
+    pyr = [torch.as_tensor(p).cuda().contiguous(memory_format=torch.channels_last) for p in ref['pyramid']]
+    img = pipe.img_feats if pipe.fusion else None
+    b0, f0 = head._get_init_proposals(img, pyr, sigmoid_centres=True)
+    out = dict(tf_init_boxes=float(np.abs(b0.cpu().numpy() - tr['init_boxes']).max()), tf_init_prop=rel(f0[0].cpu().numpy(), tr['init_prop']),
+               tf_logits=[], tf_boxes=[], tf_obj=[])
+    for s, stage in enumerate(head.head_series_lidar):
+        boxes = torch.as_tensor(tr['stage_in'][s][0]).cuda().contiguous()
+        prop = torch.as_tensor(tr['stage_in'][s][1]).cuda().contiguous()
+        if pipe.fusion:
+            lg, pred, obj = stage(img, pyr, boxes, prop, head.roi_extractor_lidar, None, pooler_img=head.roi_extractor_img, precision=prec,
+                                  lidar2img=pipe.lidar2img)
+        else:
+            lg, pred, obj = stage(pyr, boxes, prop, head.roi_extractor_lidar, None, precision=prec)
+        rl, rp, ro = tr['stage_out'][s]
+        out['tf_logits'].append(rel(lg[0].cpu().numpy(), rl))
+        out['tf_boxes'].append(float(np.abs(pred[0].cpu().numpy() - rp).max()))
+        out['tf_obj'].append(rel(obj.cpu().numpy(), ro))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workloads', default='nusc_L,nusc_LC,waymo_L,kitti_L')
@@ -74,6 +99,7 @@ def main():
                                  bev_rms=float(np.sqrt(((b - ref_bev) ** 2).mean()) / np.sqrt((ref_bev ** 2).mean())))
             if ref_x is not None:
                 res[wl][prec].update(box_errors(pipe.last, ref_x, synth.GEOM[kind]['pc_range']))
+                res[wl][prec].update(teacher_forced(pipe, ref_x, prec))
             print(wl, prec, res[wl][prec], flush=True)
     s = json.dumps(res, indent=1)
     if args.out:
