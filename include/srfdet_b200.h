@@ -274,6 +274,29 @@ int srf_pack_linear_tc(const float* w_f32, int32_t n, int32_t k, int32_t enc, vo
 int srf_linear_tc(const void* a, int32_t a_enc, int32_t m, int32_t k, const void* w_packed, int32_t n,
                   const float* bias, const void* residual, int32_t epi, const float* ln_w, const float* ln_b,
                   float ln_eps, void* out, int32_t out_enc, int32_t k_splits, void* stream);
+/* The same through an argument block, with the options the head's stage tail uses: A read through a row stride
+ * (a column block of a wider buffer), a second copy of the result in another encoding (fp32 trunk + 16-bit GEMM
+ * operand from one epilogue), one LayerNorm per 128-column tile (cls | reg towers merged into one GEMM). */
+typedef struct srf_linear_args {
+  const void* a;        /* (m, k) in a_enc */
+  int32_t a_enc, m, k;
+  int64_t a_stride;     /* elements between rows of A; 0 = k (2k for split encodings) */
+  int64_t a_lo_off;     /* split encodings: elements from a row's hi part to its lo part; 0 = k */
+  const void* w;        /* packed by srf_pack_linear_tc */
+  int32_t n;
+  const float* bias;    /* (n) nullable */
+  const void* residual; /* (m, n) in out_enc, nullable */
+  int32_t epi;          /* bit0 relu, bit1 layernorm */
+  const float *ln_w, *ln_b;
+  float ln_eps;
+  int32_t ln_per_tile;  /* 1: ln_w / ln_b are (n) and every 128-column tile is normalised on its own */
+  void* out;
+  int32_t out_enc;
+  void* out2;           /* nullable: (m, n) second copy in out2_enc */
+  int32_t out2_enc;
+  int32_t k_splits;
+} srf_linear_args;
+int srf_linear(const srf_linear_args* args_host, void* stream);
 int srf_linear_tile_k(int32_t k); /* host: K-slice width used by the packer (min(k,128)) */
 int srf_linear_tile_n(int32_t n); /* host: N tile width (min(n,128)) */
 int srf_linear_splits(int32_t k, int32_t k_splits); /* host: effective split count used for (k, k_splits) */
@@ -292,10 +315,11 @@ int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_
                   const float* bias, const float* gamma, const float* beta, float eps, int32_t relu,
                   void* out, void* stream);
 /* same with separate encodings (in f32 | bf16 | f16, out any SRF_* encoding) and an optional f32
- * residual (rows, n) added before the norm: out = act(LN(sum_p in[p] + bias + residual)) */
+ * residual (rows, n) added before the norm: out = act(LN(sum_p in[p] + bias + residual)); out2 (nullable):
+ * a second copy of the result in out2_enc (fp32 trunk + 16-bit GEMM operand from one pass) */
 int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, int32_t n_partials,
                       const float* bias, const float* residual, const float* gamma, const float* beta, float eps,
-                      int32_t relu, void* out, int32_t out_enc, void* stream);
+                      int32_t relu, void* out, int32_t out_enc, void* out2, int32_t out2_enc, void* stream);
 
 /* ---------------------------------------------------------------------------------- *
  * Region features.

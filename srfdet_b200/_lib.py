@@ -78,6 +78,13 @@ class Pyramid(Structure):
                 ('n_levels', c_int32), ('channels', c_int32), ('channels_last', c_int32)]
 
 
+class LinearArgs(Structure):
+    _fields_ = [('a', c_void_p), ('a_enc', c_int32), ('m', c_int32), ('k', c_int32), ('a_stride', c_int64), ('a_lo_off', c_int64),
+                ('w', c_void_p), ('n', c_int32), ('bias', c_void_p), ('residual', c_void_p), ('epi', c_int32), ('ln_w', c_void_p),
+                ('ln_b', c_void_p), ('ln_eps', c_float), ('ln_per_tile', c_int32), ('out', c_void_p), ('out_enc', c_int32),
+                ('out2', c_void_p), ('out2_enc', c_int32), ('k_splits', c_int32)]
+
+
 class Map(Structure):
     _fields_ = [('ptr', c_void_p), ('c', c_int32), ('sn', c_int64), ('sc', c_int64), ('sh', c_int64), ('sw', c_int64)]
 
@@ -142,10 +149,11 @@ PROTOTYPES = {
     'srf_linear_tile_k_enc': (c_int32, [c_int32, c_int32]),
     'srf_linear_splits_enc': (c_int32, [c_int32, c_int32, c_int32]),
     'srf_pack_linear_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'srf_linear': (c_int32, [POINTER(LinearArgs), c_void_p]),
     'srf_linear_tc': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_float, c_void_p, c_int32, c_int32, c_void_p]),
     'srf_layernorm_enc': (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
-                                    c_int32, c_void_p, c_int32, c_void_p]),
+                                    c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
     'srf_mha_attention': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     'srf_apply_deltas': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_float, POINTER(c_float), c_void_p, c_void_p]),
     'srf_dwconv3x3_s2': (c_int32, [POINTER(Map), POINTER(Map), c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

@@ -121,6 +121,9 @@ struct IgemmArgs {
   int out_enc;   // SRF_F32 | SRF_BF16 | SRF_F16 | SRF_BF16X2 | SRF_F16X2 (16-bit forms use fmt)
   long long out_stride;   // elements of the out array between rows
   long long out_lo_off;   // split output: elements from hi to lo part
+  void* out2;             // dense linear: optional second copy of the result (e.g. fp32 trunk + 16-bit GEMM operand)
+  int out2_enc;
+  int ln_per_tile;        // LayerNorm parameters indexed by global column (one norm per column tile: merged towers)
   float* dense;
   const int4* out_coors;
   int D, H, W;
@@ -160,18 +163,18 @@ __device__ __forceinline__ void add_residual(const IgemmArgs& a, size_t row, int
   }
 }
 
-// store of NC consecutive channels of one row at column c in the output's encoding
+// store of NC consecutive channels of one row at column c in encoding `enc` (row stride / lo offset in elements)
 template <int NC>
-__device__ __forceinline__ void store_cols(const IgemmArgs& a, size_t row, int c, const float* v) {
-  if (a.out_enc == SRF_F32) {
-    float4* op = (float4*)((float*)a.out + row * a.out_stride + c);
+__device__ __forceinline__ void store_cols_to(void* out, int enc, long long stride, long long lo_off, bool f16, size_t row, int c,
+                                              const float* v) {
+  if (enc == SRF_F32) {
+    float4* op = (float4*)((float*)out + row * stride + c);
 #pragma unroll
     for (int i = 0; i < NC; i += 4) op[i / 4] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     return;
   }
-  const bool f16 = a.fmt != 0;
-  uint16_t* base = (uint16_t*)a.out + row * a.out_stride + c;
-  if (!enc_is_split(a.out_enc)) {
+  uint16_t* base = (uint16_t*)out + row * stride + c;
+  if (!enc_is_split(enc)) {
     uint4* op = (uint4*)base;
 #pragma unroll
     for (int i = 0; i < NC; i += 8)
@@ -180,7 +183,7 @@ __device__ __forceinline__ void store_cols(const IgemmArgs& a, size_t row, int c
     return;
   }
   uint4* oh = (uint4*)base;
-  uint4* ol = (uint4*)(base + a.out_lo_off);
+  uint4* ol = (uint4*)(base + lo_off);
 #pragma unroll
   for (int i = 0; i < NC; i += 8) {
     uint32_t h[4], l[4];
@@ -189,6 +192,11 @@ __device__ __forceinline__ void store_cols(const IgemmArgs& a, size_t row, int c
     oh[i / 8] = make_uint4(h[0], h[1], h[2], h[3]);
     ol[i / 8] = make_uint4(l[0], l[1], l[2], l[3]);
   }
+}
+
+template <int NC>
+__device__ __forceinline__ void store_cols(const IgemmArgs& a, size_t row, int c, const float* v) {
+  store_cols_to<NC>(a.out, a.out_enc, a.out_stride, a.out_lo_off, a.fmt != 0, row, c, v);
 }
 
 // Sparse-conv epilogue of NC consecutive output channels [c0, c0+NC) of one row (the row's
@@ -241,13 +249,20 @@ __device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt
     for (int c = 0; c < COUT; ++c) { float d = v[c] - mean; var += d * d; }
     const float rstd = rsqrtf(var * (1.f / COUT) + a.ln_eps);
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) v[c] = (v[c] - mean) * rstd * __ldg(a.ln_w + c) + __ldg(a.ln_b + c);
+    const float* lw = a.ln_w + (a.ln_per_tile ? col0 : 0);
+    const float* lb = a.ln_b + (a.ln_per_tile ? col0 : 0);
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) v[c] = (v[c] - mean) * rstd * __ldg(lw + c) + __ldg(lb + c);
   }
   if (a.relu) {
 #pragma unroll
     for (int c = 0; c < COUT; ++c) v[c] = fmaxf(v[c], 0.f);
   }
   store_cols<COUT>(a, (size_t)row, col0, v);
+  if (a.out2) {
+    const long long n_total = enc_is_split(a.out_enc) ? a.out_stride / 2 : a.out_stride;   // logical columns of a row
+    store_cols_to<COUT>(a.out2, a.out2_enc, enc_is_split(a.out2_enc) ? 2 * n_total : n_total, n_total, a.fmt != 0, (size_t)row, col0, v);
+  }
 }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

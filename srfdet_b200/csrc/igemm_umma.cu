@@ -721,10 +721,18 @@ int srf_linear_splits_enc(int32_t k, int32_t enc, int32_t k_splits) {
 }
 int srf_linear_splits(int32_t k, int32_t k_splits) { return srf_linear_splits_enc(k, SRF_BF16, k_splits); }
 
-int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
-                  const void* residual, int32_t epi, const float* ln_w, const float* ln_b, float ln_eps, void* out, int32_t out_enc,
-                  int32_t k_splits, void* stream) {
+int srf_linear(const srf_linear_args* p, void* stream) {
+  SRF_CHECK_ARG(p, "srf_linear: null args");
+  const void* a_in = p->a;
+  const int32_t a_enc = p->a_enc, m = p->m, k = p->k, n = p->n, epi = p->epi, out_enc = p->out_enc, k_splits = p->k_splits;
+  const void* w_packed = p->w;
+  const float *bias = p->bias, *ln_w = p->ln_w, *ln_b = p->ln_b;
+  const void* residual = p->residual;
+  void* out = p->out;
+  const float ln_eps = p->ln_eps;
   SRF_CHECK_ARG(a_in && w_packed && out && m >= 0 && k > 0 && n > 0, "srf_linear_tc: bad args");
+  SRF_CHECK_ARG(!p->out2 || p->out2_enc == SRF_F32 || (enc_is_16(p->out2_enc) && enc_is_f16(p->out2_enc) == enc_is_f16(a_enc)),
+                "srf_linear_tc: a 16-bit second output must use A's element format");
   SRF_CHECK_ARG(enc_is_16(a_enc), "srf_linear_tc: A must be bf16 / f16 / split");
   SRF_CHECK_ARG(out_enc == SRF_F32 || (enc_is_16(out_enc) && enc_is_f16(out_enc) == enc_is_f16(a_enc)),
                 "srf_linear_tc: a 16-bit output must use A's element format");
@@ -732,13 +740,17 @@ int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const v
   const bool split = enc_is_split(a_enc);
   int tk = srf_linear_tile_k_enc(k, a_enc), tn = srf_linear_tile_n(n);
   SRF_CHECK_ARG(k % tk == 0 && n % tn == 0, "srf_linear_tc: n=%d k=%d not tileable", n, k);
-  SRF_CHECK_ARG(!(epi & 2) || (n == tn && ln_w && ln_b), "srf_linear_tc: fused LayerNorm needs n <= 128 and ln weights");
+  SRF_CHECK_ARG(!(epi & 2) || ((n == tn || p->ln_per_tile) && ln_w && ln_b),
+                "srf_linear_tc: fused LayerNorm needs n <= 128 (or one norm per 128-column tile) and ln weights");
   IgemmArgs a = {};
   a.in = (const uint16_t*)a_in;
-  a.in_stride = split ? 2 * k : k;
-  a.in_lo_off = k;
+  a.in_stride = p->a_stride > 0 ? p->a_stride : (split ? 2 * k : k);
+  a.in_lo_off = p->a_lo_off > 0 ? p->a_lo_off : k;
   a.k_stride = tk;
   a.m_rows = m;
+  a.out2 = p->out2;
+  a.out2_enc = p->out2_enc;
+  a.ln_per_tile = p->ln_per_tile;
   a.cap_out = m;
   a.kvol = k / tk;
   a.n_tiles = n / tn;
@@ -757,12 +769,22 @@ int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const v
   a.out_lo_off = n;
   a.k_splits = 1;
   if (k_splits > 1) {
-    SRF_CHECK_ARG(epi == 0 && !bias && !residual && out_enc == SRF_F32, "srf_linear_tc: split-K needs epi=0, no bias / residual and an f32 output of k_splits slabs");
+    SRF_CHECK_ARG(epi == 0 && !bias && !residual && !p->out2 && out_enc == SRF_F32,
+                  "srf_linear_tc: split-K needs epi=0, no bias / residual / second output and an f32 output of k_splits slabs");
     const int kper = (a.kvol + k_splits - 1) / k_splits;
     a.k_splits = (a.kvol + kper - 1) / kper;   // every split owns at least one K slice
   }
   const int tiles = cdiv(m, 128) * (n / tn) * a.k_splits;
   return split ? dispatch_dense<true>(tk, tn, a, tiles, (cudaStream_t)stream) : dispatch_dense<false>(tk, tn, a, tiles, (cudaStream_t)stream);
+}
+
+int srf_linear_tc(const void* a_in, int32_t a_enc, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,
+                  const void* residual, int32_t epi, const float* ln_w, const float* ln_b, float ln_eps, void* out, int32_t out_enc,
+                  int32_t k_splits, void* stream) {
+  srf_linear_args p = {};
+  p.a = a_in; p.a_enc = a_enc; p.m = m; p.k = k; p.w = w_packed; p.n = n; p.bias = bias; p.residual = residual; p.epi = epi;
+  p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps; p.out = out; p.out_enc = out_enc; p.k_splits = k_splits;
+  return srf_linear(&p, stream);
 }
 
 int srf_linear_bf16(const void* a_bf16, int32_t m, int32_t k, const void* w_packed, int32_t n, const float* bias,

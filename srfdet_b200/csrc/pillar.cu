@@ -47,34 +47,49 @@ __global__ void __launch_bounds__(128) pillar_vfe_kernel(const PillarArgs a) {
       const int t = threadIdx.x;
       const int4 q = __ldg(reinterpret_cast<const int4*>(a.coors) + v);
       float raw[8];
-      for (int c = 0; c < a.C; ++c) raw[c] = __ldg(pv + t * a.C + c);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) raw[c] = c < a.C ? __ldg(pv + t * a.C + c) : 0.f;     // fully unrolled: stays in registers
       const float cx = raw[0] - ((float)q.w * a.vx + a.xo), cy = raw[1] - ((float)q.z * a.vy + a.yo),
                   cz = raw[2] - ((float)q.y * a.vz + a.zo);
-      float f[PILLAR_MAXF];
+      // features are written straight to shared memory one scalar at a time (a register array filled through a
+      // running index made ptxas pair the stores into 8-byte local stores at 4-byte-aligned offsets)
+      const float m = t < np ? 1.f : 0.f;     // get_paddings_indicator
+      float* f = sf[t];
       int k = 0;
       // legacy=True: f_center aliases features[:, :, :3] and is modified in place, so the raw xyz
       // channels carry the centre offsets too (pillar_encoder_custom.py:133-143)
       const bool alias = a.with_center && a.legacy;
-      for (int c = 0; c < a.C; ++c) f[k++] = (alias && c < 3) ? (c == 0 ? cx : (c == 1 ? cy : cz)) : raw[c];
-      if (a.with_cluster) { f[k++] = raw[0] - smean[0]; f[k++] = raw[1] - smean[1]; f[k++] = raw[2] - smean[2]; }
-      if (a.with_center) { f[k++] = cx; f[k++] = cy; f[k++] = cz; }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < a.C) f[k++] = m * ((alias && c < 3) ? (c == 0 ? cx : (c == 1 ? cy : cz)) : raw[c]);
+      if (a.with_cluster) {
+        f[k++] = m * (raw[0] - smean[0]);
+        f[k++] = m * (raw[1] - smean[1]);
+        f[k++] = m * (raw[2] - smean[2]);
+      }
+      if (a.with_center) {
+        f[k++] = m * cx;
+        f[k++] = m * cy;
+        f[k++] = m * cz;
+      }
       if (a.with_distance) {
         const float dx = alias ? cx : raw[0], dy = alias ? cy : raw[1], dz = alias ? cz : raw[2];
-        f[k++] = sqrtf(dx * dx + dy * dy + dz * dz);
+        f[k++] = m * sqrtf(dx * dx + dy * dy + dz * dz);
       }
-      const float m = t < np ? 1.f : 0.f;     // get_paddings_indicator
-      for (int j = 0; j < a.F; ++j) sf[t][j] = f[j] * m;
     }
     __syncthreads();
     if (threadIdx.x < a.cout) {
       const float* wr = a.w + (size_t)threadIdx.x * a.F;
       float wreg[PILLAR_MAXF];
-      for (int j = 0; j < a.F; ++j) wreg[j] = __ldg(wr + j);
+#pragma unroll
+      for (int j = 0; j < PILLAR_MAXF; ++j) wreg[j] = j < a.F ? __ldg(wr + j) : 0.f;
       const float bias = __ldg(a.b + threadIdx.x);
       float red = a.avg ? 0.f : -INFINITY;
       for (int t = 0; t < a.T; ++t) {
         float acc = 0.f;
-        for (int j = 0; j < a.F; ++j) acc = fmaf(sf[t][j], wreg[j], acc);
+#pragma unroll
+        for (int j = 0; j < PILLAR_MAXF; ++j)
+          if (j < a.F) acc = fmaf(sf[t][j], wreg[j], acc);
         const float y = fmaxf(acc + bias, 0.f);
         red = a.avg ? red + y : fmaxf(red, y);
       }

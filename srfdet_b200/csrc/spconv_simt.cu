@@ -288,12 +288,35 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
   }
 }
 
+// narrow outputs (n <= 16: class logits, box deltas): block = 16 rows x 16 columns, W transposed in shared memory
+constexpr int SN_ROWS = 16, SN_MAXK = 512;
+__global__ void __launch_bounds__(256) linear_smalln_kernel(const float* __restrict__ A, int m, int k, const float* __restrict__ W, int n,
+                                                           const float* __restrict__ bias, int relu, float* __restrict__ out) {
+  extern __shared__ float swt[];                       // [k][17]
+  for (int e = threadIdx.x; e < n * k; e += blockDim.x) swt[(e % k) * 17 + e / k] = W[e];
+  __syncthreads();
+  const int col = threadIdx.x & 15, row = blockIdx.x * SN_ROWS + (threadIdx.x >> 4);
+  if (row >= m || col >= n) return;
+  const float* a = A + (size_t)row * k;
+  float acc = 0.f;
+  for (int j = 0; j < k; j += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a + j));
+    acc = fmaf(v.x, swt[j * 17 + col], acc);
+    acc = fmaf(v.y, swt[(j + 1) * 17 + col], acc);
+    acc = fmaf(v.z, swt[(j + 2) * 17 + col], acc);
+    acc = fmaf(v.w, swt[(j + 3) * 17 + col], acc);
+  }
+  acc += bias ? bias[col] : 0.f;
+  out[(size_t)row * n + col] = relu ? fmaxf(acc, 0.f) : acc;
+}
+
 // row-wise LayerNorm (+ReLU) of (sum of split-K slabs + bias), one warp per row; f32 or bf16.
 // The row is read once into registers (n <= 32*LN_MAXPL), then reduced with shuffles.
 constexpr int LN_MAXPL = 16;   // values per lane -> n <= 512
 __global__ void layernorm_rows_kernel(const void* __restrict__ in, int in_enc, int64_t rows, int n, int n_partials,
                                       const float* __restrict__ bias, const float* __restrict__ resid, const float* __restrict__ g,
-                                      const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc) {
+                                      const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc,
+                                      void* __restrict__ out2, int out2_enc) {
   int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -325,6 +348,7 @@ __global__ void layernorm_rows_kernel(const void* __restrict__ in, int in_enc, i
       float y = (v[i] - mean) * rstd * g[j] + b[j];
       if (relu) y = fmaxf(y, 0.f);
       st_enc(out, out_enc, (size_t)row, n, j, y);
+      if (out2) st_enc(out2, out2_enc, (size_t)row, n, j, y);
     }
   }
 }
@@ -333,7 +357,8 @@ __global__ void layernorm_rows_kernel(const void* __restrict__ in, int in_enc, i
 // summed -- 4-32 warps per row instead of one keeps enough loads in flight.
 __global__ void layernorm_cols_kernel(const void* __restrict__ in, int in_enc, int64_t rows, int n, int n_partials,
                                       const float* __restrict__ bias, const float* __restrict__ resid, const float* __restrict__ g,
-                                      const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc) {
+                                      const float* __restrict__ b, float eps, int relu, void* __restrict__ out, int out_enc,
+                                      void* __restrict__ out2, int out2_enc) {
   __shared__ float red[2][32];
   const int64_t row = blockIdx.x;
   const int j = threadIdx.x, lane = j & 31, w = j >> 5, nw = (blockDim.x + 31) >> 5;
@@ -362,6 +387,7 @@ __global__ void layernorm_cols_kernel(const void* __restrict__ in, int in_enc, i
     float y = d * rstd * g[j] + b[j];
     if (relu) y = fmaxf(y, 0.f);
     st_enc(out, out_enc, (size_t)row, n, j, y);
+    if (out2) st_enc(out2, out2_enc, (size_t)row, n, j, y);
   }
 }
 
@@ -481,8 +507,13 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
                    int32_t relu, float* out, void* stream) {
   SRF_CHECK_ARG(a && w && out && m >= 0 && k > 0 && n > 0, "srf_linear_f32: bad args");
   if (m == 0) return SRF_OK;
-  dim3 grid(cdiv(m, LIN_ROWS), cdiv(n, 256));
   SRF_COUNT(1);
+  if (n <= 16 && k <= SN_MAXK && k % 4 == 0 && ((uintptr_t)a % 16 == 0)) {
+    linear_smalln_kernel<<<cdiv(m, SN_ROWS), 256, (size_t)k * 17 * sizeof(float), (cudaStream_t)stream>>>(a, m, k, w, n, bias, relu, out);
+    SRF_LAUNCH_CHECK();
+    return SRF_OK;
+  }
+  dim3 grid(cdiv(m, LIN_ROWS), cdiv(n, 256));
   linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, m, k, w, n, bias, relu, out);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
@@ -490,7 +521,7 @@ int srf_linear_f32(const float* a, int32_t m, int32_t k, const float* w, int32_t
 
 int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
                       const float* residual, const float* gamma, const float* beta, float eps, int32_t relu,
-                      void* out, int32_t out_enc, void* stream) {
+                      void* out, int32_t out_enc, void* out2, int32_t out2_enc, void* stream) {
   if (n_partials < 1) n_partials = 1;
   SRF_CHECK_ARG(in && out && gamma && beta && rows >= 0 && n > 0, "srf_layernorm: bad args");
   SRF_CHECK_ARG(in_enc == SRF_F32 || in_enc == SRF_BF16 || in_enc == SRF_F16, "srf_layernorm: input must be f32 / bf16 / f16");
@@ -499,20 +530,20 @@ int srf_layernorm_enc(const void* in, int32_t in_enc, int64_t rows, int32_t n, i
   SRF_COUNT(1);
   if (n_partials > 1 && n <= 1024) {
     const int threads = (n + 31) / 32 * 32;
-    layernorm_cols_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, residual, gamma, beta, eps, relu, out, out_enc);
+    layernorm_cols_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, residual, gamma, beta, eps, relu, out, out_enc, out2, out2_enc);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }
   int wpb = 4;
   int grid = (int)((rows + wpb - 1) / wpb);
-  layernorm_rows_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, residual, gamma, beta, eps, relu, out, out_enc);
+  layernorm_rows_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(in, in_enc, rows, n, n_partials, bias, residual, gamma, beta, eps, relu, out, out_enc, out2, out2_enc);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }
 
 int srf_layernorm(const void* in, int32_t dtype, int64_t rows, int32_t n, int32_t n_partials, const float* bias,
                   const float* gamma, const float* beta, float eps, int32_t relu, void* out, void* stream) {
-  return srf_layernorm_enc(in, dtype, rows, n, n_partials, bias, nullptr, gamma, beta, eps, relu, out, dtype, stream);
+  return srf_layernorm_enc(in, dtype, rows, n, n_partials, bias, nullptr, gamma, beta, eps, relu, out, dtype, nullptr, 0, stream);
 }
 
 }  // extern "C"

@@ -8,6 +8,7 @@ the proposals, FFN, cls/reg towers, apply_deltas) run as plain
 so the five stages chain with real boxes; they are not part of the measured path.
 Parameter names equal the reference's, so its checkpoints load unchanged.
 """
+import ctypes
 import math
 
 import torch
@@ -57,13 +58,18 @@ def encode_rows(x, enc):
     return out
 
 
-def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None, residual=None):
+def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None, residual=None, out2_enc=None, a_cols=None,
+            ln_per_tile=False):
     """nn.Linear (+LayerNorm +ReLU) on the library's GEMMs.
 
     x: (M,K) fp32, or an (M, K|2K) tensor already in the activation encoding of `precision`.
     'fp32_simt': FFMA kernel, fp32 in/out.  Tensor-core modes: tcgen05 GEMM on operands in the
     mode's encoding (weights packed once, re-packed when they change); the result is written in
-    `out_enc` (default: the mode's activation encoding; L.F32 for an fp32 result)."""
+    `out_enc` (default: the mode's activation encoding; L.F32 for an fp32 result).
+    residual (M,N) fp32: added before the LayerNorm.  out2_enc: additionally return a second copy of the
+    result in that encoding (-> (out, out2)).  a_cols=(c0, width): A is the column block [c0, c0+K) of an encoded
+    buffer whose rows have `width` logical columns.  ln_per_tile: `ln` holds N parameters and every 128-column tile is
+    normalised on its own (two towers merged into one GEMM)."""
     lib = L.load()
     m = x.shape[0]
     k, n = lin.in_features, lin.out_features
@@ -76,9 +82,12 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None, re
         tk = lib.srf_linear_tile_k_enc(k, enc)
         if min(k, tk) not in (16, 32, 64, 128) or min(n, 128) not in (16, 32, 64, 128) or k % tk or (n > 128 and n % 128) \
                 or (ln is not None and n > 1024):
+            assert a_cols is None and not ln_per_tile
             out = _linear(L.decode(x, k) if x.dtype != torch.float32 else x, lin, 'fp32_simt', cache, key, relu, ln, residual=residual)
-            return _encode_out(out, enc if out_enc is None else out_enc)
+            res = _encode_out(out, enc if out_enc is None else out_enc)
+            return (res, _encode_out(out, out2_enc)) if out2_enc is not None else res
     if enc is None:
+        assert a_cols is None and not ln_per_tile
         x = _f(x)
         w = _f(lin.weight)
         out = torch.empty((m, n), dtype=torch.float32, device=dev)
@@ -86,15 +95,23 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None, re
         L.check(lib.srf_linear_f32(L.ptr(x), m, k, L.ptr(w), n, L.ptr(bias), int(fuse_relu), L.ptr(out), st), 'srf_linear_f32')
         if ln is not None:
             L.check(lib.srf_layernorm_enc(L.ptr(out), L.F32, m, n, 1, None, L.ptr(residual), L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)),
-                                          ln.eps, int(relu), L.ptr(out), L.F32, st), 'srf_layernorm')
+                                          ln.eps, int(relu), L.ptr(out), L.F32, None, 0, st), 'srf_layernorm')
         elif residual is not None:
             out = out + residual
             out = torch.relu_(out) if relu else out
-        return out
-    if x.dtype == torch.float32:
-        x = encode_rows(x, enc)
-    assert x.dtype == L.enc_torch_dtype(enc) and x.shape[1] == L.enc_width(enc, k), 'operand is not in the mode\'s encoding'
-    x = x.contiguous()
+        return (out, out) if out2_enc is not None else out
+    a = L.LinearArgs()
+    if a_cols is not None:
+        c0, width = a_cols
+        assert x.dtype == L.enc_torch_dtype(enc) and x.shape[1] == L.enc_width(enc, width) and x.is_contiguous()
+        a.a = x.data_ptr() + c0 * x.element_size()
+        a.a_stride, a.a_lo_off = x.shape[1], width
+    else:
+        if x.dtype == torch.float32:
+            x = encode_rows(x, enc)
+        assert x.dtype == L.enc_torch_dtype(enc) and x.shape[1] == L.enc_width(enc, k), 'operand is not in the mode\'s encoding'
+        x = x.contiguous()
+        a.a = x.data_ptr()
 
     def pack():
         wp = torch.empty((L.enc_width(enc, n * k),), dtype=L.enc_torch_dtype(enc), device=dev)
@@ -106,36 +123,43 @@ def _linear(x, lin, precision, cache, key, relu=False, ln=None, out_enc=None, re
 
     def alloc(e):
         return torch.empty((m, L.enc_width(e, n)), dtype=L.enc_torch_dtype(e), device=dev)
+    a.a_enc, a.m, a.k, a.w, a.n = enc, m, k, L.ptr(wp), n
+    a.ln_eps, a.k_splits = eps, 1
     # few output tiles but a long reduction (DynamicConv.out_layer: 900 x 6272 -> 128): split K
     # over CTAs, fp32 partials in per-split slabs, bias + LayerNorm + ReLU in one pass after
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
     kvol = k // lib.srf_linear_tile_k_enc(k, enc)
-    if ln is not None and tiles * 4 <= 148 and kvol >= 8:
+    if ln is not None and not ln_per_tile and tiles * 4 <= 148 and kvol >= 8:
         splits = lib.srf_linear_splits_enc(k, enc, min(kvol, max(1, 148 // tiles)))
         part = torch.empty((splits, m, n), dtype=torch.float32, device=dev)
-        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, None, None, 0, None, None, eps, L.ptr(part), L.F32, splits, st),
-                'srf_linear_tc')
+        a.out, a.out_enc, a.k_splits = L.ptr(part), L.F32, splits
+        L.check(lib.srf_linear(ctypes.byref(a), st), 'srf_linear')
         out = alloc(out_enc)
+        out2 = alloc(out2_enc) if out2_enc is not None else None
         L.check(lib.srf_layernorm_enc(L.ptr(part), L.F32, m, n, splits, L.ptr(bias), L.ptr(residual), L.ptr(_f(ln.weight)),
-                                      L.ptr(_f(ln.bias)), eps, int(relu), L.ptr(out), out_enc, st), 'srf_layernorm')
-        return out
-    fuse_ln = ln is not None and n <= 128
-    epi = (1 if relu and (ln is None or fuse_ln) else 0) | (2 if fuse_ln else 0)
-    lnw = _f(ln.weight) if fuse_ln else None
-    lnb = _f(ln.bias) if fuse_ln else None
+                                      L.ptr(_f(ln.bias)), eps, int(relu), L.ptr(out), out_enc, L.ptr(out2), out2_enc or 0, st), 'srf_layernorm')
+        return (out, out2) if out2_enc is not None else out
+    fuse_ln = ln is not None and (n <= 128 or ln_per_tile)
     if ln is not None and not fuse_ln:
         tmp = alloc(L.F32)
-        L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), None, 0, None, None, eps, L.ptr(tmp), L.F32, 1, st),
-                'srf_linear_tc')
+        a.bias, a.out, a.out_enc = L.ptr(bias), L.ptr(tmp), L.F32
+        L.check(lib.srf_linear(ctypes.byref(a), st), 'srf_linear')
         out = alloc(out_enc)
+        out2 = alloc(out2_enc) if out2_enc is not None else None
         L.check(lib.srf_layernorm_enc(L.ptr(tmp), L.F32, m, n, 1, None, L.ptr(residual), L.ptr(_f(ln.weight)), L.ptr(_f(ln.bias)), eps,
-                                      int(relu), L.ptr(out), out_enc, st), 'srf_layernorm')
-        return out
+                                      int(relu), L.ptr(out), out_enc, L.ptr(out2), out2_enc or 0, st), 'srf_layernorm')
+        return (out, out2) if out2_enc is not None else out
     out = alloc(out_enc)
+    out2 = alloc(out2_enc) if out2_enc is not None else None
     assert residual is None or out_enc == L.F32, 'a fused residual is read in the output encoding (fp32 here)'
-    L.check(lib.srf_linear_tc(L.ptr(x), enc, m, k, L.ptr(wp), n, L.ptr(bias), L.ptr(residual), epi, L.ptr(lnw), L.ptr(lnb), eps,
-                              L.ptr(out), out_enc, 1, st), 'srf_linear_tc')
-    return out
+    lnw = _f(ln.weight) if fuse_ln else None
+    lnb = _f(ln.bias) if fuse_ln else None
+    a.bias, a.residual = L.ptr(bias), L.ptr(residual)
+    a.epi = (1 if relu else 0) | (2 if fuse_ln else 0)
+    a.ln_w, a.ln_b, a.ln_per_tile = L.ptr(lnw), L.ptr(lnb), int(bool(ln_per_tile))
+    a.out, a.out_enc, a.out2, a.out2_enc = L.ptr(out), out_enc, L.ptr(out2), out2_enc or 0
+    L.check(lib.srf_linear(ctypes.byref(a), st), 'srf_linear')
+    return (out, out2) if out2_enc is not None else out
 
 
 class DynamicConv(nn.Module):
@@ -154,16 +178,17 @@ class DynamicConv(nn.Module):
         self.norm3 = nn.LayerNorm(feat_channels)
         self._cache = {}
 
-    def make_params(self, prop_feats, precision=None):
+    def make_params(self, prop_feats, precision=None, prop_enc=None):
         """dynamic_layer(prop_feats): (K,C) -> (K, 2*C*d).  Depends only on the proposal features,
         so callers may run it concurrently with the RoI sampling of the same stage.  The split
         ('fp32') mode keeps the generated parameters in fp32 (the interaction kernel splits them)."""
         precision = precision or registry.get_precision()
         enc = registry.act_enc(precision)
         out_enc = L.F32 if (enc is None or L.enc_is_split(enc)) else enc
-        return _linear(prop_feats, self.dynamic_layer, precision, self._cache, ('dyn', str(prop_feats.device)), out_enc=out_enc)
+        x = prop_enc if (prop_enc is not None and enc is not None) else prop_feats
+        return _linear(x, self.dynamic_layer, precision, self._cache, ('dyn', str(prop_feats.device)), out_enc=out_enc)
 
-    def forward_kc(self, prop_feats, roi_feats, precision=None, params=None):
+    def forward_kc(self, prop_feats, roi_feats, precision=None, params=None, prop_enc=None):
         """prop_feats (K,C) f32; roi_feats (K,49,C) f32 or (K,49,C|2C) in the mode's encoding
         (channel-last RoI features) -> (K,C) f32."""
         precision = precision or registry.get_precision()
@@ -173,7 +198,7 @@ class DynamicConv(nn.Module):
         dev = prop_feats.device
         enc = registry.act_enc(precision)
         if params is None:
-            params = self.make_params(prop_feats, precision)
+            params = self.make_params(prop_feats, precision, prop_enc=prop_enc)
         roi_feats = roi_feats.contiguous()
         if enc is not None and (c, d) not in ((128, 32), (256, 64)):
             # dims without a tensor-core interaction kernel: FFMA kernel on fp32 buffers
@@ -231,6 +256,38 @@ class _SingleHeadBase(nn.Module):
 
     # dense tail of a stage: attention, interaction, FFN, towers, box update -- all on this
     # library's kernels (tcgen05 GEMMs with bias / residual / LayerNorm / ReLU epilogues, fp32 attention core)
+    def _merged_towers(self, dev):
+        """cls | reg towers as merged GEMMs (both are stacks of Linear(C, C, bias=False) + LayerNorm + ReLU, C = 128):
+        layer 0 shares its input -> one (C -> 2C) GEMM; deeper layers pair up as block-diagonal (2C -> 2C) GEMMs; one
+        LayerNorm per 128-column tile.  Returns [(view, ln_view, n_pairs)] or None when the shapes do not allow it."""
+        C = self.feat_channels_lidar
+        ncls, nreg = len(self.cls_module_lidar) // 3, len(self.reg_module_lidar) // 3
+        if C != 128 or ncls < 1 or nreg < ncls:
+            return None
+        cache = self.__dict__.setdefault('_tail_cache', {})
+        src = [p for mods in (self.cls_module_lidar, self.reg_module_lidar) for p in mods.parameters()]
+
+        def make():
+            layers = []
+            for t in range(ncls):
+                cl, rl = self.cls_module_lidar[3 * t], self.reg_module_lidar[3 * t]
+                cn, rn = self.cls_module_lidar[3 * t + 1], self.reg_module_lidar[3 * t + 1]
+                if t == 0:
+                    w = torch.cat([cl.weight, rl.weight], 0)                      # (2C, C)
+                else:
+                    w = torch.zeros(2 * C, 2 * C, device=dev)
+                    w[:C, :C], w[C:, C:] = cl.weight, rl.weight                     # block diagonal
+                ln = nn.LayerNorm(C, eps=cn.eps)                                   # holder of the concatenated parameters
+                ln.weight = nn.Parameter(torch.cat([cn.weight, rn.weight]).detach().to(dev), requires_grad=False)
+                ln.bias = nn.Parameter(torch.cat([cn.bias, rn.bias]).detach().to(dev), requires_grad=False)
+                assert cn.eps == rn.eps
+                layers.append((_LinearView(w.detach().to(dev).contiguous(), None), ln))
+            return layers
+        return _cached(cache, ('towers', str(dev)), src, make)
+
+    # dense tail of a stage (SURVEY.md 8f rank 2): attention, interaction, FFN, towers, box update -- all on this
+    # library's kernels (tcgen05 GEMMs with bias / residual / LayerNorm / ReLU epilogues, fp32 attention core).
+    # The fp32 trunk and the 16-bit operand of the next GEMM come out of the same epilogue (dual outputs).
     def _stage_tail(self, roi_feats_kc, bboxes, prop_feats, bs, n_p, precision=None):
         precision = precision or registry.get_precision()
         lib = L.load()
@@ -247,25 +304,52 @@ class _SingleHeadBase(nn.Module):
         qkv = _linear(x, _LinearView(mha.in_proj_weight, mha.in_proj_bias), precision, cache, 'in_proj', out_enc=L.F32)
         att = torch.empty((k, L.enc_width(act, C)), dtype=L.enc_torch_dtype(act), device=dev)
         L.check(lib.srf_mha_attention(L.ptr(qkv), bs, n_p, mha.num_heads, C // mha.num_heads, L.ptr(att), act, st), 'srf_mha_attention')
-        prop = _linear(att, mha.out_proj, precision, cache, 'out_proj', ln=self.norm1_lidar, residual=x, out_enc=L.F32)
+        prop, prop_e = _linear(att, mha.out_proj, precision, cache, 'out_proj', ln=self.norm1_lidar, residual=x, out_enc=L.F32, out2_enc=act)
         # instance interaction (:2289-2297)
-        prop2 = self.inst_interact_lidar.forward_kc(prop, roi_feats_kc, precision)
+        prop2 = self.inst_interact_lidar.forward_kc(prop, roi_feats_kc, precision, prop_enc=prop_e)
         obj = torch.empty_like(prop)
+        obj_e = torch.empty((k, L.enc_width(act, C)), dtype=L.enc_torch_dtype(act), device=dev) if act != L.F32 else None
         L.check(lib.srf_layernorm_enc(L.ptr(prop2), L.F32, k, C, 1, None, L.ptr(prop), L.ptr(_f(self.norm2_lidar.weight)),
-                                      L.ptr(_f(self.norm2_lidar.bias)), self.norm2_lidar.eps, 0, L.ptr(obj), L.F32, st), 'srf_layernorm')
+                                      L.ptr(_f(self.norm2_lidar.bias)), self.norm2_lidar.eps, 0, L.ptr(obj), L.F32, L.ptr(obj_e), act, st),
+                'srf_layernorm')
         # FFN (:2299-2304)
-        hid = _linear(obj, self.linear1_lidar, precision, cache, 'ffn1', relu=True)
-        obj = _linear(hid, self.linear2_lidar, precision, cache, 'ffn2', ln=self.norm3_lidar, residual=obj, out_enc=L.F32)
+        hid = _linear(obj_e if obj_e is not None else obj, self.linear1_lidar, precision, cache, 'ffn1', relu=True)
+        obj, obj_e = _linear(hid, self.linear2_lidar, precision, cache, 'ffn2', ln=self.norm3_lidar, residual=obj, out_enc=L.F32, out2_enc=act)
         # towers (:2306-2313): (Linear(no bias), LayerNorm, ReLU) x n, then the two small projections
-        obj_e = encode_rows(obj, act) if act != L.F32 else obj
+        merged = self._merged_towers(dev) if enc is not None else None
+        if merged is not None:
+            ncls = len(merged)
+            f_e, f32 = obj_e, None
+            for t, (lin, ln) in enumerate(merged):
+                last = t == ncls - 1
+                r = _linear(f_e, lin, precision, cache, ('tw', t), relu=True, ln=ln, ln_per_tile=True, out_enc=L.F32 if last else None,
+                            out2_enc=act if last else None)
+                f32, f_e = r if last else (None, r)
+            cls_f = f32[:, :C].contiguous()
+            reg_f, mods = None, self.reg_module_lidar
+            nreg = len(mods) // 3
+            if nreg == ncls:
+                reg_f = f32[:, C:].contiguous()
+            for t in range(ncls, nreg):                      # the regression tower is deeper: its remaining layers run alone
+                lastr = t == nreg - 1
+                a_cols = (C, 2 * C) if t == ncls else None
+                reg_in = f_e if t == ncls else reg_in_next
+                r = _linear(reg_in, mods[3 * t], precision, cache, ('reg', t), relu=True, ln=mods[3 * t + 1], out_enc=L.F32 if lastr else None,
+                            a_cols=a_cols)
+                if lastr:
+                    reg_f = r
+                else:
+                    reg_in_next = r
+        else:
+            obj_in = obj_e if obj_e is not None else obj
 
-        def tower(mods, tag):
-            f = obj_e
-            for t in range(0, len(mods), 3):
-                last = t + 3 >= len(mods)
-                f = _linear(f, mods[t], precision, cache, (tag, t), relu=True, ln=mods[t + 1], out_enc=L.F32 if last else None)
-            return f if f.dtype == torch.float32 else L.decode(f, C)
-        cls_f, reg_f = tower(self.cls_module_lidar, 'cls'), tower(self.reg_module_lidar, 'reg')
+            def tower(mods, tag):
+                f = obj_in
+                for t in range(0, len(mods), 3):
+                    last = t + 3 >= len(mods)
+                    f = _linear(f, mods[t], precision, cache, (tag, t), relu=True, ln=mods[t + 1], out_enc=L.F32 if last else None)
+                return f if f.dtype == torch.float32 else L.decode(f, C)
+            cls_f, reg_f = tower(self.cls_module_lidar, 'cls'), tower(self.reg_module_lidar, 'reg')
         logits = _linear(cls_f, self.class_logits_lidar, 'fp32_simt', cache, 'logits')
         deltas = _linear(reg_f, self.bboxes_delta_lidar, 'fp32_simt', cache, 'deltas')
         pred = self.apply_deltas_lidar(deltas, bboxes.view(-1, len(self.bbox_weights)))
