@@ -10,8 +10,8 @@
 
 namespace srf {
 
-constexpr int PILLAR_MAXT = 64;     // point slots per pillar
-constexpr int PILLAR_MAXF = 16;     // decorated features per point
+constexpr int PILLAR_MAXT = 1024;   // point slots per pillar
+constexpr int PILLAR_MAXF = 64;     // decorated features per point
 
 struct PillarArgs {
   const float* voxels;      // (cap, T, C)
@@ -27,74 +27,62 @@ struct PillarArgs {
   float* out;               // (cap, cout)
 };
 
-// one block per pillar, one thread per output channel (cout <= 128)
-__global__ void __launch_bounds__(128) pillar_vfe_kernel(const PillarArgs a) {
-  __shared__ float sf[PILLAR_MAXT][PILLAR_MAXF + 1];
-  __shared__ float smean[3];
+// one thread per (pillar, output channel): the T x F decorated features are recomputed by every channel's thread
+// (a few hundred flops; the pillar's 100-odd input floats are L1 hits after the first thread) -- no staging, no
+// dynamically indexed arrays.  Weights are read through the read-only cache (one row of F floats per thread).
+__global__ void __launch_bounds__(256) pillar_vfe_kernel(const PillarArgs a) {
   const int n = a.d_n ? min(*a.d_n, a.cap) : a.cap;
-  for (int v = blockIdx.x; v < n; v += gridDim.x) {
+  const long long total = (long long)n * a.cout;
+  const bool alias = a.with_center && a.legacy;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(e / a.cout), co = (int)(e % a.cout);
     const float* pv = a.voxels + (size_t)v * a.T * a.C;
     const int np = __ldg(a.num_points + v);
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      // points_mean = features[:, :, :3].sum(dim=1) / num_points (padded slots are zeros, in slot order)
-      float s = 0.f;
-      for (int t = 0; t < a.T; ++t) s += __ldg(pv + t * a.C + threadIdx.x);
-      smean[threadIdx.x] = s / (float)np;
+    const int32_t* cq = a.coors + (size_t)v * 4;
+    const float ctr_x = (float)__ldg(cq + 3) * a.vx + a.xo, ctr_y = (float)__ldg(cq + 2) * a.vy + a.yo,
+                ctr_z = (float)__ldg(cq + 1) * a.vz + a.zo;
+    // points_mean = features[:, :, :3].sum(dim=1) / num_points (padded slots are zeros, summed in slot order)
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    for (int t = 0; t < a.T; ++t) {
+      mx += __ldg(pv + t * a.C);
+      my += __ldg(pv + t * a.C + 1);
+      mz += __ldg(pv + t * a.C + 2);
     }
-    __syncthreads();
-    if (threadIdx.x < a.T) {
-      const int t = threadIdx.x;
-      const int4 q = __ldg(reinterpret_cast<const int4*>(a.coors) + v);
-      float raw[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) raw[c] = c < a.C ? __ldg(pv + t * a.C + c) : 0.f;     // fully unrolled: stays in registers
-      const float cx = raw[0] - ((float)q.w * a.vx + a.xo), cy = raw[1] - ((float)q.z * a.vy + a.yo),
-                  cz = raw[2] - ((float)q.y * a.vz + a.zo);
-      // features are written straight to shared memory one scalar at a time (a register array filled through a
-      // running index made ptxas pair the stores into 8-byte local stores at 4-byte-aligned offsets)
-      const float m = t < np ? 1.f : 0.f;     // get_paddings_indicator
-      float* f = sf[t];
-      int k = 0;
-      // legacy=True: f_center aliases features[:, :, :3] and is modified in place, so the raw xyz
-      // channels carry the centre offsets too (pillar_encoder_custom.py:133-143)
-      const bool alias = a.with_center && a.legacy;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < a.C) f[k++] = m * ((alias && c < 3) ? (c == 0 ? cx : (c == 1 ? cy : cz)) : raw[c]);
+    mx /= (float)np; my /= (float)np; mz /= (float)np;
+    const float* wr = a.w + (size_t)co * a.F;
+    const float bias = __ldg(a.b + co);
+    float red = a.avg ? 0.f : -INFINITY;
+    for (int t = 0; t < a.T; ++t) {
+      const float m = t < np ? 1.f : 0.f;     // get_paddings_indicator: the decorated features of a padded slot are zeroed
+      const float* pt = pv + t * a.C;
+      const float x = __ldg(pt), y = __ldg(pt + 1), z = __ldg(pt + 2);
+      const float cx = x - ctr_x, cy = y - ctr_y, cz = z - ctr_z;
+      int j = 0;
+      float acc = 0.f;
+      // legacy=True: f_center aliases features[:, :, :3] and is modified in place, so the raw xyz channels carry the
+      // centre offsets too (pillar_encoder_custom.py:133-143)
+      acc = fmaf(m * (alias ? cx : x), __ldg(wr + j++), acc);
+      acc = fmaf(m * (alias ? cy : y), __ldg(wr + j++), acc);
+      acc = fmaf(m * (alias ? cz : z), __ldg(wr + j++), acc);
+      for (int c = 3; c < a.C; ++c) acc = fmaf(m * __ldg(pt + c), __ldg(wr + j++), acc);
       if (a.with_cluster) {
-        f[k++] = m * (raw[0] - smean[0]);
-        f[k++] = m * (raw[1] - smean[1]);
-        f[k++] = m * (raw[2] - smean[2]);
+        acc = fmaf(m * (x - mx), __ldg(wr + j++), acc);
+        acc = fmaf(m * (y - my), __ldg(wr + j++), acc);
+        acc = fmaf(m * (z - mz), __ldg(wr + j++), acc);
       }
       if (a.with_center) {
-        f[k++] = m * cx;
-        f[k++] = m * cy;
-        f[k++] = m * cz;
+        acc = fmaf(m * cx, __ldg(wr + j++), acc);
+        acc = fmaf(m * cy, __ldg(wr + j++), acc);
+        acc = fmaf(m * cz, __ldg(wr + j++), acc);
       }
       if (a.with_distance) {
-        const float dx = alias ? cx : raw[0], dy = alias ? cy : raw[1], dz = alias ? cz : raw[2];
-        f[k++] = m * sqrtf(dx * dx + dy * dy + dz * dz);
+        const float dx = alias ? cx : x, dy = alias ? cy : y, dz = alias ? cz : z;
+        acc = fmaf(m * sqrtf(dx * dx + dy * dy + dz * dz), __ldg(wr + j++), acc);
       }
+      const float yv = fmaxf(acc + bias, 0.f);
+      red = a.avg ? red + yv : fmaxf(red, yv);
     }
-    __syncthreads();
-    if (threadIdx.x < a.cout) {
-      const float* wr = a.w + (size_t)threadIdx.x * a.F;
-      float wreg[PILLAR_MAXF];
-#pragma unroll
-      for (int j = 0; j < PILLAR_MAXF; ++j) wreg[j] = j < a.F ? __ldg(wr + j) : 0.f;
-      const float bias = __ldg(a.b + threadIdx.x);
-      float red = a.avg ? 0.f : -INFINITY;
-      for (int t = 0; t < a.T; ++t) {
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < PILLAR_MAXF; ++j)
-          if (j < a.F) acc = fmaf(sf[t][j], wreg[j], acc);
-        const float y = fmaxf(acc + bias, 0.f);
-        red = a.avg ? red + y : fmaxf(red, y);
-      }
-      a.out[(size_t)v * a.cout + threadIdx.x] = a.avg ? red / (float)np : red;
-    }
+    a.out[e] = a.avg ? red / (float)np : red;
   }
 }
 
@@ -124,10 +112,11 @@ int srf_pillar_vfe(const float* voxels, const int32_t* num_points, const int32_t
                    int32_t t, int32_t c, const float* w_folded, const float* b_folded, int32_t cout, const float voxel_size[3],
                    const float offsets[3], int32_t flags, float* out, void* stream) {
   SRF_CHECK_ARG(voxels && num_points && coors && w_folded && b_folded && out && voxel_size && offsets, "srf_pillar_vfe: null arg");
-  SRF_CHECK_ARG(cap >= 0 && t >= 1 && t <= PILLAR_MAXT && c >= 3 && c <= 8 && cout >= 1 && cout <= 128,
-                "srf_pillar_vfe: need 1 <= T <= %d, 3 <= C <= 8, cout <= 128", PILLAR_MAXT);
+  SRF_CHECK_ARG(cap >= 0 && t >= 1 && t <= PILLAR_MAXT && c >= 3 && c <= 8 && cout >= 1,
+                "srf_pillar_vfe: need 1 <= T <= %d, 3 <= C <= 8", PILLAR_MAXT);
   if (cap == 0) return SRF_OK;
-  PillarArgs a;
+  PillarArgs a = {};
+  a.out = out;
   a.voxels = voxels; a.num_points = num_points; a.coors = coors; a.d_n = d_n; a.cap = cap; a.T = t; a.C = c;
   a.w = w_folded; a.b = b_folded; a.cout = cout;
   a.vx = voxel_size[0]; a.vy = voxel_size[1]; a.vz = voxel_size[2];
@@ -136,9 +125,10 @@ int srf_pillar_vfe(const float* voxels, const int32_t* num_points, const int32_t
   a.legacy = (flags >> 3) & 1; a.avg = (flags >> 4) & 1;
   a.F = c + (a.with_cluster ? 3 : 0) + (a.with_center ? 3 : 0) + (a.with_distance ? 1 : 0);
   SRF_CHECK_ARG(a.F <= PILLAR_MAXF, "srf_pillar_vfe: too many decorated features");
-  int grid = cap < sm_count() * 16 ? cap : sm_count() * 16;
+  long long g = ((long long)cap * cout + 255) / 256;
+  if (g > sm_count() * 16) g = sm_count() * 16;
   SRF_COUNT(1);
-  pillar_vfe_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  pillar_vfe_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(a);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }
