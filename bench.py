@@ -144,8 +144,9 @@ def kernel_families(pipe, pts, pk, torch, reps=3):
         fams = profiling.families(cap, ctx, pk)
         tot = sum(f['ms'] for f in fams)
         if best is None or tot < best[0]:
-            best = (tot, fams, sparse)
-    tot, fams, sparse = best
+            best = (tot, fams, sparse, list(cap.per_call))
+    tot, fams, sparse, per_call = best
+    kernel_families.per_call = per_call
     for f in fams:
         f['share_of_kernel_time'] = round(f['ms'] / tot, 4)
     return fams, round(tot, 4), [dict(flops=f, bytes=b, **d) for f, b, d in sparse]
@@ -319,7 +320,7 @@ def main():
         if args.kernels_out:
             with open(args.kernels_out, 'w') as f:
                 json.dump(dict(workload=args.workload, scope=args.scope, precision=args.precision, kernel_ms_per_frame=kernel_ms,
-                               families=kernels, sparse_conv_layers=sparse_layers), f, indent=1)
+                               families=kernels, sparse_conv_layers=sparse_layers, calls_in_order=kernel_families.per_call), f, indent=1)
         dom = kernels[0]
         traffic, traffic_src = None, None
         try:

@@ -18,82 +18,109 @@ namespace srf {
 // ------------------------------------------------------------------------------------------------
 // Self-attention core.  qkv (B*P, 3C) fp32 = in_proj(x) (q | k | v, each H heads x HD), rows batch-major.
 // out (B*P, C) = softmax(q k^T / sqrt(HD)) v per (batch, head), written in any encoding (A operand of
-// the out_proj GEMM).  Block = 32 queries x 8 key partitions; K/V of the (batch, head) stream through
-// shared memory in chunks; online softmax per thread, partitions merged with shuffles.
+// the out_proj GEMM).  fp32 FFMA (exact softmax weights in every precision mode).
+// Block = 32 query groups x 8 key partitions; a thread owns QT queries (register tile: every K / V value read
+// from shared memory feeds QT FMAs) and the keys j == part (mod 8).  K and V of the (batch, head) stream through
+// shared memory in chunks, stored TRANSPOSED ([d][key]) so the 8 partitions of a warp read 8 consecutive words
+// (conflict-free) and the 4 query groups of a warp share them by broadcast.  Online softmax per thread,
+// partitions merged with shuffles.
 // ------------------------------------------------------------------------------------------------
-constexpr int ATT_QB = 32, ATT_KP = 8, ATT_CHUNK = 128;     // 232 CTAs of 8 warps for 900 proposals x 8 heads
+constexpr int ATT_QG = 32, ATT_KP = 8, ATT_CHUNK = 128;
 
-template <int HD>
-__global__ void __launch_bounds__(ATT_QB* ATT_KP) mha_attention_kernel(const float* __restrict__ qkv, int n_p, int n_heads, float scale,
+template <int HD, int QT>
+__global__ void __launch_bounds__(ATT_QG* ATT_KP) mha_attention_kernel(const float* __restrict__ qkv, int n_p, int n_heads, float scale,
                                                                        void* __restrict__ out, int out_enc) {
-  __shared__ __align__(16) float sK[ATT_CHUNK][HD];
-  __shared__ __align__(16) float sV[ATT_CHUNK][HD];
+  __shared__ float sK[HD][ATT_CHUNK + 1];
+  __shared__ float sV[HD][ATT_CHUNK + 1];
   const int C = n_heads * HD;
   const int b = blockIdx.z, h = blockIdx.y;
-  const int qi = blockIdx.x * ATT_QB + threadIdx.x / ATT_KP, part = threadIdx.x % ATT_KP;
+  const int part = threadIdx.x % ATT_KP, qg = threadIdx.x / ATT_KP;
+  const int q0 = (blockIdx.x * ATT_QG + qg) * QT;
   const size_t row0 = (size_t)b * n_p;
-  float q[HD], acc[HD];
-  const bool live = qi < n_p;
+  float q[QT][HD], acc[QT][HD], m[QT], l[QT];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) {
-    q[d] = live ? __ldg(qkv + (row0 + qi) * 3 * C + h * HD + d) * scale : 0.f;
-    acc[d] = 0.f;
+  for (int t = 0; t < QT; ++t) {
+    const bool live = q0 + t < n_p;
+    m[t] = -INFINITY;
+    l[t] = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      q[t][d] = live ? __ldg(qkv + (row0 + q0 + t) * 3 * C + h * HD + d) * scale : 0.f;
+      acc[t][d] = 0.f;
+    }
   }
-  float m = -INFINITY, l = 0.f;
   for (int k0 = 0; k0 < n_p; k0 += ATT_CHUNK) {
     __syncthreads();
-    for (int e = threadIdx.x; e < ATT_CHUNK * HD / 4; e += blockDim.x) {
-      const int j = e / (HD / 4), d4 = e % (HD / 4);
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    for (int e = threadIdx.x; e < ATT_CHUNK * HD; e += blockDim.x) {
+      const int j = e / HD, d = e % HD;                  // consecutive threads read consecutive d of one key (coalesced)
+      float kv = 0.f, vv = 0.f;
       if (k0 + j < n_p) {
-        const float* base = qkv + (row0 + k0 + j) * 3 * C + h * HD + d4 * 4;
-        kv = __ldg(reinterpret_cast<const float4*>(base + C));
-        vv = __ldg(reinterpret_cast<const float4*>(base + 2 * C));
+        const float* base = qkv + (row0 + k0 + j) * 3 * C + h * HD + d;
+        kv = __ldg(base + C);
+        vv = __ldg(base + 2 * C);
       }
-      *reinterpret_cast<float4*>(&sK[j][d4 * 4]) = kv;
-      *reinterpret_cast<float4*>(&sV[j][d4 * 4]) = vv;
+      sK[d][j] = kv;
+      sV[d][j] = vv;
     }
     __syncthreads();
     const int kn = min(ATT_CHUNK, n_p - k0);
     for (int j = part; j < kn; j += ATT_KP) {
-      float s = 0.f;
+      float s[QT];
 #pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(q[d], sK[j][d], s);
-      const float mn = fmaxf(m, s);
-      const float corr = __expf(m - mn), p = __expf(s - mn);
-      l = l * corr + p;
+      for (int t = 0; t < QT; ++t) s[t] = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = fmaf(acc[d], corr, p * sV[j][d]);
-      m = mn;
+      for (int d = 0; d < HD; ++d) {
+        const float kv = sK[d][j];
+#pragma unroll
+        for (int t = 0; t < QT; ++t) s[t] = fmaf(q[t][d], kv, s[t]);
+      }
+      float p[QT], corr[QT];
+#pragma unroll
+      for (int t = 0; t < QT; ++t) {
+        const float mn = fmaxf(m[t], s[t]);
+        corr[t] = __expf(m[t] - mn);
+        p[t] = __expf(s[t] - mn);
+        l[t] = l[t] * corr[t] + p[t];
+        m[t] = mn;
+      }
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        const float vv = sV[d][j];
+#pragma unroll
+        for (int t = 0; t < QT; ++t) acc[t][d] = fmaf(acc[t][d], corr[t], p[t] * vv);
+      }
     }
   }
-  // merge the ATT_KP partitions of a query (adjacent lanes)
 #pragma unroll
-  for (int o = 1; o < ATT_KP; o <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
-    const float mn = fmaxf(m, m2);
-    const float c1 = (m == -INFINITY) ? 0.f : __expf(m - mn), c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
-    l = l * c1 + l2 * c2;
+  for (int t = 0; t < QT; ++t) {
+    // merge the ATT_KP partitions of a query (adjacent lanes)
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = acc[d] * c1 + __shfl_xor_sync(0xffffffffu, acc[d], o) * c2;
-    m = mn;
-  }
-  if (live && part == 0) {
-    const float inv = 1.f / l;
-    const size_t row = row0 + qi;
-    if (out_enc == SRF_F32) {
-      float* o = (float*)out + row * C + h * HD;
+    for (int o = 1; o < ATT_KP; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m[t], o), l2 = __shfl_xor_sync(0xffffffffu, l[t], o);
+      const float mn = fmaxf(m[t], m2);
+      const float c1 = (m[t] == -INFINITY) ? 0.f : __expf(m[t] - mn), c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+      l[t] = l[t] * c1 + l2 * c2;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) o[d] = acc[d] * inv;
-    } else {
-      const bool f16 = enc_is_f16(out_enc), split = enc_is_split(out_enc);
-      uint16_t* o = (uint16_t*)out + row * C * (split ? 2 : 1) + h * HD;
+      for (int d = 0; d < HD; ++d) acc[t][d] = acc[t][d] * c1 + __shfl_xor_sync(0xffffffffu, acc[t][d], o) * c2;
+      m[t] = mn;
+    }
+    if (q0 + t < n_p && part == 0) {
+      const float inv = 1.f / l[t];
+      const size_t row = row0 + q0 + t;
+      if (out_enc == SRF_F32) {
+        float* o = (float*)out + row * C + h * HD;
 #pragma unroll
-      for (int d = 0; d < HD; d += 2) {
-        uint32_t hi, lo;
-        split16x2(f16, acc[d] * inv, acc[d + 1] * inv, hi, lo);
-        *reinterpret_cast<uint32_t*>(o + d) = hi;
-        if (split) *reinterpret_cast<uint32_t*>(o + C + d) = lo;
+        for (int d = 0; d < HD; ++d) o[d] = acc[t][d] * inv;
+      } else {
+        const bool f16 = enc_is_f16(out_enc), split = enc_is_split(out_enc);
+        uint16_t* o = (uint16_t*)out + row * C * (split ? 2 : 1) + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 2) {
+          uint32_t hi, lo;
+          split16x2(f16, acc[t][d] * inv, acc[t][d + 1] * inv, hi, lo);
+          *reinterpret_cast<uint32_t*>(o + d) = hi;
+          if (split) *reinterpret_cast<uint32_t*>(o + C + d) = lo;
+        }
       }
     }
   }
@@ -346,14 +373,14 @@ int srf_mha_attention(const float* qkv, int32_t n_batch, int32_t n_p, int32_t n_
   SRF_CHECK_ARG(qkv && out && n_batch >= 1 && n_p >= 0 && n_heads >= 1, "srf_mha_attention: bad args");
   SRF_CHECK_ARG(out_enc == SRF_F32 || enc_is_16(out_enc), "srf_mha_attention: bad output encoding");
   if (n_p == 0) return SRF_OK;
-  dim3 grid(cdiv(n_p, ATT_QB), n_heads, n_batch);
   const float scale = 1.f / sqrtf((float)head_dim);
   cudaStream_t st = (cudaStream_t)stream;
   SRF_COUNT(1);
-  switch (head_dim) {
-    case 8: mha_attention_kernel<8><<<grid, ATT_QB * ATT_KP, 0, st>>>(qkv, n_p, n_heads, scale, out, out_enc); break;
-    case 16: mha_attention_kernel<16><<<grid, ATT_QB * ATT_KP, 0, st>>>(qkv, n_p, n_heads, scale, out, out_enc); break;
-    case 32: mha_attention_kernel<32><<<grid, ATT_QB * ATT_KP, 0, st>>>(qkv, n_p, n_heads, scale, out, out_enc); break;
+  constexpr int T = ATT_QG * ATT_KP;
+  switch (head_dim) {     // QT queries per thread: 2 (64 queries per block: 120 blocks for 900 proposals x 8 heads), 1 for 32-wide heads
+    case 8: mha_attention_kernel<8, 2><<<dim3(cdiv(n_p, ATT_QG * 2), n_heads, n_batch), T, 0, st>>>(qkv, n_p, n_heads, scale, out, out_enc); break;
+    case 16: mha_attention_kernel<16, 2><<<dim3(cdiv(n_p, ATT_QG * 2), n_heads, n_batch), T, 0, st>>>(qkv, n_p, n_heads, scale, out, out_enc); break;
+    case 32: mha_attention_kernel<32, 1><<<dim3(cdiv(n_p, ATT_QG), n_heads, n_batch), T, 0, st>>>(qkv, n_p, n_heads, scale, out, out_enc); break;
     default: set_error("srf_mha_attention: head_dim must be 8/16/32 (got %d)", head_dim); return SRF_ERR_UNSUPPORTED;
   }
   SRF_LAUNCH_CHECK();

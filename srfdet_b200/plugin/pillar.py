@@ -96,8 +96,8 @@ class PointPillarsScatter(nn.Module):
         n, c = voxel_features.shape
         if batch_size is None:
             batch_size = int(coors[:, 0].max().item()) + 1 if n else 1
-        canvas = torch.zeros((batch_size, c, self.ny, self.nx), dtype=torch.float32, device=voxel_features.device,
-                             memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+        canvas = torch.empty((batch_size, c, self.ny, self.nx), dtype=torch.float32, device=voxel_features.device,
+                             memory_format=torch.channels_last if self.channels_last else torch.contiguous_format).zero_()
         L.check(L.load().srf_pillars_scatter(L.ptr(voxel_features), L.ptr(coors), n, L.ptr(num_voxels), c, self.ny, self.nx,
                                              int(self.channels_last), canvas.data_ptr(), L.stream_ptr()), 'srf_pillars_scatter')
         return canvas

@@ -26,6 +26,7 @@ def _iv(x):
 class Capture:
     def __init__(self):
         self.calls = []       # (name, args tuple, struct summary, start event, end event)
+        self.per_call = []    # (ms, name, family) filled by families()
 
 
 @contextlib.contextmanager
@@ -46,6 +47,9 @@ def capture():
             if isinstance(a0, L.ConvArgs):
                 summary = dict(cin=a0.cin, cout=a0.cout, kvol=a0.kvol, cap=a0.cap_out, in_enc=a0.in_dtype, out_enc=a0.out_dtype,
                                dense=bool(a0.dense), in_rows=a0.in_rows)
+            elif isinstance(a0, L.LinearArgs):
+                summary = dict(enc=a0.a_enc, m=a0.m, k=a0.k, n=a0.n, out_enc=a0.out_enc, out2=bool(a0.out2), out2_enc=a0.out2_enc,
+                               k_splits=max(1, a0.k_splits))
             elif isinstance(a0, L.Pyramid):
                 summary = dict(channels=a0.channels, levels=a0.n_levels, hw=[(a0.h[i], a0.w[i]) for i in range(a0.n_levels)])
                 for a in args:
@@ -81,8 +85,8 @@ def _family(name, a, s):
         return 'BEV RoIAlign'
     if name == 'srf_img_roi_features':
         return 'image RoIAlign (6 cameras)'
-    if name in ('srf_linear_tc', 'srf_linear_bf16'):
-        m, k, n = (a[2], a[3], a[5]) if name == 'srf_linear_tc' else (a[1], a[2], a[4])
+    if name in ('srf_linear', 'srf_linear_tc', 'srf_linear_bf16'):
+        m, k, n = (s['m'], s['k'], s['n']) if name == 'srf_linear' else ((a[2], a[3], a[5]) if name == 'srf_linear_tc' else (a[1], a[2], a[4]))
         return f'GEMM {k}->{n}' + (' (pixel rows)' if m > 5000 and k <= 512 and m != 44100 else '')
     if name in ('srf_linear_f32', 'srf_gemv_f32'):
         return 'small projections (FFMA)'
@@ -123,6 +127,10 @@ def _work(name, a, s, ctx):
         c = s['channels']
         k, n_cam = a[2], a[5]
         return 0.0, k * 49 * c * ES[s.get('out_enc', L.F32)] + n_cam * sum(h * w for h, w in s['hw']) * c * 4
+    if name == 'srf_linear':
+        es = ES[s['enc']]
+        return 2.0 * s['m'] * s['k'] * s['n'], s['m'] * s['k'] * es + s['k'] * s['n'] * es + s['m'] * s['n'] * (
+            ES[s['out_enc']] * s['k_splits'] + (ES[s['out2_enc']] if s['out2'] else 0))
     if name == 'srf_linear_tc':
         enc, m, k, n, out_enc = a[1], a[2], a[3], a[5], a[13]
         return 2.0 * m * k * n, m * k * ES[enc] + k * n * ES[enc] + m * n * ES[out_enc] * max(1, a[14] or 1)
@@ -153,6 +161,7 @@ def families(cap, ctx, peaks):
         w = _work(name, a, s, ctx)
         if w is None:
             w = ctx['conv_work'](s)
+        cap.per_call.append((round(ms, 4), name, fam))
         g = groups.setdefault(fam, dict(family=fam, launches=0, ms=0.0, flops=0.0, bytes=0.0, entry_points=set()))
         g['launches'] += 1
         g['ms'] += ms
