@@ -160,44 +160,53 @@ struct MapView {
 // out = relu(bn(dwconv3x3_s2_p1(cat(a, b)))); w (Ca+Cb, 9) with BN folded, bias (Ca+Cb).  out is
 // (n, Ca+Cb, Ho, Wo) NCHW, or (n, Ho, Wo, Ca+Cb) when cl_out (channel-fastest threads: coalesced on
 // torch.channels_last inputs)
-// channels_last fast path: 4 consecutive channels per thread (float4 loads / stores), a.c and b.c multiples of 4
+// channels_last fast path: a thread owns 4 consecutive channels (float4 loads / stores; a.c and b.c multiples of 4) of
+// DW_PX consecutive output pixels of a row: the 36 folded weights are read once per thread, index math is 32-bit.
+constexpr int DW_PX = 4;
 __global__ void __launch_bounds__(256) dwconv3x3_s2_cl4_kernel(MapView a, MapView b, int n, int h, int w, int ho, int wo,
                                                                const float* __restrict__ wt, const float* __restrict__ bias, int relu,
                                                                float* __restrict__ out) {
   const int ctot = a.c + b.c, c4n = ctot / 4;
-  const long long total = (long long)n * ho * wo * c4n;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+  const int wq = (wo + DW_PX - 1) / DW_PX;
+  const unsigned total = (unsigned)n * ho * wq * c4n;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int c = (int)(e % c4n) * 4;
-    long long t = e / c4n;
-    const int x = (int)(t % wo);
-    t /= wo;
+    unsigned t = e / c4n;
+    const int xq = (int)(t % wq);
+    t /= wq;
     const int y = (int)(t % ho), img = (int)(t / ho);
     const MapView& mv = c < a.c ? a : b;
     const int cl = c < a.c ? c : c - a.c;
-    const float* base = mv.p + img * mv.sn + cl;          // sc == 1
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const float* base = mv.p + (long long)img * mv.sn + cl;          // sc == 1
+    const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + c));
     float wv[4][9];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
       for (int k = 0; k < 9; ++k) wv[q][k] = __ldg(wt + (c + q) * 9 + k);
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = 2 * y - 1 + ky;
-      if (iy < 0 || iy >= h) continue;
+    for (int px = 0; px < DW_PX; ++px) {
+      const int x = xq * DW_PX + px;
+      if (x >= wo) break;
+      float4 acc = bz;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * x - 1 + kx;
-        if (ix < 0 || ix >= w) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + iy * mv.sh + ix * mv.sw));
-        acc.x = fmaf(v.x, wv[0][ky * 3 + kx], acc.x);
-        acc.y = fmaf(v.y, wv[1][ky * 3 + kx], acc.y);
-        acc.z = fmaf(v.z, wv[2][ky * 3 + kx], acc.z);
-        acc.w = fmaf(v.w, wv[3][ky * 3 + kx], acc.w);
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * y - 1 + ky;
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = 2 * x - 1 + kx;
+          if (ix < 0 || ix >= w) continue;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)iy * mv.sh + (long long)ix * mv.sw));
+          acc.x = fmaf(v.x, wv[0][ky * 3 + kx], acc.x);
+          acc.y = fmaf(v.y, wv[1][ky * 3 + kx], acc.y);
+          acc.z = fmaf(v.z, wv[2][ky * 3 + kx], acc.z);
+          acc.w = fmaf(v.w, wv[3][ky * 3 + kx], acc.w);
+        }
       }
+      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      *reinterpret_cast<float4*>(out + (((size_t)img * ho + y) * wo + x) * ctot + c) = acc;
     }
-    if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-    *reinterpret_cast<float4*>(out + e * 4) = acc;
   }
 }
 
@@ -406,11 +415,12 @@ int srf_dwconv3x3_s2(const srf_map* a, const srf_map* b, int32_t n, int32_t h, i
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const long long total = (long long)n * (va.c + vb.c) * ho * wo;
   SRF_COUNT(1);
-  const bool vec = channels_last_out && va.sc == 1 && (vb.c == 0 || vb.sc == 1) && va.c % 4 == 0 && vb.c % 4 == 0 &&
+  const bool vec = channels_last_out && total < (1ll << 31) && va.sc == 1 && (vb.c == 0 || vb.sc == 1) && va.c % 4 == 0 && vb.c % 4 == 0 &&
                    va.sw % 4 == 0 && va.sh % 4 == 0 && va.sn % 4 == 0 && (vb.c == 0 || (vb.sw % 4 == 0 && vb.sh % 4 == 0 && vb.sn % 4 == 0)) &&
                    ((uintptr_t)va.p % 16 == 0) && (vb.c == 0 || (uintptr_t)vb.p % 16 == 0);
   if (vec) {
-    dwconv3x3_s2_cl4_kernel<<<egrid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(va, vb, n, h, w, ho, wo, wt_folded, bias_folded, relu, out);
+    const long long nthr = (long long)n * ho * ((wo + DW_PX - 1) / DW_PX) * ((va.c + vb.c) / 4);
+    dwconv3x3_s2_cl4_kernel<<<egrid(nthr, 256), 256, 0, (cudaStream_t)stream>>>(va, vb, n, h, w, ho, wo, wt_folded, bias_folded, relu, out);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }

@@ -157,6 +157,7 @@ class RegionFeaturePipeline:
         self.use_graph = use_graph
         self._graphs = {}
         self.overlap_stage = True
+        self.overlap_image_branch = True      # scope 'full': the image half of DPG runs on a side stream under the encoder
         self._aux = None
         self._aux2 = None
         self.precision = precision or registry.get_precision()
@@ -341,14 +342,15 @@ class RegionFeaturePipeline:
         self._graphs = {}
 
     @torch.no_grad()
-    def full_chain(self, bev):
+    def full_chain(self, bev, dpg_img=None):
         """dense BEV map -> SECONDCustom -> FPN -> SRFDetHead (DPG, chained stages) -> decode.
-        Returns the last stage's object features; logits / boxes / decoded results in self.last."""
+        Returns the decoded boxes + scores; logits / boxes / pyramid in self.last."""
         from .plugin.bev_backbone import nchw_to_rows, _tc_enc
         n, c, h, w = bev.shape
         feats = self.backbone.forward_rows(nchw_to_rows(bev, _tc_enc(self.precision)), n, h, w, self.precision)
         pyramid = self.neck.forward_rows(feats, n, self.precision)
-        logits, boxes = self.head(self.img_feats if self.fusion else None, pyramid, None, lidar2img=self.lidar2img, precision=self.precision)
+        logits, boxes = self.head(self.img_feats if self.fusion else None, pyramid, None, lidar2img=self.lidar2img, precision=self.precision,
+                                  dpg_img_logits=dpg_img)
         scores, dec = self.head.decode(logits, boxes)
         self.last = dict(pyramid=pyramid, logits=logits, boxes=boxes, scores=scores, det_boxes=dec)
         self.last_pyramid = pyramid
@@ -356,10 +358,28 @@ class RegionFeaturePipeline:
 
     @torch.no_grad()
     def _run_frame_eager(self, points):
+        if self.scope != 'full':
+            return self.encode(points), self.region_stages()
+        dpg_img = ev = None
+        if self.fusion:
+            # the image half of Dynamic Proposal Generation depends on the image FPN maps only: start it before the
+            # encoder, on a side stream, and join right before the proposals are mixed
+            main = torch.cuda.current_stream()
+            if self.overlap_image_branch:
+                if self._aux2 is None:
+                    self._aux2 = torch.cuda.Stream()
+                self._aux2.wait_event(main.record_event())
+                with torch.cuda.stream(self._aux2):
+                    dpg_img = self.head.dpg_image_logits(self.img_feats)
+                    ev = self._aux2.record_event()
+                if not torch.cuda.is_current_stream_capturing():
+                    dpg_img.record_stream(main)
+            else:
+                dpg_img = self.head.dpg_image_logits(self.img_feats)
         bev = self.encode(points)
-        if self.scope == 'full':
-            return bev, self.full_chain(bev)
-        return bev, self.region_stages()
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        return bev, self.full_chain(bev, dpg_img)
 
     @torch.no_grad()
     def run_frames(self, clouds, host=False):

@@ -120,7 +120,16 @@ class SRFDetHead(nn.Module):
                                  L.ptr(out), st), 'srf_gemv_f32')
         return out          # (bs, n_exp * n_p)
 
-    def _get_init_proposals(self, img_feats, point_feats, sigmoid_centres=False):
+    def dpg_image_logits(self, img_feats):
+        """Image half of Dynamic Proposal Generation (:556-596): depends on the image FPN maps only, so a caller may
+        run it ahead of / concurrently with the LiDAR branch and hand the result to forward(dpg_img_logits=)."""
+        img_feats = self._image_maps(img_feats)
+        bs = img_feats[0].shape[0]
+        flat = [f.float().reshape(-1, *f.shape[2:]) if f.dim() == 5 else f.float() for f in img_feats]     # (bs*n_cam, C, H, W)
+        n_cam = flat[0].shape[0] // bs
+        return self._dpg_logits(flat, self.dpg_dw_convs_img, self.dpg_fc1_img, self.dpg_fc2_img, 'dpg_i', group=n_cam, resize=self.last_imgfmap)
+
+    def _get_init_proposals(self, img_feats, point_feats, sigmoid_centres=False, dpg_img_logits=None):
         """-> (boxes (bs, n_p, dim), feats (bs, n_p, C)).  sigmoid_centres=True additionally applies
         `bboxes[..., :3].sigmoid()` of forward (:403) inside the mixing kernel."""
         bs = point_feats[0].shape[0]
@@ -134,12 +143,9 @@ class SRFDetHead(nn.Module):
             return boxes, ef.unsqueeze(0).repeat(bs, 1, 1)
         point_feats = [f.float() for f in point_feats]
         la = self._dpg_logits(point_feats, self.dpg_dw_convs_lidar, self.dpg_fc1_lidar, self.dpg_fc2_lidar, 'dpg_l')
-        lb = None
-        if self.use_img:
-            flat = [f.float().reshape(-1, *f.shape[2:]) if f.dim() == 5 else f.float() for f in img_feats]     # (bs*n_cam, C, H, W)
-            n_cam = flat[0].shape[0] // bs
-            lb = self._dpg_logits(flat, self.dpg_dw_convs_img, self.dpg_fc1_img, self.dpg_fc2_img, 'dpg_i', group=n_cam,
-                                  resize=self.last_imgfmap)
+        lb = dpg_img_logits
+        if self.use_img and lb is None:
+            lb = self.dpg_image_logits(img_feats)
         boxes = torch.empty((bs, self.num_proposals, dim), dtype=torch.float32, device=dev)
         feats = torch.empty((bs, self.num_proposals, c), dtype=torch.float32, device=dev)
         L.check(L.load().srf_dpg_mix(L.ptr(la), L.ptr(lb), bs, self.num_dpg_exp, self.num_proposals, L.ptr(eb), dim, L.ptr(ef), c,
@@ -160,13 +166,13 @@ class SRFDetHead(nn.Module):
         return list(img_feats)
 
     @torch.no_grad()
-    def forward(self, img_feats, point_feats, img_metas=None, lidar2img=None, precision=None):
+    def forward(self, img_feats, point_feats, img_metas=None, lidar2img=None, precision=None, dpg_img_logits=None):
         """img_feats: list of (bs, n_cam, C, H, W) | None; point_feats: list of (bs, C, H, W) BEV maps (NCHW or
         torch.channels_last).  -> (pred_logits (#stages, bs, n_p, #cls), pred_bboxes (#stages, bs, n_p, dim)) with
         absolute centres and log sizes, like the reference (:474-498).  lidar2img (n_cam,4,4) tensor may replace
         img_metas[*]['lidar2img'] (keeps the call free of host work)."""
         img_feats = self._image_maps(img_feats)
-        bboxes, prop = self._get_init_proposals(img_feats, point_feats, sigmoid_centres=True)
+        bboxes, prop = self._get_init_proposals(img_feats, point_feats, sigmoid_centres=True, dpg_img_logits=dpg_img_logits)
         if self.use_img and lidar2img is None:
             import numpy as np
             lidar2img = torch.as_tensor(np.asarray([m['lidar2img'] for m in img_metas]), dtype=torch.float32, device=bboxes.device)
