@@ -6,7 +6,8 @@
   torchrun ... bench.py --gpus N ...          (one rank per GPU; frames are independent)
   python bench.py --impl reference ...        (restated reference CPU path on the host cores)
 
-A step = F frames per rank (F = --frames-in-flight, default 1), each frame one pass of the hot path:
+A step = a batch of F independent frames per rank (F = --frames-in-flight, default 4: BASELINE config 5's frame batches; every
+frame is its own CUDA graph on its own stream, so latency-bound kernels of different frames overlap), each frame one pass of the hot path:
   scope 'full' (default): hard/dynamic voxelization (+VFE) -> SparseEncoder -> SECOND + FPN -> Dynamic Proposal
       Generation -> 5 CHAINED stages (BEV RoIAlign on the real FPN maps [+ 6-camera image RoIAlign + fusion Linear],
       self-attention, DynamicConv, FFN, towers, apply_deltas -> next stage's boxes) -> decode;
@@ -228,7 +229,8 @@ def main():
     ap.add_argument('--workload', default='nusc_LC', choices=sorted(WORKLOADS))
     ap.add_argument('--scope', default='full', choices=sorted(SCOPES))
     ap.add_argument('--precision', default='fp16', choices=sorted(DTYPES))
-    ap.add_argument('--frames-in-flight', type=int, default=1, help='frames per rank per step, each its own CUDA graph on its own stream')
+    ap.add_argument('--frames-in-flight', type=int, default=4,
+                    help='frames per rank per step (BASELINE config 5: frame batches), each its own CUDA graph on its own stream')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the modes / sweep / kernel-family measurements (timed value and e2e only)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying a CUDA graph of the frame')
