@@ -10,8 +10,10 @@
 
 namespace srf {
 
+// (branch on the SIGN BIT, not on v >= 0: -0.0f must take the unsigned path, otherwise its pattern 0x80000000 =
+// INT_MIN never beats the -inf initial value and a channel whose maximum is -0.0 would come out as -inf)
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  if (v >= 0.f)
+  if (__float_as_int(v) >= 0)
     atomicMax((int*)addr, __float_as_int(v));
   else
     atomicMin((unsigned int*)addr, __float_as_uint(v));

@@ -141,3 +141,14 @@ def test_pillar_path_vs_oracle():
         canvas = sc(feats, o['coors'], batch_size=1, num_voxels=o['count'])
         assert canvas.shape == (1, 64, 512, 512)
         np.testing.assert_allclose(canvas.cpu().numpy(), ref_canvas, rtol=1e-5, atol=2e-5)
+
+
+def test_dynamic_scatter_max_of_negative_zero():
+    """A voxel channel whose maximum is exactly -0.0 must come out as (-)0.0, not -inf (sign-bit branch of the float atomic max)."""
+    from srfdet_b200.plugin import DynamicScatter
+    sc = DynamicScatter([0.5, 0.5, 0.5], [0, 0, 0, 4, 4, 4], average_points=False)
+    feats = torch.tensor([[-0.0, -1.0], [-2.0, -0.0], [-3.0, -3.0]], device='cuda')
+    coors = torch.tensor([[1, 1, 1], [1, 1, 1], [1, 1, 1]], dtype=torch.int32, device='cuda')
+    vf, vc = sc(feats, coors)
+    assert vf.shape == (1, 2)
+    assert torch.equal(vf.abs().cpu(), torch.zeros(1, 2)) and bool(torch.isfinite(vf).all())
