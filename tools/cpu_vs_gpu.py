@@ -2,7 +2,7 @@ import sys, time, torch
 sys.path.insert(0, '.')
 from srfdet_b200 import synth
 from srfdet_b200.pipeline import RegionFeaturePipeline
-pipe = RegionFeaturePipeline('nusc', precision='bf16')
+pipe = RegionFeaturePipeline('nusc', precision='fp16')
 pts = torch.as_tensor(synth.cloud('nusc', 1000)).cuda()
 for _ in range(5): pipe.run_frame(pts)
 torch.cuda.synchronize()

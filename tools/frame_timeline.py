@@ -12,7 +12,7 @@ from srfdet_b200.pipeline import RegionFeaturePipeline  # noqa: E402
 
 def main():
     fusion = 'LC' in sys.argv
-    pipe = RegionFeaturePipeline('nusc', fusion=fusion, precision='bf16')
+    pipe = RegionFeaturePipeline('nusc', fusion=fusion, precision='fp16')
     pts = torch.as_tensor(synth.cloud('nusc', 1)).cuda()
     for _ in range(3):
         pipe.run_frame(pts)

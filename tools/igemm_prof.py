@@ -31,7 +31,7 @@ def main():
             e['t'] = tbuf.reshape(1024, 4).copy()
             super().append(e)
 
-    pipe = RegionFeaturePipeline('nusc', fusion=False, precision='bf16')
+    pipe = RegionFeaturePipeline('nusc', fusion=False, precision='fp16')
     enc = pipe.detector.pts_middle_encoder
     enc.overlap_geometry = False
     pts = torch.as_tensor(synth.cloud('nusc', 1)).cuda()
@@ -82,7 +82,7 @@ def gaps():
     lib = L.load()
     lib.srf_prof_read_t.argtypes = [ctypes.c_void_p, ctypes.c_int]
     tbuf = np.zeros(1024 * 4, dtype=np.uint64)
-    pipe = RegionFeaturePipeline('nusc', fusion=False, precision='bf16', use_graph=True)
+    pipe = RegionFeaturePipeline('nusc', fusion=False, precision='fp16', use_graph=True)
     pts = torch.as_tensor(synth.cloud('nusc', 1)).cuda()
     for _ in range(3):
         pipe.run_frame(pts)
@@ -120,7 +120,7 @@ def trace(dbg_layers=(2, 7, 12, 17)):
             e['trace'] = [(int(v) >> 56, int(v) & ((1 << 56) - 1)) for v in ebuf[:n]]
             super().append(e)
 
-    pipe = RegionFeaturePipeline('nusc', fusion=False, precision='bf16')
+    pipe = RegionFeaturePipeline('nusc', fusion=False, precision='fp16')
     enc = pipe.detector.pts_middle_encoder
     enc.overlap_geometry = False
     pts = torch.as_tensor(synth.cloud('nusc', 1)).cuda()
