@@ -224,9 +224,12 @@ __device__ __forceinline__ void epilogue_chunk(const IgemmArgs& a, int row, int 
   }
 }
 
-// dense-linear epilogue of a whole COUT-wide row: bias / residual / LayerNorm / ReLU / store
+// dense-linear epilogue of a whole COUT-wide row: bias / residual / LayerNorm / ReLU / store.
+// sp: the tile's bias | ln_w | ln_b (3 x 128 floats) staged in shared memory by the epilogue warps -- with one thread per
+// row every lane needs the same 3 x COUT parameters, and fetching them with 3 x COUT broadcast global loads per thread
+// made the epilogue (not the main loop) the per-tile cost of the short-K GEMMs of the head (ncu: 16 k cycles per tile).
 template <int COUT>
-__device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt, float* v, int ks = 0) {
+__device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt, float* v, const float* sp, int ks = 0) {
   if (a.k_splits > 1) {   // partial sum of one K range -> its own (m, n) slab; summed in fixed order by srf_layernorm
     float4* op = (float4*)((float*)a.out + ((size_t)ks * a.m_rows + row) * a.out_stride + nt * COUT);
 #pragma unroll
@@ -236,23 +239,33 @@ __device__ __forceinline__ void epilogue_row(const IgemmArgs& a, int row, int nt
   const int col0 = nt * COUT;
   if (a.bias) {
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) v[c] += __ldg(a.bias + col0 + c);
+    for (int c = 0; c < COUT; c += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sp + c);
+      v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+    }
   }
   if (a.residual) add_residual<COUT>(a, (size_t)row, col0, v);
   if (a.ln) {
-    float mean = 0.f;
+    // four partial sums: the reductions are latency chains in a single thread
+    float m4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) mean += v[c];
-    mean *= (1.f / COUT);
-    float var = 0.f;
+    for (int c = 0; c < COUT; c += 4) { m4[0] += v[c]; m4[1] += v[c + 1]; m4[2] += v[c + 2]; m4[3] += v[c + 3]; }
+    const float mean = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (1.f / COUT);
+    float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) { float d = v[c] - mean; var += d * d; }
-    const float rstd = rsqrtf(var * (1.f / COUT) + a.ln_eps);
+    for (int c = 0; c < COUT; c += 4) {
 #pragma unroll
-    const float* lw = a.ln_w + (a.ln_per_tile ? col0 : 0);
-    const float* lb = a.ln_b + (a.ln_per_tile ? col0 : 0);
+      for (int q = 0; q < 4; ++q) { const float d = v[c + q] - mean; q4[q] = fmaf(d, d, q4[q]); }
+    }
+    const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.f / COUT) + a.ln_eps);
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) v[c] = (v[c] - mean) * rstd * __ldg(lw + c) + __ldg(lb + c);
+    for (int c = 0; c < COUT; c += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(sp + 128 + c), b4 = *reinterpret_cast<const float4*>(sp + 256 + c);
+      v[c] = (v[c] - mean) * rstd * w4.x + b4.x;
+      v[c + 1] = (v[c + 1] - mean) * rstd * w4.y + b4.y;
+      v[c + 2] = (v[c + 2] - mean) * rstd * w4.z + b4.z;
+      v[c + 3] = (v[c + 3] - mean) * rstd * w4.w + b4.w;
+    }
   }
   if (a.relu) {
 #pragma unroll

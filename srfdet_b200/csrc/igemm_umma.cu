@@ -153,7 +153,7 @@ struct Cfg {
   static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > SRF_IGEMM_MAXSTAGES ? SRF_IGEMM_MAXSTAGES : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + (SPARSE ? 0 : 3 * 128 * 4);   // + the dense epilogue's staged bias | ln_w | ln_b
   static constexpr int SMEM_BYTES = W_BYTES + IDX_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
   static constexpr int MINB = (TRI && COUT <= 64) ? 3 : ((SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1);
   // kind::f16: D fp32 (bit 4), A/B format at bits 7 / 10 (0 = f16, 1 = bf16: set at run time), K-major both, N>>3 @17, M>>4 @24
@@ -197,6 +197,7 @@ igemm_umma_kernel(const IgemmArgs a) {
   uint8_t* stage_base = smem + C::W_BYTES + C::IDX_BYTES;
   uint64_t* bars = (uint64_t*)(stage_base + S * C::STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  float* epi_par = reinterpret_cast<float*>(tmem_slot + 4);          // dense form: 3 x 128 floats (16-byte aligned)
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
@@ -530,13 +531,22 @@ igemm_umma_kernel(const IgemmArgs a) {
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
       } else {
+        // stage the tile's epilogue parameters (the 4 epilogue warps = threads 0..127; COUT <= 128)
+        asm volatile("bar.sync 2, 128;" ::: "memory");      // the previous tile's parameters are no longer read
+        if ((int)threadIdx.x < COUT && a.k_splits <= 1) {
+          const int col = nt * COUT + threadIdx.x;
+          epi_par[threadIdx.x] = a.bias ? __ldg(a.bias + col) : 0.f;
+          epi_par[128 + threadIdx.x] = a.ln ? __ldg(a.ln_w + (a.ln_per_tile ? col : (int)threadIdx.x)) : 1.f;
+          epi_par[256 + threadIdx.x] = a.ln ? __ldg(a.ln_b + (a.ln_per_tile ? col : (int)threadIdx.x)) : 0.f;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
         float v[COUT];
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 16) tc_ld16(taddr + c0, v + c0);
         // accumulator is in registers: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
-        if (row < m_rows && !DBG(8)) epilogue_row<COUT>(a, row, nt, v, tile / mn_tiles);
+        if (row < m_rows && !DBG(8)) epilogue_row<COUT>(a, row, nt, v, epi_par, tile / mn_tiles);
       }
       if (threadIdx.x == 0) PROF_TRACE(7);
     }
