@@ -16,6 +16,7 @@ extern unsigned long long g_launches;  // kernels launched by this library (benc
 #define SRF_COUNT(n) (srf::g_launches += (n))
 int sm_count();
 int spconv16_warp_launch(const srf_conv_args* cv, bool f16, cudaStream_t st);   // spconv_warp16.cu
+bool mha_attention_mma_launch(const float* qkv, int n_batch, int n_p, int n_heads, int head_dim, void* out, int out_enc, cudaStream_t st);   // attention.cu
 
 #define SRF_CHECK_ARG(cond, ...)          \
   do {                                    \

@@ -161,12 +161,19 @@ struct MapView {
 // (n, Ca+Cb, Ho, Wo) NCHW, or (n, Ho, Wo, Ca+Cb) when cl_out (channel-fastest threads: coalesced on
 // torch.channels_last inputs)
 // channels_last fast path: a thread owns 4 consecutive channels (float4 loads / stores; a.c and b.c multiples of 4) of
-// DW_PX consecutive output pixels of a row: the 36 folded weights are read once per thread, index math is 32-bit.
-constexpr int DW_PX = 4;
-__global__ void __launch_bounds__(256) dwconv3x3_s2_cl4_kernel(MapView a, MapView b, int n, int h, int w, int ho, int wo,
-                                                               const float* __restrict__ wt, const float* __restrict__ bias, int relu,
-                                                               float* __restrict__ out) {
+// DW_PX consecutive output pixels of a row.  The folded weights sit in shared memory transposed to [tap][channel] (one
+// conflict-free LDS.128 per tap instead of 36 registers per thread: 4 blocks of 256 threads per SM keep ~80 KB of loads in
+// flight, the kernel streams its input once from HBM); per kernel row the 2*DW_PX+1 input columns are loaded as one batch
+// and shared by the DW_PX outputs.  Index math is 32-bit.
+constexpr int DW_PX = 2;
+__global__ void __launch_bounds__(256, 4) dwconv3x3_s2_cl4_kernel(MapView a, MapView b, int n, int h, int w, int ho, int wo,
+                                                                  const float* __restrict__ wt, const float* __restrict__ bias, int relu,
+                                                                  float* __restrict__ out) {
+  extern __shared__ __align__(16) float dw_smem[];     // [9][ctot] weights, [ctot] bias
   const int ctot = a.c + b.c, c4n = ctot / 4;
+  for (int i = threadIdx.x; i < ctot * 9; i += blockDim.x) dw_smem[(i % 9) * ctot + i / 9] = __ldg(wt + i);
+  for (int i = threadIdx.x; i < ctot; i += blockDim.x) dw_smem[9 * ctot + i] = __ldg(bias + i);
+  __syncthreads();
   const int wq = (wo + DW_PX - 1) / DW_PX;
   const unsigned total = (unsigned)n * ho * wq * c4n;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -178,34 +185,42 @@ __global__ void __launch_bounds__(256) dwconv3x3_s2_cl4_kernel(MapView a, MapVie
     const MapView& mv = c < a.c ? a : b;
     const int cl = c < a.c ? c : c - a.c;
     const float* base = mv.p + (long long)img * mv.sn + cl;          // sc == 1
-    const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + c));
-    float wv[4][9];
+    const float4 bz = *reinterpret_cast<const float4*>(dw_smem + 9 * ctot + c);
+    float4 acc[DW_PX];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int px = 0; px < DW_PX; ++px) acc[px] = bz;
+    const int x0 = xq * DW_PX * 2 - 1;                               // first input column of the patch
 #pragma unroll
-      for (int k = 0; k < 9; ++k) wv[q][k] = __ldg(wt + (c + q) * 9 + k);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * y - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+      const float* rowp = base + (long long)iy * mv.sh;
+      float4 v[2 * DW_PX + 1];
+#pragma unroll
+      for (int j = 0; j < 2 * DW_PX + 1; ++j) {
+        const int ix = x0 + j;
+        v[j] = (ix >= 0 && ix < w) ? __ldg(reinterpret_cast<const float4*>(rowp + (long long)ix * mv.sw)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 wv = *reinterpret_cast<const float4*>(dw_smem + (ky * 3 + kx) * ctot + c);
+#pragma unroll
+        for (int px = 0; px < DW_PX; ++px) {
+          const float4 u = v[2 * px + kx];
+          acc[px].x = fmaf(u.x, wv.x, acc[px].x);
+          acc[px].y = fmaf(u.y, wv.y, acc[px].y);
+          acc[px].z = fmaf(u.z, wv.z, acc[px].z);
+          acc[px].w = fmaf(u.w, wv.w, acc[px].w);
+        }
+      }
+    }
 #pragma unroll
     for (int px = 0; px < DW_PX; ++px) {
       const int x = xq * DW_PX + px;
       if (x >= wo) break;
-      float4 acc = bz;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = 2 * y - 1 + ky;
-        if (iy < 0 || iy >= h) continue;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ix = 2 * x - 1 + kx;
-          if (ix < 0 || ix >= w) continue;
-          const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)iy * mv.sh + (long long)ix * mv.sw));
-          acc.x = fmaf(v.x, wv[0][ky * 3 + kx], acc.x);
-          acc.y = fmaf(v.y, wv[1][ky * 3 + kx], acc.y);
-          acc.z = fmaf(v.z, wv[2][ky * 3 + kx], acc.z);
-          acc.w = fmaf(v.w, wv[3][ky * 3 + kx], acc.w);
-        }
-      }
-      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-      *reinterpret_cast<float4*>(out + (((size_t)img * ho + y) * wo + x) * ctot + c) = acc;
+      float4 r = acc[px];
+      if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+      *reinterpret_cast<float4*>(out + (((size_t)img * ho + y) * wo + x) * ctot + c) = r;
     }
   }
 }
@@ -385,6 +400,11 @@ int srf_mha_attention(const float* qkv, int32_t n_batch, int32_t n_p, int32_t n_
   const float scale = 1.f / sqrtf((float)head_dim);
   cudaStream_t st = (cudaStream_t)stream;
   SRF_COUNT(1);
+  // 16-bit modes: tensor-core kernel (attention.cu); fp32 / split outputs: the fp32 kernel below
+  if (mha_attention_mma_launch(qkv, n_batch, n_p, n_heads, head_dim, out, out_enc, st)) {
+    SRF_LAUNCH_CHECK();
+    return SRF_OK;
+  }
   constexpr int T = ATT_QG * ATT_KP;
   switch (head_dim) {     // QT queries per thread: 2 (64 queries per block: 120 blocks for 900 proposals x 8 heads), 1 for 32-wide heads
     case 8: mha_attention_kernel<8, 2><<<dim3(cdiv(n_p, ATT_QG * 2), n_heads, n_batch), T, 0, st>>>(qkv, n_p, n_heads, scale, out, out_enc); break;
@@ -415,12 +435,12 @@ int srf_dwconv3x3_s2(const srf_map* a, const srf_map* b, int32_t n, int32_t h, i
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const long long total = (long long)n * (va.c + vb.c) * ho * wo;
   SRF_COUNT(1);
-  const bool vec = channels_last_out && total < (1ll << 31) && va.sc == 1 && (vb.c == 0 || vb.sc == 1) && va.c % 4 == 0 && vb.c % 4 == 0 &&
+  const bool vec = channels_last_out && total < (1ll << 31) && va.c + vb.c <= 1024 && va.sc == 1 && (vb.c == 0 || vb.sc == 1) && va.c % 4 == 0 && vb.c % 4 == 0 &&
                    va.sw % 4 == 0 && va.sh % 4 == 0 && va.sn % 4 == 0 && (vb.c == 0 || (vb.sw % 4 == 0 && vb.sh % 4 == 0 && vb.sn % 4 == 0)) &&
                    ((uintptr_t)va.p % 16 == 0) && (vb.c == 0 || (uintptr_t)vb.p % 16 == 0);
   if (vec) {
     const long long nthr = (long long)n * ho * ((wo + DW_PX - 1) / DW_PX) * ((va.c + vb.c) / 4);
-    dwconv3x3_s2_cl4_kernel<<<egrid(nthr, 256), 256, 0, (cudaStream_t)stream>>>(va, vb, n, h, w, ho, wo, wt_folded, bias_folded, relu, out);
+    dwconv3x3_s2_cl4_kernel<<<egrid(nthr, 256), 256, (size_t)(va.c + vb.c) * 10 * sizeof(float), (cudaStream_t)stream>>>(va, vb, n, h, w, ho, wo, wt_folded, bias_folded, relu, out);
     SRF_LAUNCH_CHECK();
     return SRF_OK;
   }

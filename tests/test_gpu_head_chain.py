@@ -100,6 +100,25 @@ def test_mha_attention_vs_torch(c, heads, n_p, bs):
     assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 2e-5
 
 
+@pytest.mark.parametrize('c,heads,n_p,bs', [(128, 8, 900, 1), (256, 8, 300, 2), (128, 8, 64, 1), (128, 8, 65, 3), (32, 2, 7, 1)])
+@pytest.mark.parametrize('enc_name', ['F16', 'BF16'])
+def test_mha_attention_tensor_core_vs_torch(c, heads, n_p, bs, enc_name):
+    """16-bit modes: the mma.sync kernel (csrc/attention.cu; head widths 16 / 32) against torch's fp32 attention
+    core.  Inputs are deliberately hot (|score| up to ~10): f16 operands stay inside 3e-3 of the largest output, bf16
+    operands (8-bit mantissa on the scores) inside the bf16 mode's 2e-2 -- bf16 is not the benchmarked mode."""
+    from srfdet_b200 import _lib as L
+    torch.manual_seed(1)
+    enc = getattr(L, enc_name)
+    x = torch.randn(bs * n_p, 3 * c, device='cuda') * 1.5
+    hd = c // heads
+    q, k, v = [t.view(bs, n_p, heads, hd).transpose(1, 2) for t in x.split(c, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(bs * n_p, c)
+    att = torch.empty((bs * n_p, c), dtype=L.enc_torch_dtype(enc), device='cuda')
+    L.check(L.load().srf_mha_attention(L.ptr(x), bs, n_p, heads, hd, L.ptr(att), enc, L.stream_ptr()), 'attn')
+    got = att.view(torch.float16 if enc_name == 'F16' else torch.bfloat16).float()
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < (3e-3 if enc_name == 'F16' else 2e-2)
+
+
 @pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('fp32_simt', 2e-4), ('fp16', 1e-2)])
 def test_stage_tail_kernels_vs_torch(precision, tol):
     """Production dims (900 proposals, C 128, d 32, ff 512, 8 heads): the kernel path of a whole stage
