@@ -595,7 +595,9 @@ static int launch_igemm(const IgemmArgs& a, int host_tiles, cudaStream_t st) {
   return SRF_OK;
 }
 
-// NOTE: two other producers were built and measured slower on B200 (profiles/r01_notes.md): the TMA
+// NOTE: a window-staged mma.sync form of the 32 -> 32 / 16 -> 16 layers (contiguous input windows in shared memory, ldmatrix
+// gathers) is parity-green but instruction-bound at 98 vs 77 us (profiles/r02_notes.md; tools/variants/spconv_window.cu.txt).
+// Two other producers were built and measured slower on B200 (profiles/r01_notes.md): the TMA
 // tile::gather4 form (~45 clk per 4-row instruction, ~2x slower; archived in tools/variants/) and a
 // register-staged LDG -> STS form (1.5x slower).  Neither is part of the build.
 

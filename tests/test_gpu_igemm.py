@@ -123,3 +123,77 @@ def test_linear_split_k(m, k, n, splits, enc):
     L.check(lib.srf_layernorm(L.ptr(part), L.F32, m, n, eff, L.ptr(bias), L.ptr(lw), L.ptr(lb), 1e-5, 1, L.ptr(out), st), 'ln')
     ref2 = torch.relu(torch.nn.functional.layer_norm(ref + bias, (n,), lw, lb))
     assert rel_err(out.cpu().numpy(), ref2.cpu().numpy()) < max(TOL[enc] * 2, 1e-5)
+
+
+# ------------------------------------------------------------------------------ sparse conv on arbitrary neighbour tables
+def _conv_case(c, enc_name, rows, n_in, nbr, residual, relu, n_out=None):
+    """srf_spconv_tc (cin = cout = c, kvol 27, 16-bit in / out) on an arbitrary neighbour table vs fp64 torch."""
+    from srfdet_b200 import _lib as L
+    from srfdet_b200.plugin.head import encode_rows
+    lib = L.load()
+    enc = _encs()[enc_name]
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(n_in, c, generator=g) * 0.7).cuda()
+    w = (torch.randn(27, c, c, generator=g) / (9 * c) ** 0.5).cuda()
+    bias = torch.randn(c, generator=g).cuda()
+    res = (torch.randn(rows, c, generator=g)).cuda() if residual else None
+    xe = encode_rows(x, enc)
+    wp = torch.empty(27 * c * c, dtype=L.enc_torch_dtype(enc), device='cuda')
+    st = L.stream_ptr()
+    L.check(lib.srf_pack_weight_tc(L.ptr(w), 27, c, c, enc, L.ptr(wp), st), 'pack')
+    cnt = torch.tensor([rows if n_out is None else n_out], dtype=torch.int32, device='cuda')
+    out = torch.full((rows, c), 7.0, dtype=L.enc_torch_dtype(enc), device='cuda')
+    re = encode_rows(res, enc) if residual else None
+    a = L.ConvArgs()
+    a.in_, a.in_dtype, a.in_rows = L.ptr(xe), enc, n_in
+    a.cin, a.cout, a.kvol = c, c, 27
+    a.nbr, a.tile_mask, a.cap_out, a.d_n_out = L.ptr(nbr), None, rows, L.ptr(cnt)
+    a.w, a.bias, a.residual, a.relu = L.ptr(wp), L.ptr(bias), (L.ptr(re) if residual else None), int(relu)
+    a.out, a.out_dtype = L.ptr(out), enc
+    import ctypes
+    L.check(lib.srf_spconv_tc(ctypes.byref(a), st), 'conv')
+    torch.cuda.synchronize()
+    xr, wr = _round(x, enc_name).double(), _round(w, enc_name).double()
+    ref = bias.double().repeat(rows, 1)
+    for k in range(27):
+        idx = nbr[k].long()
+        ok = idx >= 0
+        ref[ok] += xr[idx[ok]] @ wr[k]
+    if residual:
+        ref += _round(res, enc_name).double()
+    if relu:
+        ref = torch.relu(ref)
+    live = rows if n_out is None else n_out
+    return out.float()[:live].cpu().numpy(), ref[:live].cpu().numpy(), out.float()[live:].cpu().numpy()
+
+
+@pytest.mark.parametrize('enc', ['f16', 'bf16'])
+@pytest.mark.parametrize('c', [16, 32])
+@pytest.mark.parametrize('pattern', ['random', 'banded', 'two_clusters', 'empty'])
+def test_sparse_conv_arbitrary_rulebooks(c, enc, pattern):
+    """The 16-bit sparse-conv kernels (tcgen05 gather-GEMM, warp-MMA 16 -> 16) on neighbour tables that are NOT rulebooks of
+    a real cloud: random tables, a banded SubM-like table, neighbours in two far-apart clusters, all-missing offset groups
+    and a whole table of -1, with a ragged device-side row count; rows beyond the count must stay untouched."""
+    rows, n_in = 1024, 6000
+    g = torch.Generator().manual_seed(5)
+    if pattern == 'random':
+        nbr = torch.randint(0, n_in, (27, rows), generator=g, dtype=torch.int32)
+        nbr[torch.rand(27, rows, generator=g) < 0.5] = -1
+    elif pattern == 'banded':
+        base = torch.arange(rows, dtype=torch.int32)[None, :] * 5
+        nbr = base + torch.randint(-150, 150, (27, rows), generator=g, dtype=torch.int32)
+        nbr = nbr.clamp_(0, n_in - 1)
+        nbr[torch.rand(27, rows, generator=g) < 0.4] = -1
+    elif pattern == 'two_clusters':
+        lowc = torch.randint(0, 200, (27, rows), generator=g, dtype=torch.int32)
+        highc = torch.randint(n_in - 200, n_in, (27, rows), generator=g, dtype=torch.int32)
+        nbr = torch.where(torch.rand(27, rows, generator=g) < 0.5, lowc, highc)
+        nbr[torch.rand(27, rows, generator=g) < 0.3] = -1
+        nbr[9:18, 128:256] = -1                                   # a whole (tile, dz) group without neighbours
+    else:
+        nbr = torch.full((27, rows), -1, dtype=torch.int32)
+    nbr = nbr.cuda().contiguous()
+    got, ref, tail = _conv_case(c, enc, rows, n_in, nbr, residual=(pattern != 'random'), relu=(pattern != 'banded'), n_out=1000 - 37)
+    tol = 3e-3 if enc == 'f16' else 1.5e-2        # 16-bit OUTPUT rounding of values up to ~4
+    assert rel_err(got, ref) < tol
+    assert (tail == 7.0).all()                    # rows beyond the device-side count are not written

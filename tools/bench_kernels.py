@@ -67,7 +67,23 @@ def bench_dwconv(iters, flush):
         x = buf.permute(0, 3, 1, 2)
 
 
-CASES = {'attention': bench_attention, 'dwconv': bench_dwconv}
+def bench_encoder(iters, flush):
+    """Sparse-conv launches of one eagerly launched nusc_L frame (path scope), one kernel at a time: bench.py's
+    kernel-family pass restricted to the encoder."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+    import bench
+    from srfdet_b200 import synth
+    from srfdet_b200.pipeline import RegionFeaturePipeline
+    pipe = RegionFeaturePipeline('nusc', fusion=False, precision=os.environ.get('SRF_PRECISION', 'fp16'), scope='path')
+    pts = torch.as_tensor(synth.cloud('nusc', 1000)).cuda()
+    fams, tot, layers = bench.kernel_families(pipe, pts, bench.peaks(), torch, reps=3)
+    for f in fams:
+        print(json.dumps({'case': f['family'], 'launches': f['launches'], 'us_per_launch': round(1e3 * f['ms'] / f['launches'], 2),
+                          'ms': f['ms'], 'bound': f['bound'], 'frac': f['frac']}), flush=True)
+    print(json.dumps({'case': 'encoder frame, serialised kernel time', 'ms': tot}))
+
+
+CASES = {'attention': bench_attention, 'dwconv': bench_dwconv, 'encoder': bench_encoder}
 
 if __name__ == '__main__':
     args = [a for a in sys.argv[1:] if not a.startswith('--')]
