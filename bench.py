@@ -45,6 +45,20 @@ SCOPES = {
 DTYPES = {'fp16': 'f16', 'bf16': 'bf16', 'fp32': 'f16x2 (hi+lo split operands on tcgen05, 3 MMAs per product, fp32 accumulate: FP32-mode tolerance 1e-4)',
           'fp32_simt': 'f32'}
 N_CLOUDS = 8
+
+
+def ncu_traffic():
+    """family -> {dram_read_bytes_per_launch, dram_write_bytes_per_launch, ...} from the committed ncu --set full capture
+    (profiles/r02_ncu_traffic.json, written by tools/ncu_summary.py traffic); {} when absent."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')) as f:
+            return json.load(f)['families']
+    except (OSError, ValueError, KeyError):
+        return {}
+
+
+TRAFFIC = ncu_traffic()
+IMG_ROI_TOUCHED_BYTES = (TRAFFIC.get('image RoIAlign (6 cameras)') or {}).get('dram_read_bytes_per_launch')
 METRIC = 'frames/s (voxelize+SparseEncoder+RoI fusion)'
 
 
@@ -146,7 +160,11 @@ def kernel_families(pipe, pts, pk, torch, reps=3):
             f, b, _ = next(it)
             return f, b
         n_vox = int(enc.last_counts[0])
-        ctx = dict(n_points=int(pts.shape[0]), c_points=int(pts.shape[1]), n_voxels=n_vox, conv_work=conv_work)
+        cnts = [int(c) for c in enc.last_counts]
+        shapes = getattr(enc, 'last_level_shapes', None) or []
+        ctx = dict(n_points=int(pts.shape[0]), c_points=int(pts.shape[1]), n_voxels=n_vox, conv_work=conv_work,
+                   level_counts={d: c for (d, _), c in zip(shapes, cnts)}, cap_counts={cap: c for (_, cap), c in zip(shapes, cnts)},
+                   img_roi_input_bytes=IMG_ROI_TOUCHED_BYTES)
         fams = profiling.families(cap, ctx, pk)
         tot = sum(f['ms'] for f in fams)
         if best is None or tot < best[0]:
@@ -329,15 +347,14 @@ def main():
             with open(args.kernels_out, 'w') as f:
                 json.dump(dict(workload=args.workload, scope=args.scope, precision=args.precision, kernel_ms_per_frame=kernel_ms,
                                families=kernels, sparse_conv_layers=sparse_layers, calls_in_order=kernel_families.per_call), f, indent=1)
-        dom = kernels[0]
+        # the dominant KERNEL: the largest family that is one kernel (one entry point) with algorithmic work attached
+        single = [k for k in kernels if len(k['entry_points']) == 1 and (k['bytes'] > 0 or k['flops'] > 0)]
+        dom = (single or kernels)[0]
         traffic, traffic_src = None, None
-        try:
-            with open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')) as f:
-                t = json.load(f)['families'].get(dom['family'])
-            if t:
-                traffic, traffic_src = t['dram_bytes_per_launch'], 'profiles/r02_ncu_traffic.json (ncu --set full, dram read+write per launch, cold cache)'
-        except (OSError, ValueError, KeyError):
-            pass
+        t = TRAFFIC.get(dom['family'])
+        if t:
+            traffic = t['dram_read_bytes_per_launch'] + t['dram_write_bytes_per_launch']
+            traffic_src = 'profiles/r02_ncu_traffic.json (ncu --set full, dram read+write per launch, cold cache)'
         n = dom['launches']
         roof = dict(bound=dom['bound'], kernel=f"{dom['family']} ({n} launches per frame; entry points {dom['entry_points']})",
                     achieved=dom['achieved'], peak=dom['peak'], unit=dom['unit'], frac=dom['frac'], traffic=traffic, traffic_source=traffic_src,

@@ -203,6 +203,11 @@ __global__ void index_mark_strided_kernel(uint32_t* __restrict__ bits, Dims4 od,
   }
 }
 
+// coordinates of the occupied cells in rank order.  A word's 32 cells are consecutive along x: the word's first cell is
+// decoded once (32-bit divisions when the grid has < 2^31 cells, which every config's has), each set bit then only steps
+// x and carries into y / z / b when it runs off the line (64-bit divisions per voxel made this kernel 15-30 us on the
+// coarse levels, whose words hold many voxels each).
+template <typename I>
 __global__ void index_emit_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ rank,
                                   int64_t nwords, Dims4 d, int4* __restrict__ out, int cap) {
   for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
@@ -210,15 +215,19 @@ __global__ void index_emit_kernel(const uint32_t* __restrict__ bits, const uint3
     uint32_t word = __ldg(bits + w);
     if (!word) continue;
     int r = (int)__ldg(rank + w);
+    I cell = (I)(w << 5);
+    const int x0 = (int)(cell % (I)d.x); cell /= (I)d.x;
+    const int y0 = (int)(cell % (I)d.y); cell /= (I)d.y;
+    const int z0 = (int)(cell % (I)d.z);
+    const int b0 = (int)(cell / (I)d.z);
     while (word) {
-      int b = __ffs(word) - 1;
+      const int b = __ffs(word) - 1;
       word &= word - 1;
-      int64_t cell = (w << 5) + b;
-      int4 q;
-      q.w = (int)(cell % d.x); cell /= d.x;
-      q.z = (int)(cell % d.y); cell /= d.y;
-      q.y = (int)(cell % d.z); cell /= d.z;
-      q.x = (int)cell;
+      int4 q = make_int4(b0, z0, y0, x0 + b);
+      while (q.w >= d.x) {
+        q.w -= d.x;
+        if (++q.z == d.y) { q.z = 0; if (++q.y == d.z) { q.y = 0; ++q.x; } }
+      }
       if (r < cap) out[r] = q;
       ++r;
     }
@@ -280,6 +289,68 @@ __global__ void __launch_bounds__(256) rulebook_kernel(const uint32_t* __restric
         }
       }
     }
+  }
+}
+
+// Unrolled form for the kernel shapes the encoders use ((3,3,3) and the (3,1,1) conv_out): the K2 cells of a (kz, ky) line
+// are consecutive along x, so they share one bitmap / rank word (two when the run crosses a word boundary): 9-12 word
+// loads per row instead of 27 probes; every probe of a row is resolved into registers before the first store (all loads
+// independent), 32-bit cell arithmetic (I) when the grid has < 2^31 cells, one tile-mask atomic per warp.
+template <int K0, int K1, int K2, typename I>
+__global__ void __launch_bounds__(256) rulebook_fast_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ rank, Dims4 id,
+                                                           const int32_t* __restrict__ in_perm, const int4* __restrict__ out_coors,
+                                                           int cap_out, const int32_t* __restrict__ d_n_out, Conv3 cv,
+                                                           int32_t* __restrict__ nbr, uint32_t* __restrict__ tile_mask) {
+  const int n_out = d_n_out ? min(*d_n_out, cap_out) : cap_out;
+  const int n_pad = min((n_out + 127) / 128 * 128, cap_out);
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n_pad; base += gridDim.x * blockDim.x) {
+    const int o = base + (threadIdx.x & 31);
+    const bool live = o < n_out;
+    const int4 q = live ? __ldg(out_coors + o) : make_int4(0, 0, 0, 0);
+    int rr[K0 * K1 * K2];
+    const int xs = q.w * cv.s[2] - cv.p[2];
+#pragma unroll
+    for (int kz = 0; kz < K0; ++kz) {
+      const int z = q.y * cv.s[0] - cv.p[0] + kz;
+#pragma unroll
+      for (int ky = 0; ky < K1; ++ky) {
+        const int y = q.z * cv.s[1] - cv.p[1] + ky;
+        const bool ok = live && z >= 0 && z < id.z && y >= 0 && y < id.y;
+        const I line = (((I)q.x * (I)id.z + (I)(ok ? z : 0)) * (I)id.y + (I)(ok ? y : 0)) * (I)id.x;
+        // words of the first and of the last in-range cell of the run
+        const int xa = max(xs, 0), xb = min(xs + K2 - 1, id.x - 1);
+        const bool any = ok && xa <= xb;
+        const I wa = (line + (I)(any ? xa : 0)) >> 5, wb = (line + (I)(any ? xb : 0)) >> 5;
+        const uint32_t ba = any ? __ldg(bits + wa) : 0u;
+        const uint32_t bb = (any && wb != wa) ? __ldg(bits + wb) : ba;
+        const uint32_t ra = ba ? __ldg(rank + wa) : 0u;
+        const uint32_t rb = (wb != wa && bb) ? __ldg(rank + wb) : ra;
+#pragma unroll
+        for (int kx = 0; kx < K2; ++kx) {
+          const int x = xs + kx;
+          int r = -1;
+          if (any && x >= 0 && x < id.x) {
+            const I cell = line + (I)x;
+            const bool first = (cell >> 5) == wa;
+            const uint32_t word = first ? ba : bb, bit = 1u << (uint32_t)(cell & 31);
+            if (word & bit) r = (int)((first ? ra : rb) + __popc(word & (bit - 1u)));
+          }
+          rr[(kz * K1 + ky) * K2 + kx] = r;
+        }
+      }
+    }
+    if (in_perm) {
+#pragma unroll
+      for (int kk = 0; kk < K0 * K1 * K2; ++kk)
+        if (rr[kk] >= 0) rr[kk] = __ldg(in_perm + rr[kk]);
+    }
+    uint32_t mask = 0u;
+#pragma unroll
+    for (int kk = 0; kk < K0 * K1 * K2; ++kk) {
+      nbr[(size_t)kk * cap_out + o] = rr[kk];              // o < n_pad: base is a multiple of 32 below n_pad (a multiple of 128)
+      if (__ballot_sync(0xffffffffu, rr[kk] >= 0)) mask |= 1u << kk;
+    }
+    if (mask && (threadIdx.x & 31) == 0) atomicOr(tile_mask + (base >> 7), mask);
   }
 }
 
@@ -381,8 +452,10 @@ int srf_index_emit_coors(const void* index, const int32_t dims[4], int32_t* coor
   SRF_CHECK_ARG(index && dims && coors_out && cap >= 0, "srf_index_emit_coors: bad args");
   IndexView v = index_view(index, ncells4(dims));
   SRF_COUNT(1);
-  index_emit_kernel<<<grid_for(v.nwords, 256), 256, 0, (cudaStream_t)stream>>>(
-      v.bits, v.rank, v.nwords, dims4(dims), (int4*)coors_out, cap);
+  if (ncells4(dims) < (1ll << 31))
+    index_emit_kernel<uint32_t><<<grid_for(v.nwords, 256), 256, 0, (cudaStream_t)stream>>>(v.bits, v.rank, v.nwords, dims4(dims), (int4*)coors_out, cap);
+  else
+    index_emit_kernel<int64_t><<<grid_for(v.nwords, 256), 256, 0, (cudaStream_t)stream>>>(v.bits, v.rank, v.nwords, dims4(dims), (int4*)coors_out, cap);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }
@@ -439,9 +512,17 @@ int srf_rulebook_build(const void* in_index, const int32_t in_dims[4], const int
   SRF_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)(cap_out / 128) * sizeof(uint32_t), st));
   IndexView v = index_view(in_index, ncells4(in_dims));
   SRF_COUNT(1);
-  rulebook_kernel<<<grid_for(cap_out, 256), 256, 0, st>>>(v.bits, v.rank, dims4(in_dims), in_perm,
-                                                         (const int4*)out_coors, cap_out, d_n_out, cv,
-                                                         nbr, tile_mask);
+  const bool small = ncells4(in_dims) < (1ll << 31);
+  const int grid = grid_for(cap_out, 256);
+#define SRF_RB(k0, k1, k2, I) rulebook_fast_kernel<k0, k1, k2, I><<<grid, 256, 0, st>>>(v.bits, v.rank, dims4(in_dims), in_perm, (const int4*)out_coors, cap_out, d_n_out, cv, nbr, tile_mask)
+  if (cv.k[0] == 3 && cv.k[1] == 3 && cv.k[2] == 3) {
+    if (small) SRF_RB(3, 3, 3, uint32_t); else SRF_RB(3, 3, 3, int64_t);
+  } else if (cv.k[0] == 3 && cv.k[1] == 1 && cv.k[2] == 1) {
+    if (small) SRF_RB(3, 1, 1, uint32_t); else SRF_RB(3, 1, 1, int64_t);
+  } else {
+    rulebook_kernel<<<grid, 256, 0, st>>>(v.bits, v.rank, dims4(in_dims), in_perm, (const int4*)out_coors, cap_out, d_n_out, cv, nbr, tile_mask);
+  }
+#undef SRF_RB
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }

@@ -298,22 +298,23 @@ class RegionFeaturePipeline:
         dense backbone, the neck and the DPG staircase the running statistics of its own input on one calibration
         frame -- what training would have produced -- so activations stay O(1) through the 12 + 6 conv layers
         instead of growing heavy tails (random statistics make the chained head ill-conditioned: max / std of the
-        FPN maps reaches 40).  Plain torch ops, run once, not part of any measured frame."""
+        FPN maps reaches 40).  Plain torch ops ON THE HOST (the encoder output is copied to the CPU: no third-party GPU
+        kernel runs anywhere in this package), run once, not part of any measured frame."""
         import torch.nn.functional as F
         assert self.scope == 'full'
         g = torch.Generator().manual_seed(12345)
 
         def fit(conv, bn, x, stride, pad, groups=1):
-            y = F.conv2d(x, conv.weight, None, stride=stride, padding=pad, groups=groups)
+            y = F.conv2d(x, conv.weight.detach().float().cpu(), None, stride=stride, padding=pad, groups=groups)
             bn.running_mean.copy_(y.mean((0, 2, 3)))
             bn.running_var.copy_(y.var((0, 2, 3), unbiased=False).clamp_min(1e-6))
-            bn.weight.copy_((torch.rand(bn.weight.shape, generator=g) * 0.5 + 0.75).to(y.device))
-            bn.bias.copy_((torch.randn(bn.bias.shape, generator=g) * 0.1).to(y.device))
-            return F.relu(F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps))
+            bn.weight.copy_(torch.rand(bn.weight.shape, generator=g) * 0.5 + 0.75)
+            bn.bias.copy_(torch.randn(bn.bias.shape, generator=g) * 0.1)
+            return F.relu(F.batch_norm(y, bn.running_mean.cpu(), bn.running_var.cpu(), bn.weight.cpu(), bn.bias.cpu(), False, 0.0, bn.eps))
         old_tf32 = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
         try:
-            x = self.detector.extract_point_features([points], precision='fp32').float().contiguous()
+            x = self.detector.extract_point_features([points], precision='fp32').float().cpu().contiguous()
             feats = []
             for block in self.backbone.blocks:
                 for j in range(0, len(block), 3):
@@ -336,7 +337,7 @@ class RegionFeaturePipeline:
                     xx = fit(cm.conv, cm.bn, inp, 2, 1, groups=inp.shape[1])
             staircase(self.head.dpg_dw_convs_lidar, outs)
             if self.fusion:
-                staircase(self.head.dpg_dw_convs_img, [f[0].contiguous() for f in self.img_feats])
+                staircase(self.head.dpg_dw_convs_img, [f[0].float().cpu().contiguous() for f in self.img_feats])
         finally:
             torch.backends.cudnn.allow_tf32 = old_tf32
         self._graphs = {}

@@ -375,6 +375,7 @@ class SparseEncoderCustom(nn.Module):
                                          out_bytes=4 if last else (2 if act_dtype in (L.BF16, L.F16) else 4)))
             x, x_dtype, lv = y, act_dtype, lv_out
         self.last_counts = [l.count for l in levels]
+        self.last_level_shapes = [(tuple(l.dims), l.cap) for l in levels]      # (dims, row capacity) per level (measurement only)
         if return_levels:
             return dense, levels
         return dense

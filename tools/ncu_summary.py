@@ -121,5 +121,42 @@ def full(raw, out, out_json=None):
     print(f'{out}: {len(agg)} kernel instantiations')
 
 
+FAMILY_OF = [          # kernel-name regex -> bench.py kernel family (only the unambiguous ones)
+    (r'img_roi_cl_kernel', 'image RoIAlign (6 cameras)'), (r'bev_roi_cl_kernel', 'BEV RoIAlign'),
+    (r'dynconv_interact', 'DynamicConv interaction'), (r'mha_attention', 'self-attention core'),
+    (r'igemm_umma_kernel<16, 32, 1', 'sparse conv 16->32'), (r'igemm_umma_kernel<32, 32, 1', 'sparse conv 32->32'),
+    (r'igemm_umma_kernel<32, 64, 1', 'sparse conv 32->64'), (r'igemm_umma_kernel<64, 64, 1', 'sparse conv 64->64'),
+    (r'igemm_umma_kernel<64, 128, 1', 'sparse conv 64->128'), (r'spconv16_warp_kernel', 'sparse conv 16->16'),
+    (r'rulebook_(fast_)?kernel', 'rulebook build'),
+]
+
+
+def traffic(out_json, *raws):
+    """profiles/r02_ncu_traffic.json: per-launch DRAM bytes of the kernel families bench.py reports, from ncu --set full captures."""
+    fam = OrderedDict()
+    for raw in raws:
+        rows = rows_of(raw)
+        hdr, units = rows[0], rows[1]
+        ki = hdr.index('Kernel Name')
+        cr, cw, ct = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
+        for r in rows[2:]:
+            name = next((f for pat, f in FAMILY_OF if re.search(pat, r[ki])), None)
+            if name is None or r[cr] == '':
+                continue
+            d = fam.setdefault(name, dict(launches=0, rd=0.0, wr=0.0, us=0.0, sources=set()))
+            d['launches'] += 1
+            d['rd'] += float(r[cr].replace(',', '')) * SCALE.get(units[cr], 1.0) * 1e6
+            d['wr'] += float(r[cw].replace(',', '')) * SCALE.get(units[cw], 1.0) * 1e6
+            d['us'] += float(r[ct].replace(',', '')) * SCALE.get(units[ct], 1.0)
+            d['sources'].add(raw)
+    js = {'source': 'ncu --set full --clock-control none captures of bench.py / tools/bench_kernels.py launches; per-launch means; '
+                    'ncu flushes caches before every replay, so reads are cold-cache',
+          'families': {k: dict(launches=d['launches'], dram_read_bytes_per_launch=int(d['rd'] / d['launches']),
+                               dram_write_bytes_per_launch=int(d['wr'] / d['launches']), ncu_duration_us=round(d['us'] / d['launches'], 2),
+                               raw=sorted(d['sources'])) for k, d in fam.items()}}
+    json.dump(js, open(out_json, 'w'), indent=1)
+    print(f'{out_json}: {len(fam)} families')
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](*sys.argv[2:])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
