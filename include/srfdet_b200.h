@@ -202,6 +202,16 @@ int srf_nchw_to_rows(const float* in, int32_t n, int32_t c, int32_t h, int32_t w
 int srf_upsample_add(void* rows_hi, const void* rows_lo, int32_t n, int32_t h, int32_t w, int32_t h_lo,
                      int32_t w_lo, int32_t c, int32_t enc, void* stream);
 
+/* Dense 3x3 / stride 1 / pad 1 convolution + folded BatchNorm2d (+ReLU) over NHWC pixel rows: the stride-1 ConvModules of
+ * SECONDCustom (mmdet3d_plugin/models/backbones/second_custom.py:23-91, cfg configs/nus/srfdet_voxel_nusc_L.py:55-66) and
+ * the FPN output convs (:67-75).  in: (n*h*w, cin) rows in SRF_F16 / SRF_BF16, cin a multiple of 128 (<= 512); w_packed:
+ * srf_pack_weight_tc(kvol = 9 in (ky, kx) order, cin, cout, enc) with BN folded; cout a multiple of 128; out (n*h*w, cout)
+ * rows in out_enc (SRF_F32 or a 16-bit form of the input's element format).  The 18 x 10 input halo of a 16 x 8 pixel tile
+ * is staged once in shared memory and the nine kernel offsets are nine tcgen05 descriptor offsets into it (csrc/conv3x3_halo.cu).
+ * Returns SRF_ERR_UNSUPPORTED for any other shape / encoding: callers then use srf_spconv_tc over srf_dense_rulebook. */
+int srf_conv3x3_rows(const void* in, int32_t enc, int32_t n, int32_t h, int32_t w, int32_t cin, const void* w_packed,
+                     int32_t cout, const float* bias, int32_t relu, void* out, int32_t out_enc, void* stream);
+
 /* ---------------------------------------------------------------------------------- *
  * Sparse convolution + folded BatchNorm1d + residual + ReLU (+ dense scatter).
  * Replaces spconv SubMConv3d/SparseConv3d forward, BN1d, ReLU, SparseBasicBlock residual

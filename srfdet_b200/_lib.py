@@ -137,6 +137,7 @@ PROTOTYPES = {
     'srf_upsample_add': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     'srf_rulebook_build': (c_int32, [c_void_p, POINTER(c_int32), c_void_p, c_void_p, c_int32, c_void_p,
                                      POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_void_p, c_void_p, c_void_p]),
+    'srf_conv3x3_rows': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
     'srf_spconv_f32': (c_int32, [POINTER(ConvArgs), c_void_p]),
     'srf_spconv_bf16': (c_int32, [POINTER(ConvArgs), c_void_p]),
     'srf_spconv_tc': (c_int32, [POINTER(ConvArgs), c_void_p]),

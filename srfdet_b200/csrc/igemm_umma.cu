@@ -115,11 +115,16 @@ __device__ int g_trace_n[64];
 #ifndef SRF_SPLIT_KC128
 #define SRF_SPLIT_KC128 64
 #endif
+// input channels per ring slot of PLAIN 16-bit operands with >= 128 input channels in the sparse form (A/B knob: 64 halves the
+// slot so that two CTAs fit per SM)
+#ifndef SRF_KC128
+#define SRF_KC128 128
+#endif
 
 template <int CIN, int COUT, bool SPARSE, bool SPLIT>
 struct Cfg {
   // input channels carried by one slot member; an offset takes KSPL consecutive slots
-  static constexpr int KC = !SPLIT ? (CIN > 128 ? 128 : CIN)
+  static constexpr int KC = !SPLIT ? ((SPARSE && CIN >= 128) ? SRF_KC128 : (CIN > 128 ? 128 : CIN))
                                    : (CIN == 64 ? (SPARSE ? SRF_SPLIT_KC64 : 64) : (CIN >= 128 ? SRF_SPLIT_KC128 : CIN));
   static constexpr int KSPL = CIN / KC;
   static constexpr int NJ = KC / 16;                     // MMA K-steps per member (x3 when split)
@@ -149,13 +154,15 @@ struct Cfg {
   static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES + 127) / 128 * 128;
   static constexpr bool BIG = SPARSE && ((CH <= 4 && SRF_IGEMM_BIG_NARROW) || (CH == 8 && SRF_IGEMM_BIG_64));   // one CTA per SM, deep ring
-  static constexpr int BUDGET = TRI ? 73 * 1024 : ((BIG || STAGE_BYTES * 3 + W_BYTES + IDX_BYTES > 100 * 1024) ? 222 * 1024 : 104 * 1024);
+  static constexpr int NEED3 = STAGE_BYTES * 3 + W_BYTES + IDX_BYTES;        // three ring slots
+  static constexpr bool TWO_WIDE = SPARSE && SRF_KC128 < 128 && NEED3 > 100 * 1024 && NEED3 <= 113 * 1024 - 512;   // knob: 2 CTAs/SM x 3 slots for 128-wide tiles
+  static constexpr int BUDGET = TRI ? 73 * 1024 : (TWO_WIDE ? NEED3 + 256 : ((BIG || NEED3 > 100 * 1024) ? 222 * 1024 : 104 * 1024));
   static constexpr int STAGES_RAW = (BUDGET - W_BYTES - IDX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > SRF_IGEMM_MAXSTAGES ? SRF_IGEMM_MAXSTAGES : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + (SPARSE ? 0 : 3 * 128 * 4);   // + the dense epilogue's staged bias | ln_w | ln_b
   static constexpr int SMEM_BYTES = W_BYTES + IDX_BYTES + STAGES * STAGE_BYTES + BAR_BYTES + 128;
-  static constexpr int MINB = (TRI && COUT <= 64) ? 3 : ((SMEM_BYTES <= 110 * 1024 && COUT <= 64) ? 2 : 1);
+  static constexpr int MINB = (TRI && COUT <= 64) ? 3 : (((SMEM_BYTES <= 110 * 1024 && COUT <= 64) || TWO_WIDE) ? 2 : 1);
   // kind::f16: D fp32 (bit 4), A/B format at bits 7 / 10 (0 = f16, 1 = bf16: set at run time), K-major both, N>>3 @17, M>>4 @24
   static constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((128u >> 4) << 24);
 };
@@ -710,7 +717,7 @@ int srf_spconv_bf16(const srf_conv_args* c, void* stream) { return srf_spconv_tc
 
 // K chunk per ring slot of the sparse kernel (the packer lays the weights out per chunk)
 int srf_pack_weight_kc(int32_t cin, int32_t enc) {
-  if (!enc_is_split(enc)) return cin;
+  if (!enc_is_split(enc)) return cin >= 128 ? SRF_KC128 : cin;
   return cin == 64 ? SRF_SPLIT_KC64 : (cin >= 128 ? SRF_SPLIT_KC128 : cin);
 }
 // output-channel tile of the sparse kernel: layers wider than 128 outputs run as cout / 128 column tiles

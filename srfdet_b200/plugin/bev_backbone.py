@@ -13,6 +13,7 @@ outputs are written fp32 NHWC, i.e. exactly the `torch.channels_last` tensors th
 the DPG kernels read in place.
 """
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -22,6 +23,9 @@ from . import registry
 from .head import _cached, _f, encode_rows
 from .registry import BACKBONES, NECKS
 from .voxel_encoder import fold_bn
+
+
+HALO_CONV = os.environ.get('SRF_HALO_CONV', '1') != '0'      # A/B switch: '0' sends every dense conv through the gather-GEMM kernel
 
 
 def _tc_enc(precision):
@@ -67,8 +71,15 @@ def conv_bn_act_rows(x_rows, n, h, w, conv, bn, enc, cache, key, relu=True, out_
         L.check(lib.srf_pack_weight_tc(L.ptr(kio), ks * ks, cin, cout, enc, L.ptr(wp), L.stream_ptr()), 'srf_pack_weight_tc')
         return wp, bf.to(dev).contiguous()
     wp, bias = _cached(cache, (key, enc), src, pack)
-    nbr, mask, ho, wo, cap = _Grid.get(n, h, w, ks, stride, pad, dev)
     out_enc = enc if out_enc is None else out_enc
+    if HALO_CONV and ks == 3 and stride == 1 and pad == 1 and not L.enc_is_split(enc) and cin % 128 == 0 and cin <= 512 and cout % 128 == 0:
+        # stride-1 3x3 layers with >= 128 channels: halo-tile kernel, no rulebook (csrc/conv3x3_halo.cu)
+        cap = (n * h * w + 127) // 128 * 128
+        y = torch.empty((cap, L.enc_width(out_enc, cout)), dtype=L.enc_torch_dtype(out_enc), device=dev)
+        L.check(lib.srf_conv3x3_rows(L.ptr(x_rows), enc, n, h, w, cin, L.ptr(wp), cout, L.ptr(bias), int(relu), L.ptr(y), out_enc,
+                                     L.stream_ptr()), 'srf_conv3x3_rows')
+        return y, h, w
+    nbr, mask, ho, wo, cap = _Grid.get(n, h, w, ks, stride, pad, dev)
     y = torch.empty((cap, L.enc_width(out_enc, cout)), dtype=L.enc_torch_dtype(out_enc), device=dev)
     a = L.ConvArgs()
     a.in_, a.in_dtype, a.in_rows = L.ptr(x_rows), enc, x_rows.shape[0]

@@ -94,6 +94,8 @@ def _family(name, a, s):
         if s['kvol'] == 9:
             return f"dense conv3x3 {s['cin']}->{s['cout']}"
         return f"sparse conv {s['cin']}->{s['cout']}" + (' (first layer, FFMA)' if name == 'srf_spconv_f32' else '')
+    if name == 'srf_conv3x3_rows':
+        return f'dense conv3x3 {a[5]}->{a[7]}'
     if name == 'srf_bev_roi_features':
         return 'BEV RoIAlign'
     if name == 'srf_img_roi_features':
@@ -132,6 +134,9 @@ def _work(name, a, s, ctx):
         return 0.0, 3 * (n_pts * c_pts * 4 + n_pts * 4 + ctx['n_voxels'] * c_pts * 4) + n_pts * (c_pts + 35) * 4
     if name in ('srf_spconv_tc', 'srf_spconv_f32', 'srf_spconv_bf16'):
         return None            # filled from the rulebooks (sparse) / the grid (dense) by the caller
+    if name == 'srf_conv3x3_rows':
+        rows, cin, cout = a[2] * a[3] * a[4], a[5], a[7]
+        return 2.0 * rows * 9 * cin * cout, rows * cin * ES[a[1]] + rows * cout * ES[a[11]] + 9 * cin * cout * ES[a[1]]
     if name == 'srf_bev_roi_features':
         c = s['channels']
         k = a[2] * a[3]

@@ -74,12 +74,19 @@ def bench_encoder(iters, flush):
     import bench
     from srfdet_b200 import synth
     from srfdet_b200.pipeline import RegionFeaturePipeline
-    pipe = RegionFeaturePipeline('nusc', fusion=False, precision=os.environ.get('SRF_PRECISION', 'fp16'), scope='path')
+    scope = os.environ.get('SRF_BENCH_SCOPE', 'path')          # 'full' adds the dense backbone / neck / head kernels
+    pipe = RegionFeaturePipeline('nusc', fusion=False, precision=os.environ.get('SRF_PRECISION', 'fp16'), scope=scope)
     pts = torch.as_tensor(synth.cloud('nusc', 1000)).cuda()
+    if scope == 'full':
+        pipe.calibrate(torch.as_tensor(synth.cloud('nusc', 999)).cuda())
     fams, tot, layers = bench.kernel_families(pipe, pts, bench.peaks(), torch, reps=3)
     for f in fams:
         print(json.dumps({'case': f['family'], 'launches': f['launches'], 'us_per_launch': round(1e3 * f['ms'] / f['launches'], 2),
                           'ms': f['ms'], 'bound': f['bound'], 'frac': f['frac']}), flush=True)
+    if os.environ.get('SRF_BENCH_CALLS'):
+        for ms, name, fam in bench.kernel_families.per_call:
+            if os.environ['SRF_BENCH_CALLS'] in fam or os.environ['SRF_BENCH_CALLS'] in name:
+                print(json.dumps({'call': name, 'family': fam, 'us': round(ms * 1e3, 2)}))
     print(json.dumps({'case': 'encoder frame, serialised kernel time', 'ms': tot}))
 
 
