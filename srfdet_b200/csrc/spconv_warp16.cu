@@ -43,7 +43,8 @@ struct Warp16Args {
 template <bool F16>
 __global__ void __launch_bounds__(128) spconv16_warp_kernel(Warp16Args a) {
   __shared__ uint32_t sW[27 * 128];
-  for (int e = threadIdx.x; e < a.kvol * 128; e += blockDim.x) sW[e] = __ldg(a.w + e);
+  // offsets >= kvol multiply all-zero A fragments: their weights must be finite (0 x NaN = NaN)
+  for (int e = threadIdx.x; e < 27 * 128; e += blockDim.x) sW[e] = e < a.kvol * 128 ? __ldg(a.w + e) : 0u;
   __syncthreads();
   const int n_out = a.d_n_out ? min(*a.d_n_out, a.cap_out) : a.cap_out;
   const int lane = threadIdx.x & 31;

@@ -61,11 +61,16 @@ def conv_bn_act_rows(x_rows, n, h, w, conv, bn, enc, cache, key, relu=True, out_
     dev = x_rows.device
     ks, stride, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
     cin, cout = conv.in_channels, conv.out_channels
-    assert conv.kernel_size[0] == conv.kernel_size[1] and conv.groups == 1 and conv.bias is None
-    src = [conv.weight] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+    assert conv.kernel_size[0] == conv.kernel_size[1] and conv.groups == 1 and (conv.bias is None or bn is None)
+    src = [conv.weight] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else []) + (
+        [conv.bias] if conv.bias is not None else [])
 
     def pack():
-        wf, bf = fold_bn(conv.weight, bn) if bn is not None else (conv.weight.detach().float(), torch.zeros(cout))
+        if bn is not None:
+            wf, bf = fold_bn(conv.weight, bn)
+        else:                                   # plain Conv2d (+ its own bias): SRFDetHead.img_convs
+            wf = conv.weight.detach().float()
+            bf = conv.bias.detach().float() if conv.bias is not None else torch.zeros(cout)
         kio = wf.to(dev).permute(2, 3, 1, 0).reshape(ks * ks, cin, cout).contiguous()       # (cout,cin,ky,kx) -> (ky*ks+kx, cin, cout)
         wp = torch.empty(L.enc_width(enc, kio.numel()), dtype=L.enc_torch_dtype(enc), device=dev)
         L.check(lib.srf_pack_weight_tc(L.ptr(kio), ks * ks, cin, cout, enc, L.ptr(wp), L.stream_ptr()), 'srf_pack_weight_tc')

@@ -73,3 +73,31 @@ def test_halo_conv_equals_gather_path():
         bb.HALO_CONV = old
     for u, v in zip(a, b):
         assert rel_err(u.cpu().numpy(), v.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize('precision,tol', [('fp16', 2e-3), ('fp32', 2e-4)])
+def test_img_convs_vs_torch(precision, tol):
+    """SRFDetHead.img_convs (srfdet_head.py:146-157, :404-416: Conv2d(256 -> 128, 3x3, pad 1, bias) per image FPN level over all
+    cameras) on the library's dense conv kernels vs torch conv2d in float64; ragged map sizes; the per-frame memo is
+    shared by dpg_image_logits() / forward() and follows in-place weight updates."""
+    from srfdet_b200.pipeline import head_cfg
+    from srfdet_b200.plugin import registry
+    torch.manual_seed(7)
+    head = registry.build_head(head_cfg('nusc', True)).cuda().eval()
+    assert head.feat_channels_img == 256 and head.hidden_dim == 128 and len(head.img_convs) == 4
+    sizes = [(29, 50), (15, 25), (8, 13), (4, 7)]
+    feats = [torch.randn(1, 3, 256, h, w, device='cuda') for h, w in sizes]
+    with torch.no_grad():
+        maps = head._image_maps(feats, precision)
+        again = head._image_maps(feats, precision)
+    assert all(a is b for a, b in zip(maps, again))                    # one evaluation per set of input maps
+    for i, (m, f) in enumerate(zip(maps, feats)):
+        assert m.shape == (1, 3, 128, *sizes[i])
+        assert m[0].is_contiguous(memory_format=torch.channels_last)   # what the samplers / DPG kernels read in place
+        cv = head.img_convs[i]
+        ref = torch.nn.functional.conv2d(f[0].double(), cv.weight.double(), cv.bias.double(), padding=1)
+        assert rel_err(m[0].cpu().numpy(), ref.cpu().numpy()) < tol
+    with torch.no_grad():
+        head.img_convs[0].bias.add_(1.0)
+        new = head._image_maps(feats, precision)
+    assert rel_err((new[0] - maps[0]).cpu().numpy(), torch.ones_like(maps[0]).cpu().numpy()) < 1e-3
