@@ -10,28 +10,44 @@
 
 namespace srf {
 
-// tile transpose through shared memory: coalesced reads along w, coalesced writes along c
+// tile transpose through shared memory: 64 channels x 32 pixels per CTA; coalesced 128-byte reads along w, and 128-byte
+// writes along c (a lane packs two adjacent channels into one 32-bit store)
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ in, int c, int hw, int enc, uint16_t* __restrict__ out) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   const int img = blockIdx.z;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
   const float* src = in + (size_t)img * c * hw;
-  for (int j = ty; j < 32; j += 8) {
+#pragma unroll
+  for (int j = ty; j < 64; j += 8) {
     const int ch = c0 + j, p = p0 + tx;
     tile[j][tx] = (ch < c && p < hw) ? __ldg(src + (size_t)ch * hw + p) : 0.f;
   }
   __syncthreads();
   const bool f16 = enc_is_f16(enc), split = enc_is_split(enc);
   const int width = split ? 2 * c : c;
+  const int ch = c0 + 2 * tx;
+#pragma unroll
   for (int j = ty; j < 32; j += 8) {
-    const int p = p0 + j, ch = c0 + tx;
+    const int p = p0 + j;
     if (p >= hw || ch >= c) continue;
-    const float v = tile[tx][j];
+    const float v0 = tile[2 * tx][j], v1 = tile[2 * tx + 1][j];
     uint16_t* row = out + ((size_t)img * hw + p) * width;
-    const uint16_t h = pack16(f16, v);
-    row[ch] = h;
-    if (split) row[c + ch] = pack16(f16, v - unpack16(f16, h));
+    if (ch + 1 < c && (c & 1) == 0) {
+      uint32_t h, l;
+      split16x2(f16, v0, v1, h, l);
+      *reinterpret_cast<uint32_t*>(row + ch) = h;
+      if (split) *reinterpret_cast<uint32_t*>(row + c + ch) = l;
+    } else {
+      const uint16_t h0 = pack16(f16, v0);
+      row[ch] = h0;
+      if (split) row[c + ch] = pack16(f16, v0 - unpack16(f16, h0));
+      if (ch + 1 < c) {
+        const uint16_t h1 = pack16(f16, v1);
+        row[ch + 1] = h1;
+        if (split) row[c + ch + 1] = pack16(f16, v1 - unpack16(f16, h1));
+      }
+    }
   }
 }
 
@@ -73,7 +89,7 @@ extern "C" {
 
 int srf_nchw_to_rows(const float* in, int32_t n, int32_t c, int32_t h, int32_t w, int32_t enc, void* out, void* stream) {
   SRF_CHECK_ARG(in && out && n >= 1 && c >= 1 && h >= 1 && w >= 1 && enc_is_16(enc), "srf_nchw_to_rows: bad args");
-  dim3 grid(cdiv((int64_t)h * w, 32), cdiv(c, 32), n);
+  dim3 grid(cdiv((int64_t)h * w, 32), cdiv(c, 64), n);
   SRF_COUNT(1);
   nchw_to_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, c, h * w, enc, (uint16_t*)out);
   SRF_LAUNCH_CHECK();

@@ -173,30 +173,39 @@ struct Conv3 {
   int32_t k[3], s[3], p[3];
 };
 
+// POW2: every stride is a power of two (every reference config: 1 or 2) -> the divisibility test and the division of the
+// 27 candidate offsets are a mask and a shift (runtime divisors made this kernel instruction bound: 18-24 us per level),
+// and the grid has < 2^31 cells -> 32-bit cell arithmetic.
+template <bool POW2>
 __global__ void index_mark_strided_kernel(uint32_t* __restrict__ bits, Dims4 od,
                                           const int4* __restrict__ in_coors, int cap_in,
-                                          const int32_t* __restrict__ d_n_in, Conv3 cv) {
+                                          const int32_t* __restrict__ d_n_in, Conv3 cv, int sh0, int sh1, int sh2) {
   int nn = d_n_in ? min(*d_n_in, cap_in) : cap_in;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += gridDim.x * blockDim.x) {
     int4 q = __ldg(in_coors + i);
     if (q.x < 0 || q.y < 0) continue;
     for (int kz = 0; kz < cv.k[0]; ++kz) {
       int nz = q.y + cv.p[0] - kz;
-      if (nz < 0 || nz % cv.s[0]) continue;
-      int z = nz / cv.s[0];
+      if (nz < 0 || (POW2 ? (nz & (cv.s[0] - 1)) : (nz % cv.s[0]))) continue;
+      int z = POW2 ? (nz >> sh0) : nz / cv.s[0];
       if (z >= od.z) continue;
       for (int ky = 0; ky < cv.k[1]; ++ky) {
         int ny = q.z + cv.p[1] - ky;
-        if (ny < 0 || ny % cv.s[1]) continue;
-        int y = ny / cv.s[1];
+        if (ny < 0 || (POW2 ? (ny & (cv.s[1] - 1)) : (ny % cv.s[1]))) continue;
+        int y = POW2 ? (ny >> sh1) : ny / cv.s[1];
         if (y >= od.y) continue;
         for (int kx = 0; kx < cv.k[2]; ++kx) {
           int nx = q.w + cv.p[2] - kx;
-          if (nx < 0 || nx % cv.s[2]) continue;
-          int x = nx / cv.s[2];
+          if (nx < 0 || (POW2 ? (nx & (cv.s[2] - 1)) : (nx % cv.s[2]))) continue;
+          int x = POW2 ? (nx >> sh2) : nx / cv.s[2];
           if (x >= od.x) continue;
-          int64_t cell = cell_of(od, q.x, z, y, x);
-          atomicOr(bits + (cell >> 5), 1u << (cell & 31));
+          if (POW2) {
+            const uint32_t cell = (((uint32_t)q.x * (uint32_t)od.z + (uint32_t)z) * (uint32_t)od.y + (uint32_t)y) * (uint32_t)od.x + (uint32_t)x;
+            atomicOr(bits + (cell >> 5), 1u << (cell & 31));
+          } else {
+            int64_t cell = cell_of(od, q.x, z, y, x);
+            atomicOr(bits + (cell >> 5), 1u << (cell & 31));
+          }
         }
       }
     }
@@ -435,8 +444,19 @@ int srf_index_mark_strided(void* out_index, const int32_t out_dims[4], const int
   if (cap_in == 0) return SRF_OK;
   IndexView v = index_view(out_index, ncells4(out_dims));
   SRF_COUNT(1);
-  index_mark_strided_kernel<<<grid_for(cap_in, 256), 256, 0, (cudaStream_t)stream>>>(
-      v.bits, dims4(out_dims), (const int4*)in_coors, cap_in, d_n_in, cv);
+  int sh[3];
+  bool pow2 = ncells4(out_dims) < (1ll << 31);
+  for (int j = 0; j < 3; ++j) {
+    sh[j] = 0;
+    while ((1 << sh[j]) < cv.s[j]) ++sh[j];
+    pow2 = pow2 && (1 << sh[j]) == cv.s[j];
+  }
+  if (pow2)
+    index_mark_strided_kernel<true><<<grid_for(cap_in, 256), 256, 0, (cudaStream_t)stream>>>(
+        v.bits, dims4(out_dims), (const int4*)in_coors, cap_in, d_n_in, cv, sh[0], sh[1], sh[2]);
+  else
+    index_mark_strided_kernel<false><<<grid_for(cap_in, 256), 256, 0, (cudaStream_t)stream>>>(
+        v.bits, dims4(out_dims), (const int4*)in_coors, cap_in, d_n_in, cv, sh[0], sh[1], sh[2]);
   SRF_LAUNCH_CHECK();
   return SRF_OK;
 }

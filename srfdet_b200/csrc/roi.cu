@@ -273,8 +273,11 @@ __device__ __forceinline__ RoiGeom roi_geom(const Pyr& p, float x1, float y1, fl
 
 // bilinear taps of ONE sample point (bin, iy, ix): 4 (offset, weight) pairs, weights already
 // divided by the 4 samples of a bin.  Staged in shared memory once per (proposal, camera) so
-// the channel loops only do  LDS + LDG.128 + 4 FFMA  per tap.
-__device__ __forceinline__ void sample_taps(int smp, const RoiGeom& g, int* off, float* wt) {
+// the channel loops only do  LDS + LDG.128 + 4 FFMA  per tap.  Offsets are BYTE offsets of the
+// pixel's channel vector inside one image of the level (pixel * px_bytes, < 2^32: make_pyr), so
+// a tap's address is one 32-bit-offset add (the 64-bit  pixel * C  product per tap was a third
+// of the sampler's instructions).
+__device__ __forceinline__ void sample_taps(int smp, const RoiGeom& g, uint32_t px_bytes, uint32_t* off, float* wt) {
   const int bin = smp >> 2, iy = (smp >> 1) & 1, ix = smp & 1;
   const int ph = bin / POOL, pw = bin - ph * POOL;
   const float y = g.y1s + ph * g.bh + (iy + .5f) * g.bh / 2.f;
@@ -290,15 +293,15 @@ __device__ __forceinline__ void sample_taps(int smp, const RoiGeom& g, int* off,
   if (yl >= H - 1) { yh = yl = H - 1; yy = (float)yl; } else yh = yl + 1;
   if (xl >= W - 1) { xh = xl = W - 1; xx = (float)xl; } else xh = xl + 1;
   const float ly = yy - yl, lx = xx - xl, hy = 1.f - ly, hx = 1.f - lx;
-  off[0] = yl * W + xl; wt[0] = hy * hx * 0.25f;
-  off[1] = yl * W + xh; wt[1] = hy * lx * 0.25f;
-  off[2] = yh * W + xl; wt[2] = ly * hx * 0.25f;
-  off[3] = yh * W + xh; wt[3] = ly * lx * 0.25f;
+  off[0] = (uint32_t)(yl * W + xl) * px_bytes; wt[0] = hy * hx * 0.25f;
+  off[1] = (uint32_t)(yl * W + xh) * px_bytes; wt[1] = hy * lx * 0.25f;
+  off[2] = (uint32_t)(yh * W + xl) * px_bytes; wt[2] = ly * hx * 0.25f;
+  off[3] = (uint32_t)(yh * W + xh) * px_bytes; wt[3] = ly * lx * 0.25f;
 }
 
 // resident CTAs per SM the compiler must leave room for / taps per batch of independent loads (A/B knobs)
 #ifndef SRF_ROI_MINB
-#define SRF_ROI_MINB 2
+#define SRF_ROI_MINB 3
 #endif
 #ifndef SRF_ROI_TB
 #define SRF_ROI_TB 16
@@ -309,12 +312,21 @@ constexpr int NTAP = NBIN * 16;   // taps per RoI: 49 bins x 4 samples x 4 corne
 // accumulate one bin from staged taps into acc[NP] (float4 = 4 channels per lane per pass)
 // The taps of a bin are loaded in batches of TB independent 16-byte loads per lane before any
 // FMA consumes them (a load -> FMA -> load chain kept one request in flight per warp and left the
-// kernel latency bound); weights of exactly 0 (out-of-range samples) are not loaded, as before.
-// The accumulation order is unchanged (tap 0..15).
+// kernel latency bound).  The inner loop is predicate-free: an out-of-range sample is staged as
+// (offset 0, weight 0) -- its tap reads pixel 0 of the image and contributes 0 * v exactly --
+// and lanes past the last channel read channel 0 (their accumulators are never stored).  A tap
+// then costs  64-bit add + LDG.128 + 4 FFMA  (7 instructions; the earlier form with a 64-bit
+// pixel * C product and per-tap zero-weight predicates ran at 20).  Accumulation order: tap 0..15.
 template <int NP>
-__device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_base, const int* __restrict__ s_off,
+__device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_base, const uint32_t* __restrict__ s_off,
                                                   const float* __restrict__ s_wt, int bin, int C, int lane, float4* acc) {
   constexpr int TB = NP == 1 ? SRF_ROI_TB : 8;
+  const char* lane_base[NP];
+#pragma unroll
+  for (int pss = 0; pss < NP; ++pss) {
+    const int c = (pss * 32 + lane) * 4;
+    lane_base[pss] = reinterpret_cast<const char*>(img_base) + (c < C ? c * 4 : 0);
+  }
 #pragma unroll
   for (int q0 = 0; q0 < 16; q0 += TB) {
     float w[TB];
@@ -322,23 +334,18 @@ __device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_
 #pragma unroll
     for (int q = 0; q < TB; ++q) {
       w[q] = s_wt[bin * 16 + q0 + q];
-      const float4* src = reinterpret_cast<const float4*>(img_base + (size_t)s_off[bin * 16 + q0 + q] * C) + lane;
+      const uint32_t off = s_off[bin * 16 + q0 + q];
 #pragma unroll
-      for (int pss = 0; pss < NP; ++pss) {
-        v[q][pss] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w[q] != 0.f && (pss * 32 + lane) * 4 < C) v[q][pss] = __ldg(src + pss * 32);
-      }
+      for (int pss = 0; pss < NP; ++pss) v[q][pss] = __ldg(reinterpret_cast<const float4*>(lane_base[pss] + off));
     }
 #pragma unroll
     for (int q = 0; q < TB; ++q) {
 #pragma unroll
       for (int pss = 0; pss < NP; ++pss) {
-        if (w[q] != 0.f) {
-          acc[pss].x = fmaf(w[q], v[q][pss].x, acc[pss].x);
-          acc[pss].y = fmaf(w[q], v[q][pss].y, acc[pss].y);
-          acc[pss].z = fmaf(w[q], v[q][pss].z, acc[pss].z);
-          acc[pss].w = fmaf(w[q], v[q][pss].w, acc[pss].w);
-        }
+        acc[pss].x = fmaf(w[q], v[q][pss].x, acc[pss].x);
+        acc[pss].y = fmaf(w[q], v[q][pss].y, acc[pss].y);
+        acc[pss].z = fmaf(w[q], v[q][pss].z, acc[pss].z);
+        acc[pss].w = fmaf(w[q], v[q][pss].w, acc[pss].w);
       }
     }
   }
@@ -373,7 +380,7 @@ template <int NP>
 __global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) bev_roi_cl_kernel(Pyr p, float* __restrict__ boxes, const float* __restrict__ rois_in,
                                                         int n_prop, int box_dim, Range rg, int mutate, OutSpec out,
                                                         float* __restrict__ rois_out) {
-  __shared__ int s_off[NTAP];
+  __shared__ uint32_t s_off[NTAP];
   __shared__ float s_wt[NTAP];
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) bev_roi_cl_ke
     }
   }
   const RoiGeom g = roi_geom(p, x1, y1, x2, y2);
-  if (threadIdx.x < NBIN * 4) sample_taps(threadIdx.x, g, s_off + threadIdx.x * 4, s_wt + threadIdx.x * 4);
+  if (threadIdx.x < NBIN * 4) sample_taps(threadIdx.x, g, (uint32_t)p.channels * 4u, s_off + threadIdx.x * 4, s_wt + threadIdx.x * 4);
   __syncthreads();
   const float* base = p.feat[g.lvl] + (size_t)img * g.H * g.W * p.channels;
   for (int bin = warp; bin < NBIN; bin += 8) {
@@ -424,9 +431,10 @@ __global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) img_roi_cl_ke
                                                         const float* __restrict__ lidar2img, int n_cam, Range rg,
                                                         OutSpec out, float* __restrict__ rois_out) {
   extern __shared__ __align__(16) uint8_t sm_img[];
-  int* s_off = reinterpret_cast<int*>(sm_img);                 // [n_cam][NTAP]
+  uint32_t* s_off = reinterpret_cast<uint32_t*>(sm_img);       // [n_cam][NTAP]
   float* s_wt = reinterpret_cast<float*>(s_off + n_cam * NTAP);
   __shared__ RoiGeom sg[IMG_MAX_CAM];
+  __shared__ const float* s_base[IMG_MAX_CAM];     // camera image of the RoI's level (resolved once: p.feat[] is indexed dynamically)
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < n_cam) {
@@ -451,12 +459,14 @@ __global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) img_roi_cl_ke
       float* r = rois_out + ((size_t)cam * n_prop + k) * 5;
       r[0] = (float)cam; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
     }
-    sg[cam] = roi_geom(p, x1, y1, x2, y2);
+    const RoiGeom g = roi_geom(p, x1, y1, x2, y2);
+    sg[cam] = g;
+    s_base[cam] = p.feat[g.lvl] + (size_t)cam * g.H * g.W * p.channels;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < n_cam * NBIN * 4; e += blockDim.x) {
     const int cam = e / (NBIN * 4), smp = e - cam * (NBIN * 4);
-    if (sg[cam].live) sample_taps(smp, sg[cam], s_off + cam * NTAP + smp * 4, s_wt + cam * NTAP + smp * 4);
+    if (sg[cam].live) sample_taps(smp, sg[cam], (uint32_t)p.channels * 4u, s_off + cam * NTAP + smp * 4, s_wt + cam * NTAP + smp * 4);
   }
   __syncthreads();
   for (int bin = warp; bin < NBIN; bin += 8) {
@@ -465,8 +475,7 @@ __global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) img_roi_cl_ke
     for (int q = 0; q < NP; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int cam = 0; cam < n_cam; ++cam) {
       if (!sg[cam].live) continue;
-      const float* base = p.feat[sg[cam].lvl] + (size_t)cam * sg[cam].H * sg[cam].W * p.channels;
-      bin_accumulate_cl<NP>(base, s_off + cam * NTAP, s_wt + cam * NTAP, bin, p.channels, lane, acc);
+      bin_accumulate_cl<NP>(s_base[cam], s_off + cam * NTAP, s_wt + cam * NTAP, bin, p.channels, lane, acc);
     }
     store_bin_cl<NP>(out, k, bin, p.channels, lane, acc);
   }
@@ -486,6 +495,9 @@ static int make_pyr(Pyr* d, const srf_pyramid* p) {
   d->channels = p->channels;
   d->channels_last = p->channels_last;
   if (p->channels_last && (p->channels % 4 != 0 || p->channels > 256)) return -1;
+  if (p->channels_last)      // the samplers address a pixel by a 32-bit byte offset inside one image of a level
+    for (int l = 0; l < p->n_levels; ++l)
+      if ((unsigned long long)p->h[l] * p->w[l] * p->channels * 4ull >= (1ull << 32)) return -1;
   return 0;
 }
 

@@ -95,7 +95,7 @@ def test_img_convs_vs_torch(precision, tol):
         assert m.shape == (1, 3, 128, *sizes[i])
         assert m[0].is_contiguous(memory_format=torch.channels_last)   # what the samplers / DPG kernels read in place
         cv = head.img_convs[i]
-        ref = torch.nn.functional.conv2d(f[0].double(), cv.weight.double(), cv.bias.double(), padding=1)
+        ref = torch.nn.functional.conv2d(f[0].double(), cv.weight.detach().double(), cv.bias.detach().double(), padding=1)
         assert rel_err(m[0].cpu().numpy(), ref.cpu().numpy()) < tol
     with torch.no_grad():
         head.img_convs[0].bias.add_(1.0)
