@@ -88,6 +88,11 @@ __device__ int g_trace_n[64];
 #ifndef SRF_IGEMM_BIG_64
 #define SRF_IGEMM_BIG_64 0
 #endif
+// largest weight set (KB) kept resident in shared memory for rows of <= 4 chunks (A/B knob: 0 = always stream W_k per slot,
+// which frees the space for a deeper ring)
+#ifndef SRF_IGEMM_WRES_KB
+#define SRF_IGEMM_WRES_KB 56
+#endif
 // resident CTAs per SM aimed at for rows of <= 4 chunks (2 or 3; 3 = 74 KB of smem and <= 72 registers per thread)
 #ifndef SRF_IGEMM_CTAS_NARROW
 #define SRF_IGEMM_CTAS_NARROW 2
@@ -148,7 +153,7 @@ struct Cfg {
   static constexpr int B_LBO = COUT * 16;
   static constexpr int B_MEMBER = CH * B_LBO;            // [hi planes | lo planes] of KC x COUT
   // tiny weight sets stay resident in shared memory; otherwise W_k arrives by bulk copy
-  static constexpr bool WRES = SPARSE && KSPL == 1 && (27 * B_MEMBER <= (TRI ? 16 : (CH <= 4 ? (SPLIT ? 28 : 56) : 16)) * 1024);
+  static constexpr bool WRES = SPARSE && KSPL == 1 && (27 * B_MEMBER <= (TRI ? 16 : (CH <= 4 ? (SPLIT ? 28 : SRF_IGEMM_WRES_KB) : 16)) * 1024);
   static constexpr int W_BYTES = WRES ? (27 * B_MEMBER + 127) / 128 * 128 : 0;
   static constexpr int B_BYTES = WRES ? 0 : G * B_MEMBER;
   static constexpr int IDX_BYTES = SPARSE ? 27 * 128 * 4 : 0;   // neighbour indices of the current tile
