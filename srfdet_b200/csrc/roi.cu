@@ -327,13 +327,22 @@ __device__ __forceinline__ void bin_accumulate_cl(const float* __restrict__ img_
     const int c = (pss * 32 + lane) * 4;
     lane_base[pss] = reinterpret_cast<const char*>(img_base) + (c < C ? c * 4 : 0);
   }
+  // a bin whose 4 samples all fall outside the map (12 % of the bins of live cameras on the bench frame: boxes cut by the
+  // image border) has 16 zero weights: nothing to add.  Weights are >= 0, so their sum tests them all; the branch is warp-uniform.
+  float wall[16];
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(wall + q) = *reinterpret_cast<const float4*>(s_wt + bin * 16 + q);
+  float wsum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) wsum += wall[q];
+  if (wsum == 0.f) return;
 #pragma unroll
   for (int q0 = 0; q0 < 16; q0 += TB) {
     float w[TB];
     float4 v[TB][NP];
 #pragma unroll
     for (int q = 0; q < TB; ++q) {
-      w[q] = s_wt[bin * 16 + q0 + q];
+      w[q] = wall[q0 + q];
       const uint32_t off = s_off[bin * 16 + q0 + q];
 #pragma unroll
       for (int pss = 0; pss < NP; ++pss) v[q][pss] = __ldg(reinterpret_cast<const float4*>(lane_base[pss] + off));
@@ -380,38 +389,47 @@ template <int NP>
 __global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) bev_roi_cl_kernel(Pyr p, float* __restrict__ boxes, const float* __restrict__ rois_in,
                                                         int n_prop, int box_dim, Range rg, int mutate, OutSpec out,
                                                         float* __restrict__ rois_out) {
-  __shared__ uint32_t s_off[NTAP];
-  __shared__ float s_wt[NTAP];
+  __shared__ __align__(16) uint32_t s_off[NTAP];
+  __shared__ __align__(16) float s_wt[NTAP];
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float x1, y1, x2, y2;
-  int img;
-  if (rois_in) {   // generic SingleRoIExtractor form
-    const float* r = rois_in + (size_t)k * 5;
-    img = (int)r[0]; x1 = r[1]; y1 = r[2]; x2 = r[3]; y2 = r[4];
-  } else {
-    float* b = boxes + (size_t)k * box_dim;
-    float bx[8];
+  // box -> corners -> BEV rectangle -> level geometry on warp 0 only (atan2f / sinf / cosf / expf and eight rotated corners:
+  // done by all 8 warps it was a fifth of the kernel's issued instructions); the other warps pick the result up from shared memory
+  __shared__ RoiGeom s_g;
+  __shared__ int s_img;
+  if (warp == 0) {
+    float x1, y1, x2, y2;
+    int img;
+    if (rois_in) {   // generic SingleRoIExtractor form
+      const float* r = rois_in + (size_t)k * 5;
+      img = (int)r[0]; x1 = r[1]; y1 = r[2]; x2 = r[3]; y2 = r[4];
+    } else {
+      float* b = boxes + (size_t)k * box_dim;
+      float bx[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) bx[j] = b[j];
-    __syncthreads();
-    const float cx = bx[0] * rg.span[0] + rg.lo[0], cy = bx[1] * rg.span[1] + rg.lo[1], cz = bx[2] * rg.span[2] + rg.lo[2];
-    if (mutate && threadIdx.x == 0) { b[0] = cx; b[1] = cy; b[2] = cz; }
-    float cor[8][3];
-    box_corners(cx, cy, cz, bx[3], bx[4], bx[5], bx[6], bx[7], cor);
-    x1 = INFINITY; y1 = INFINITY; x2 = -INFINITY; y2 = -INFINITY;
+      for (int j = 0; j < 8; ++j) bx[j] = b[j];
+      __syncwarp();   // every lane has read the (still normalised) box before lane 0 overwrites the centre
+      const float cx = bx[0] * rg.span[0] + rg.lo[0], cy = bx[1] * rg.span[1] + rg.lo[1], cz = bx[2] * rg.span[2] + rg.lo[2];
+      if (mutate && lane == 0) { b[0] = cx; b[1] = cy; b[2] = cz; }
+      float cor[8][3];
+      box_corners(cx, cy, cz, bx[3], bx[4], bx[5], bx[6], bx[7], cor);
+      x1 = INFINITY; y1 = INFINITY; x2 = -INFINITY; y2 = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float x = (cor[i][0] - rg.lo[0]) / rg.vs[0], y = (cor[i][1] - rg.lo[1]) / rg.vs[1];
-      x1 = fminf(x1, x); x2 = fmaxf(x2, x); y1 = fminf(y1, y); y2 = fmaxf(y2, y);
+      for (int i = 0; i < 8; ++i) {
+        float x = (cor[i][0] - rg.lo[0]) / rg.vs[0], y = (cor[i][1] - rg.lo[1]) / rg.vs[1];
+        x1 = fminf(x1, x); x2 = fmaxf(x2, x); y1 = fminf(y1, y); y2 = fmaxf(y2, y);
+      }
+      img = k / n_prop;
+      if (rois_out && lane == 0) {
+        float* r = rois_out + (size_t)k * 5;
+        r[0] = (float)img; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
+      }
     }
-    img = k / n_prop;
-    if (rois_out && threadIdx.x == 0) {
-      float* r = rois_out + (size_t)k * 5;
-      r[0] = (float)img; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
-    }
+    if (lane == 0) { s_g = roi_geom(p, x1, y1, x2, y2); s_img = img; }
   }
-  const RoiGeom g = roi_geom(p, x1, y1, x2, y2);
+  __syncthreads();
+  const RoiGeom g = s_g;
+  const int img = s_img;
   if (threadIdx.x < NBIN * 4) sample_taps(threadIdx.x, g, (uint32_t)p.channels * 4u, s_off + threadIdx.x * 4, s_wt + threadIdx.x * 4);
   __syncthreads();
   const float* base = p.feat[g.lvl] + (size_t)img * g.H * g.W * p.channels;
@@ -437,46 +455,55 @@ __global__ void __launch_bounds__(256, NP == 1 ? SRF_ROI_MINB : 1) img_roi_cl_ke
   __shared__ const float* s_base[IMG_MAX_CAM];     // camera image of the RoI's level (resolved once: p.feat[] is indexed dynamically)
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < n_cam) {
-    const int cam = threadIdx.x;
-    const float* b = boxes + (size_t)k * box_dim;
-    const float cx = b[0] * rg.span[0] + rg.lo[0], cy = b[1] * rg.span[1] + rg.lo[1], cz = b[2] * rg.span[2] + rg.lo[2];
-    float cor[8][3];
-    box_corners(cx, cy, cz, b[3], b[4], b[5], b[6], b[7], cor);
-    const float* L = lidar2img + (size_t)cam * 16;
-    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
+  // warp 0: lane = camera projects the box, resolves its level geometry, and the live cameras of this proposal are compacted
+  // (1.2 of 6 on the bench frame): the tap staging and the bin loops only see those
+  __shared__ int s_live[IMG_MAX_CAM];
+  __shared__ int s_nlive;
+  if (warp == 0) {
+    bool live = false;
+    if (lane < n_cam) {
+      const int cam = lane;
+      const float* b = boxes + (size_t)k * box_dim;
+      const float cx = b[0] * rg.span[0] + rg.lo[0], cy = b[1] * rg.span[1] + rg.lo[1], cz = b[2] * rg.span[2] + rg.lo[2];
+      float cor[8][3];
+      box_corners(cx, cy, cz, b[3], b[4], b[5], b[6], b[7], cor);
+      const float* L = lidar2img + (size_t)cam * 16;
+      float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float X = cor[i][0], Y = cor[i][1], Z = cor[i][2];
-      float u = __ldg(L + 0) * X + __ldg(L + 1) * Y + __ldg(L + 2) * Z + __ldg(L + 3);
-      float v = __ldg(L + 4) * X + __ldg(L + 5) * Y + __ldg(L + 6) * Z + __ldg(L + 7);
-      float d = __ldg(L + 8) * X + __ldg(L + 9) * Y + __ldg(L + 10) * Z + __ldg(L + 11);
-      d = fmaxf(d, 1e-5f);
-      u = u / d; v = v / d;
-      x1 = fminf(x1, u); x2 = fmaxf(x2, u); y1 = fminf(y1, v); y2 = fmaxf(y2, v);
+      for (int i = 0; i < 8; ++i) {
+        float X = cor[i][0], Y = cor[i][1], Z = cor[i][2];
+        float u = __ldg(L + 0) * X + __ldg(L + 1) * Y + __ldg(L + 2) * Z + __ldg(L + 3);
+        float v = __ldg(L + 4) * X + __ldg(L + 5) * Y + __ldg(L + 6) * Z + __ldg(L + 7);
+        float d = __ldg(L + 8) * X + __ldg(L + 9) * Y + __ldg(L + 10) * Z + __ldg(L + 11);
+        d = fmaxf(d, 1e-5f);
+        u = u / d; v = v / d;
+        x1 = fminf(x1, u); x2 = fmaxf(x2, u); y1 = fminf(y1, v); y2 = fmaxf(y2, v);
+      }
+      if (rois_out) {
+        float* r = rois_out + ((size_t)cam * n_prop + k) * 5;
+        r[0] = (float)cam; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
+      }
+      const RoiGeom g = roi_geom(p, x1, y1, x2, y2);
+      sg[cam] = g;
+      s_base[cam] = p.feat[g.lvl] + (size_t)cam * g.H * g.W * p.channels;
+      live = g.live != 0;
     }
-    if (rois_out) {
-      float* r = rois_out + ((size_t)cam * n_prop + k) * 5;
-      r[0] = (float)cam; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
-    }
-    const RoiGeom g = roi_geom(p, x1, y1, x2, y2);
-    sg[cam] = g;
-    s_base[cam] = p.feat[g.lvl] + (size_t)cam * g.H * g.W * p.channels;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (live) s_live[__popc(m & ((1u << lane) - 1u))] = lane;
+    if (lane == 0) s_nlive = __popc(m);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < n_cam * NBIN * 4; e += blockDim.x) {
-    const int cam = e / (NBIN * 4), smp = e - cam * (NBIN * 4);
-    if (sg[cam].live) sample_taps(smp, sg[cam], (uint32_t)p.channels * 4u, s_off + cam * NTAP + smp * 4, s_wt + cam * NTAP + smp * 4);
-  }
+  const int n_live = s_nlive;
+  for (int li = 0; li < n_live; ++li)
+    if (threadIdx.x < NBIN * 4)
+      sample_taps(threadIdx.x, sg[s_live[li]], (uint32_t)p.channels * 4u, s_off + li * NTAP + threadIdx.x * 4, s_wt + li * NTAP + threadIdx.x * 4);
   __syncthreads();
   for (int bin = warp; bin < NBIN; bin += 8) {
     float4 acc[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int cam = 0; cam < n_cam; ++cam) {
-      if (!sg[cam].live) continue;
-      bin_accumulate_cl<NP>(s_base[cam], s_off + cam * NTAP, s_wt + cam * NTAP, bin, p.channels, lane, acc);
-    }
+    for (int li = 0; li < n_live; ++li)
+      bin_accumulate_cl<NP>(s_base[s_live[li]], s_off + li * NTAP, s_wt + li * NTAP, bin, p.channels, lane, acc);
     store_bin_cl<NP>(out, k, bin, p.channels, lane, acc);
   }
 }
