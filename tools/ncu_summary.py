@@ -2,6 +2,8 @@
 
     python tools/ncu_summary.py launches RAW.csv OUT.csv     # --metrics gpu__time_duration.sum launch list
     python tools/ncu_summary.py full RAW.csv OUT.csv [OUT.json]   # --set full --page raw --csv capture
+    python tools/ncu_summary.py merge OUT_RAW.csv BASE_RAW.csv UPDATE_RAW.csv REGEX   # re-captured kernels replace their rows
+    python tools/ncu_summary.py traffic OUT.json RAW.csv [RAW.csv ...]             # per-family DRAM bytes per launch
 
 `launches`: one line per kernel (launch count, total / mean / min duration, share of the serialised kernel time).
 `full`: one line per kernel instantiation (mean over its launches) with the metrics DESIGN.md / bench.py quote:
@@ -158,5 +160,20 @@ def traffic(out_json, *raws):
     print(f'{out_json}: {len(fam)} families')
 
 
+def merge(out, base, update, pattern):
+    """Replace the rows of `base` whose kernel name matches `pattern` by the rows of `update` (a later capture of the kernels that
+    changed), matching columns by metric NAME (two ncu runs can differ by a column)."""
+    a, b = rows_of(base), rows_of(update)
+    ha, hb = a[0], b[0]
+    ib = {n: i for i, n in enumerate(hb)}
+    ki = ha.index('Kernel Name')
+    pat = re.compile(pattern)
+    rows = [ha, a[1]] + [r for r in a[2:] if not pat.search(r[ki])]
+    rows += [[r[ib[n]] if n in ib else '' for n in ha] for r in b[2:]]
+    with open(out, 'w', newline='') as f:
+        csv.writer(f, quoting=csv.QUOTE_ALL).writerows(rows)
+    print(f'{out}: {len(rows) - 2} launches')
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
+    {'launches': launches, 'full': full, 'traffic': traffic, 'merge': merge}[sys.argv[1]](*sys.argv[2:])
