@@ -211,6 +211,10 @@ int srf_upsample_add(void* rows_hi, const void* rows_lo, int32_t n, int32_t h, i
  * Returns SRF_ERR_UNSUPPORTED for any other shape / encoding: callers then use srf_spconv_tc over srf_dense_rulebook. */
 int srf_conv3x3_rows(const void* in, int32_t enc, int32_t n, int32_t h, int32_t w, int32_t cin, const void* w_packed,
                      int32_t cout, const float* bias, int32_t relu, void* out, int32_t out_enc, void* stream);
+/* 1 when the last srf_conv3x3_rows launch staged its halos with TMA tensor copies (cp.async.bulk.tensor.5d, out-of-image
+ * pixels zero-filled by the copy engine), 0 when it used the cp.async gather producers (tensor-map encoder unavailable or
+ * SRF_HALO_TMA=0), -1 before the first launch. */
+int srf_conv3x3_last_used_tma(void);
 
 /* ---------------------------------------------------------------------------------- *
  * Sparse convolution + folded BatchNorm1d + residual + ReLU (+ dense scatter).

@@ -107,6 +107,7 @@ PROTOTYPES = {
     'srf_version': (c_int32, []),
     'srf_last_error': (c_char_p, []),
     'srf_sm_count': (c_int32, []),
+    'srf_conv3x3_last_used_tma': (c_int32, []),
     'srf_launch_count': (ctypes.c_uint64, []),
     'srf_geom_init': (c_int32, [POINTER(Geom), POINTER(c_float), POINTER(c_float)]),
     'srf_dynamic_voxelize': (c_int32, [c_void_p, c_int32, c_int32, POINTER(Geom), c_int32, c_void_p, c_void_p]),

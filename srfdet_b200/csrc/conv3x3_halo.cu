@@ -20,6 +20,7 @@
 // MMAs through two TMEM buffers), 4-7 halo producers (cp.async, hardware arrive on the slot's mbarrier), 8 weight
 // producer (one lane, cp.async.bulk of the packed 128 x 128 tile of (offset, K half)), 9 MMA issuer.
 // Operands f16 / bf16 (run-time descriptor field), fp32 accumulate; weights in the packing of srf_pack_weight_tc.
+#include <cuda.h>   // CUtensorMap + cuTensorMapEncodeTiled prototype (types only: the entry point is fetched through cudart, no libcuda link)
 #include "igemm_common.cuh"
 
 namespace srf {
@@ -44,12 +45,22 @@ constexpr int HC_THREADS = 448;                      // 4 + 4 epilogue warps (0-
 constexpr int HC_SMEM = HC_NA * HC_A_BYTES + HC_NW * HC_W_BYTES + (2 * HC_NA + 2 * HC_NW + 4) * 8 + 16 + 2 * 128 * 4 + 128;   // + bias of two tiles in flight
 
 struct HaloArgs {
+  alignas(64) CUtensorMap tmap;   // 5-D view of the input rows: (c % 8, x, y, c / 8, image); box = one K-chunk plane of a halo
   IgemmArgs e;          // epilogue fields (bias, relu, out, out_enc, out_stride, out_lo_off, fmt)
   int n, h, w, cin;     // image batch / size, input channels (multiple of 128)
   int n_tiles;          // cout / 128
+  int use_tma;          // halo planes by TMA tensor copies (OOB zero-fill = the conv's zero padding); 0: cp.async gathers
 };
 
-__global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const HaloArgs p) {
+constexpr int HC_PLANE_TMA = HC_HY * HC_HX * 16;   // the tensor copy writes the 16 planes of a stage densely (2880-byte planes)
+
+// the 16 K-chunk planes (128 channels) of an 18 x 10 halo in one tensor copy: [16][18][10][16 B], zero-filled outside the image
+__device__ __forceinline__ void tma_halo(uint32_t dst, const CUtensorMap* tm, int x, int y, int plane, int img, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(x), "r"(y), "r"(plane), "r"(img), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const __grid_constant__ HaloArgs p) {
   extern __shared__ __align__(128) uint8_t hc_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)hc_smem_raw + 127) & ~(uintptr_t)127);
   const uint32_t a0 = smem_u32(smem), w0 = a0 + HC_NA * HC_A_BYTES;
@@ -69,7 +80,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const HaloA
   if (threadIdx.x == 0) HTRACE(1);
   pdl_trigger();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < HC_NA; ++s) { mbar_init(afull(s), 128); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < HC_NA; ++s) { mbar_init(afull(s), p.use_tma ? 1 : 128); mbar_init(aempty(s), 1); }
     for (int s = 0; s < HC_NW; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -157,6 +168,26 @@ __global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const HaloA
   } else if (warp < 8) {
     // ------------------------------------------------------------------ halo producers
     const int pt = threadIdx.x - 128;
+    if (p.use_tma) {
+      // TMA form: one thread issues ONE tensor copy per stage (box 8 ch x 10 px x 18 rows x 16 planes at (x0 - 1, y0 - 1));
+      // the copy engine zero-fills what lies outside the image, which is the convolution's padding.
+      if (pt == 0) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+          int nt, img, y0, x0;
+          decode(tile, nt, img, y0, x0);
+          for (int q = 0; q < kq; ++q, ++it) {
+            const int s = it % HC_NA;
+            mbar_wait(aempty(s), (((uint32_t)(it / HC_NA)) & 1u) ^ 1u);
+            HTRACE(20);
+            const uint32_t fb = afull(s);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)((HC_KC / 8) * HC_HY * HC_HX * 16)) : "memory");
+            tma_halo(a0 + (uint32_t)s * HC_A_BYTES, &p.tmap, x0 - 1, y0 - 1, q * (HC_KC / 8), img, fb);
+            HTRACE(21);
+          }
+        }
+      }
+    } else {
     const int c = pt & 15;                          // K-chunk plane of this thread (consecutive lanes: one pixel's 256 contiguous bytes)
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -181,6 +212,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const HaloA
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
@@ -204,6 +236,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const HaloA
     // kind::f16, D fp32, A/B format from a.fmt, K-major both, N = 128, M = 128
     const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24) | (a.fmt ? 0u : ((1u << 7) | (1u << 10)));
     constexpr uint32_t A_HI = ((HC_HX * 16u) >> 4) | (1u << 14);      // SBO = one halo row
+    const uint32_t plane = p.use_tma ? (uint32_t)HC_PLANE_TMA : (uint32_t)HC_PLANE;   // LBO: bytes between K-chunk planes
     int ia = 0, iw = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
@@ -224,12 +257,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const HaloA
           if (lane == 0) HTRACE(41);
           tc_fence_after();
           const int dy = k / 3, dx = k - dy * 3;
-          const uint32_t a_lo0 = (((abase + (uint32_t)(dy * HC_HX + dx) * 16u) >> 4) & 0x3fffu) | ((uint32_t)(HC_PLANE >> 4) << 16);
+          const uint32_t a_lo0 = (((abase + (uint32_t)(dy * HC_HX + dx) * 16u) >> 4) & 0x3fffu) | ((plane >> 4) << 16);
           const uint32_t b_lo0 = (((w0 + (uint32_t)sw * HC_W_BYTES) >> 4) & 0x3fffu) | ((uint32_t)((128 * 16) >> 4) << 16);
           if (elect_one_sync()) {
 #pragma unroll
             for (int j = 0; j < HC_KC / 16; ++j) {
-              const uint64_t ad = desc_pack(a_lo0 + (uint32_t)(j * ((2 * HC_PLANE) >> 4)), A_HI);
+              const uint64_t ad = desc_pack(a_lo0 + (uint32_t)j * ((2u * plane) >> 4), A_HI);
               const uint64_t bd = desc_pack(b_lo0 + (uint32_t)(j * ((2 * 128 * 16) >> 4)), DESC_HI);
               tc_mma_f16(tmem_d, ad, bd, idesc, accumulate);
               accumulate = 1;
@@ -255,6 +288,41 @@ __global__ void __launch_bounds__(HC_THREADS, 1) conv3x3_halo_kernel(const HaloA
 }  // namespace srf
 
 using namespace srf;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (the library links only cudart)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = getenv("SRF_HALO_TMA");
+    if (!(e && e[0] == '0')) {
+      void* ptr = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        fn = (encode_tiled_fn)ptr;
+      (void)cudaGetLastError();
+    }
+  }
+  return fn;
+}
+
+// (n, h, w, cin) 16-bit NHWC rows as the 5-D tensor (c % 8, x, y, c / 8, image); a box is one K-chunk plane of an 18 x 10 halo
+static bool make_halo_tmap(CUtensorMap* tm, const void* in, int n, int h, int w, int cin) {
+  encode_tiled_fn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[5] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(cin / 8), (cuuint64_t)n};
+  const cuuint64_t strides[4] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, 16, (cuuint64_t)h * w * cin * 2};   // bytes, dims 1..4
+  const cuuint32_t box[5] = {8, (cuuint32_t)HC_HX, (cuuint32_t)HC_HY, (cuuint32_t)(HC_KC / 8), 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_last_tma = -1;
+extern "C" int srf_conv3x3_last_used_tma(void) { return g_last_tma; }
 
 extern "C" int srf_conv3x3_rows(const void* in, int32_t enc, int32_t n, int32_t h, int32_t w, int32_t cin, const void* w_packed,
                                 int32_t cout, const float* bias, int32_t relu, void* out, int32_t out_enc, void* stream) {
@@ -283,6 +351,8 @@ extern "C" int srf_conv3x3_rows(const void* in, int32_t enc, int32_t n, int32_t 
   p.e.out_lo_off = cout;
   p.n = n; p.h = h; p.w = w; p.cin = cin;
   p.n_tiles = cout / 128;
+  p.use_tma = make_halo_tmap(&p.tmap, in, n, h, w, cin) ? 1 : 0;
+  g_last_tma = p.use_tma;
   const int tiles = n * cdiv(h, HC_TY) * cdiv(w, HC_TX) * p.n_tiles;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;

@@ -44,7 +44,7 @@ def capture():
         fn = getattr(lib, name)
         originals[name] = fn
         if name.endswith(('_bytes', '_splits', '_splits_enc', '_tile_k', '_tile_n', '_tile_k_enc')) or name in (
-                'srf_version', 'srf_last_error', 'srf_sm_count', 'srf_launch_count', 'srf_geom_init'):
+                'srf_version', 'srf_last_error', 'srf_sm_count', 'srf_launch_count', 'srf_geom_init', 'srf_conv3x3_last_used_tma'):
             continue
 
         def wrapped(*args, _fn=fn, _name=name):

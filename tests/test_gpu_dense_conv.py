@@ -53,6 +53,30 @@ def test_conv3x3_halo_vs_torch(n, h, w, cin, cout, out_f32, relu, enc):
     assert (tail == 3.0).all()                # padding rows of the output buffer are not written
 
 
+def test_halo_conv_tma_and_cp_async_producers_agree():
+    """The halo is staged by TMA tensor copies (cp.async.bulk.tensor.5d, zero padding = the copy engine's out-of-bounds fill) on
+    a B200 box; the cp.async gather producers remain as the fall-back.  Both feed the same MMAs: identical results."""
+    import os
+    import subprocess
+    import sys
+    from srfdet_b200 import _lib as L
+    got, ref, _ = _run(2, 37, 29, 256, 128, 'f16', True, True, seed=3)
+    assert L.load().srf_conv3x3_last_used_tma() == 1, 'tensor-map encoder unavailable: the TMA producer did not run'
+    code = ('import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n'
+            'import test_gpu_dense_conv as t; from srfdet_b200 import _lib as L\n'
+            'got, ref, _ = t._run(2, 37, 29, 256, 128, "f16", True, True, seed=3)\n'
+            'assert L.load().srf_conv3x3_last_used_tma() == 0\n'
+            'np.save(sys.argv[1], got)\n') % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tempfile
+    import numpy as np
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, 'cp.npy')
+        subprocess.run([sys.executable, '-c', code, out], check=True, env=dict(os.environ, SRF_HALO_TMA='0'), timeout=300)
+        other = np.load(out)
+    assert np.array_equal(got, other)
+    assert rel_err(got, ref) < 2e-3
+
+
 def test_halo_conv_equals_gather_path():
     """SECONDCustom through the halo kernel == through the gather-GEMM kernel over the dense rulebook (fp16 mode):
     same operands, same fp32 accumulation, only the summation order inside the tensor core differs."""

@@ -50,7 +50,7 @@ def main():
     for name in L.PROTOTYPES:
         fn = getattr(lib, name)
         originals[name] = fn
-        if name.endswith(skip) or name in ('srf_version', 'srf_last_error', 'srf_sm_count', 'srf_launch_count', 'srf_geom_init'):
+        if name.endswith(skip) or name in ('srf_version', 'srf_last_error', 'srf_sm_count', 'srf_launch_count', 'srf_geom_init', 'srf_conv3x3_last_used_tma'):
             continue
 
         def wrapped(*a, _fn=fn, _name=name):
