@@ -11,7 +11,7 @@ for w in waymo_L kitti_L; do python bench.py --workload $w --steps 10 --warmup 3
 B="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --frames-in-flight 1 --profiler-range"
 $B > gpurun_out/plain_graph.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
   --log-file gpurun_out/r02_launches_raw.csv $B > gpurun_out/ncu_launches.log 2>&1
-ONLY='srf_img_roi|srf_bev_roi|srf_spconv_f32|srf_nchw_to_rows|srf_layernorm|srf_index_mark_strided'
+ONLY=${ONLY:-'srf_img_roi|srf_bev_roi|srf_spconv_f32|srf_nchw_to_rows|srf_layernorm|srf_index_mark_strided|srf_conv3x3_rows'}
 python tools/ncu_frame.py --only "$ONLY" > gpurun_out/plain_frame2.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on \
   --profile-from-start off -f -o gpurun_out/r02_frame2 python tools/ncu_frame.py --only "$ONLY" > gpurun_out/ncu_frame2.log 2>&1
 ncu -i gpurun_out/r02_frame2.ncu-rep --page raw --csv > gpurun_out/r02_ncu_frame2_raw.csv
