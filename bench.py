@@ -384,10 +384,10 @@ def main():
                 p2.use_graph = True
                 _, cd, cp = (clouds_np, clouds_dev, clouds_pin) if WORKLOADS[w_]['kind'] == kind else clouds_for(WORKLOADS[w_]['kind'])
                 st = max(10, args.steps // 2)
-                m1 = timed(p2, cd, st, 3, 1, host=False)
-                m2 = timed(p2, cp, st, 3, 1, host=True)
-                modes[tag] = dict(workload=w_, scope=s_, precision=p_, value=round(st / (m1 * 1e-3), 2), e2e=round(st / (m2 * 1e-3), 2),
-                                  ms_per_step=round(m1 / st, 4), steps=st)
+                m1 = timed(p2, cd, st, 3, fif, host=False)        # same frames in flight as the headline
+                m2 = timed(p2, cp, st, 3, fif, host=True)
+                modes[tag] = dict(workload=w_, scope=s_, precision=p_, frames_in_flight=fif, value=round(st * fif / (m1 * 1e-3), 2),
+                                  e2e=round(st * fif / (m2 * 1e-3), 2), ms_per_step=round(m1 / st, 4), steps=st)
                 del p2
                 torch.cuda.empty_cache()
             # ---- frames in flight on one GPU (BASELINE config 5)
