@@ -314,8 +314,12 @@ __device__ __forceinline__ void load8_split(const void* base, int enc, size_t ro
   }
 }
 
+// resident CTAs per SM aimed at by the 16-bit form for C <= 128 (A/B knob; 900 proposals over 148 SMs: 3 -> three rounds, 4 -> two)
+#ifndef SRF_DC_MINB
+#define SRF_DC_MINB 4
+#endif
 template <int C, int D, bool F16, bool SPLIT>
-__global__ void __launch_bounds__(256, C <= 128 ? (SPLIT ? 2 : 3) : 1) dynconv_interact_mma_kernel(const DcMmaArgs a) {
+__global__ void __launch_bounds__(256, C <= 128 ? (SPLIT ? 2 : SRF_DC_MINB) : 1) dynconv_interact_mma_kernel(const DcMmaArgs a) {
   constexpr int LDF = C + 8, LDP1 = D + 8, LDP2 = C + 8, LDT = D + 8;   // 16-bit pitches (odd multiples of 16 B)
   constexpr int NP = SPLIT ? 2 : 1;                                      // hi (+ lo) copies of every operand
   constexpr int SZF = 64 * LDF, SZP1 = C * LDP1, SZP2 = D * LDP2, SZT = 64 * LDT;
