@@ -119,6 +119,24 @@ def test_mha_attention_tensor_core_vs_torch(c, heads, n_p, bs, enc_name):
     assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < (3e-3 if enc_name == 'F16' else 2e-2)
 
 
+@pytest.mark.parametrize('c,heads,n_p,bs', [(128, 8, 900, 1), (256, 8, 300, 2), (128, 8, 65, 3), (32, 2, 7, 1)])
+@pytest.mark.parametrize('enc_name,tol', [('F16X2', 2e-5), ('BF16X2', 2e-4)])
+def test_mha_attention_split_tensor_core_vs_torch(c, heads, n_p, bs, enc_name, tol):
+    """fp32 mode: the same mma.sync kernel with hi + lo operands (three MMAs per product, rows written [hi | lo]) against
+    torch's fp32 attention core on hot inputs: f16 pairs sit at the fp32 FFMA kernel's 2e-5, bf16 pairs at 2e-4."""
+    from srfdet_b200 import _lib as L
+    torch.manual_seed(1)
+    enc = getattr(L, enc_name)
+    x = torch.randn(bs * n_p, 3 * c, device='cuda') * 1.5
+    hd = c // heads
+    q, k, v = [t.view(bs, n_p, heads, hd).transpose(1, 2) for t in x.split(c, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q.double(), k.double(), v.double()).transpose(1, 2).reshape(bs * n_p, c)
+    att = torch.zeros((bs * n_p, L.enc_width(enc, c)), dtype=L.enc_torch_dtype(enc), device='cuda')
+    L.check(L.load().srf_mha_attention(L.ptr(x), bs, n_p, heads, hd, L.ptr(att), enc, L.stream_ptr()), 'attn')
+    got = L.decode(att, c)
+    assert rel_err(got.cpu().numpy(), ref.float().cpu().numpy()) < tol
+
+
 @pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('fp32_simt', 2e-4), ('fp16', 1e-2)])
 def test_stage_tail_kernels_vs_torch(precision, tol):
     """Production dims (900 proposals, C 128, d 32, ff 512, 8 heads): the kernel path of a whole stage
